@@ -1,0 +1,310 @@
+// Layer epilogue and graph readout kernels (sm_100a).
+//
+// dgn_norm_forward / backward fuse rb/nets/dgn_layer.py:122-130
+//     h = h * snorm_n ; h = BatchNorm1d(h) ; h = relu(h) ; h = h_in + h
+// into two launches per direction: a column-statistics pass (Welford partials per row slab,
+// merged in a fixed order - no atomics, so results are reproducible) and an apply pass.  The
+// problem is a tall-skinny [N, C<=~300] matrix: threads map to columns (coalesced 128 B per
+// warp row) and row slabs map to blocks.
+//
+// dgn_readout_* replace dgl.{sum,mean,max}_nodes: node rows of one graph are contiguous in the
+// batched graph, so a readout is a segmented column reduction.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/dgn_b200.h"
+
+namespace dgn {
+
+constexpr int kParts = 64;     // row slabs (fixed so that the workspace size only depends on C)
+constexpr int kTX = 32, kTY = 8;
+
+__device__ __forceinline__ int rows_of(const DgnNormArgs& a) { return a.n_rows_dev ? *a.n_rows_dev : a.n_rows; }
+
+__device__ __forceinline__ void slab(int n, int part, int& r0, int& r1) {
+  const int per = (n + kParts - 1) / kParts;
+  r0 = min(part * per, n);
+  r1 = min(r0 + per, n);
+}
+
+// Chan et al. merge of (n_a, mean_a, M2_a) with (n_b, mean_b, M2_b)
+__device__ __forceinline__ void welford_merge(float& n, float& mean, float& m2, float nb, float mb, float m2b) {
+  if (nb == 0.f) return;
+  const float nt = n + nb;
+  const float d = mb - mean;
+  mean += d * (nb / nt);
+  m2 += m2b + d * d * (n * nb / nt);
+  n = nt;
+}
+
+// partial statistics of z = y * snorm for one (row slab, 32-column tile)
+__global__ void __launch_bounds__(kTX * kTY) norm_stats_kernel(const DgnNormArgs a) {
+  const int n = rows_of(a);
+  const int col = blockIdx.y * kTX + threadIdx.x;
+  int r0, r1;
+  slab(n, blockIdx.x, r0, r1);
+  float cnt = 0.f, mean = 0.f, m2 = 0.f;
+  if (col < a.n_cols) {
+    for (int r = r0 + threadIdx.y; r < r1; r += kTY) {
+      float z = a.y[(size_t)r * a.ld_y + col];
+      if (a.snorm) z *= a.snorm[r];
+      cnt += 1.f;
+      const float d = z - mean;
+      mean += d / cnt;
+      m2 += d * (z - mean);
+    }
+  }
+  __shared__ float sn[kTY][kTX], sm[kTY][kTX], s2[kTY][kTX];
+  sn[threadIdx.y][threadIdx.x] = cnt;
+  sm[threadIdx.y][threadIdx.x] = mean;
+  s2[threadIdx.y][threadIdx.x] = m2;
+  __syncthreads();
+  if (threadIdx.y == 0 && col < a.n_cols) {
+    for (int j = 1; j < kTY; ++j) welford_merge(cnt, mean, m2, sn[j][threadIdx.x], sm[j][threadIdx.x], s2[j][threadIdx.x]);
+    float* part = a.stats + 2 * a.n_cols + (size_t)blockIdx.x * 2 * a.n_cols;
+    part[col] = mean;
+    part[a.n_cols + col] = m2;
+  }
+}
+
+// merges the slab partials of one column in slab order; returns batch mean / biased variance
+__device__ __forceinline__ void merged_stats(const DgnNormArgs& a, int n, int col, float& mean, float& var) {
+  float cnt = 0.f, m2 = 0.f;
+  mean = 0.f;
+  for (int p = 0; p < kParts; ++p) {
+    int r0, r1;
+    slab(n, p, r0, r1);
+    const float* part = a.stats + 2 * a.n_cols + (size_t)p * 2 * a.n_cols;
+    welford_merge(cnt, mean, m2, (float)(r1 - r0), part[col], part[a.n_cols + col]);
+  }
+  var = (cnt > 0.f) ? m2 / cnt : 0.f;
+}
+
+__global__ void __launch_bounds__(kTX * kTY) norm_apply_kernel(const DgnNormArgs a) {
+  const int n = rows_of(a);
+  const int col = blockIdx.y * kTX + threadIdx.x;
+  __shared__ float s_mean[kTX], s_rstd[kTX];
+  if (threadIdx.y == 0 && col < a.n_cols && a.gamma) {
+    float mean, var;
+    if (a.training) {
+      merged_stats(a, n, col, mean, var);
+      if (blockIdx.x == 0 && a.running_mean) {        // nn.BatchNorm1d: unbiased variance in the running estimate
+        const float unb = (n > 1) ? var * ((float)n / (float)(n - 1)) : var;
+        a.running_mean[col] = (1.f - a.momentum) * a.running_mean[col] + a.momentum * mean;
+        a.running_var[col] = (1.f - a.momentum) * a.running_var[col] + a.momentum * unb;
+      }
+    } else {
+      mean = a.running_mean[col];
+      var = a.running_var[col];
+    }
+    const float rstd = 1.f / sqrtf(var + a.eps);
+    s_mean[threadIdx.x] = mean;
+    s_rstd[threadIdx.x] = rstd;
+    if (blockIdx.x == 0) {
+      a.stats[col] = mean;
+      a.stats[a.n_cols + col] = rstd;
+    }
+  }
+  __syncthreads();
+  if (col >= a.n_cols) return;
+  const float mean = a.gamma ? s_mean[threadIdx.x] : 0.f;
+  const float rstd = a.gamma ? s_rstd[threadIdx.x] : 1.f;
+  const float ga = a.gamma ? a.gamma[col] : 1.f, be = a.gamma ? a.beta[col] : 0.f;
+  const int rows_cap = a.n_rows;
+  for (int r = blockIdx.x * kTY + threadIdx.y; r < rows_cap; r += gridDim.x * kTY) {
+    float o = 0.f;
+    if (r < n) {
+      float z = a.y[(size_t)r * a.ld_y + col];
+      if (a.snorm) z *= a.snorm[r];
+      o = (z - mean) * rstd * ga + be;
+      if (a.relu) o = fmaxf(o, 0.f);
+      if (a.residual) o += a.residual[(size_t)r * a.ld_res + col];
+    }
+    a.out[(size_t)r * a.ld_o + col] = o;
+  }
+}
+
+// g1 = g_out * relu'(.) ; partial sums of g1 and g1 * xhat per (row slab, column)
+__device__ __forceinline__ float masked_grad(const DgnNormArgs& a, const DgnNormGrad& g, int r, int col, float mean,
+                                             float rstd, float ga, float be, float& xhat) {
+  float z = a.y[(size_t)r * a.ld_y + col];
+  if (a.snorm) z *= a.snorm[r];
+  xhat = (z - mean) * rstd;
+  float go = g.g_out[(size_t)r * g.ld_go + col];
+  if (a.relu && !(xhat * ga + be > 0.f)) go = 0.f;
+  return go;
+}
+
+__global__ void __launch_bounds__(kTX * kTY) norm_bwd_reduce_kernel(const DgnNormArgs a, const DgnNormGrad g) {
+  const int n = rows_of(a);
+  const int col = blockIdx.y * kTX + threadIdx.x;
+  int r0, r1;
+  slab(n, blockIdx.x, r0, r1);
+  float sb = 0.f, sg = 0.f;
+  if (col < a.n_cols) {
+    const float mean = a.gamma ? a.stats[col] : 0.f, rstd = a.gamma ? a.stats[a.n_cols + col] : 1.f;
+    const float ga = a.gamma ? a.gamma[col] : 1.f, be = a.gamma ? a.beta[col] : 0.f;
+    for (int r = r0 + threadIdx.y; r < r1; r += kTY) {
+      float xhat;
+      const float g1 = masked_grad(a, g, r, col, mean, rstd, ga, be, xhat);
+      sb += g1;
+      sg = fmaf(g1, xhat, sg);
+    }
+  }
+  __shared__ float s1[kTY][kTX], s2[kTY][kTX];
+  s1[threadIdx.y][threadIdx.x] = sb;
+  s2[threadIdx.y][threadIdx.x] = sg;
+  __syncthreads();
+  if (threadIdx.y == 0 && col < a.n_cols) {
+    for (int j = 1; j < kTY; ++j) { sb += s1[j][threadIdx.x]; sg += s2[j][threadIdx.x]; }
+    float* part = g.scratch + 2 * a.n_cols + (size_t)blockIdx.x * 2 * a.n_cols;
+    part[col] = sb;
+    part[a.n_cols + col] = sg;
+  }
+}
+
+__global__ void __launch_bounds__(kTX * kTY) norm_bwd_apply_kernel(const DgnNormArgs a, const DgnNormGrad g) {
+  const int n = rows_of(a);
+  const int col = blockIdx.y * kTX + threadIdx.x;
+  __shared__ float s_b[kTX], s_g[kTX];
+  if (threadIdx.y == 0 && col < a.n_cols) {
+    float sb = 0.f, sg = 0.f;
+    for (int p = 0; p < kParts; ++p) {
+      const float* part = g.scratch + 2 * a.n_cols + (size_t)p * 2 * a.n_cols;
+      sb += part[col];
+      sg += part[a.n_cols + col];
+    }
+    s_b[threadIdx.x] = sb;
+    s_g[threadIdx.x] = sg;
+    if (blockIdx.x == 0 && a.gamma) {
+      if (g.d_beta) g.d_beta[col] = sb;
+      if (g.d_gamma) g.d_gamma[col] = sg;
+    }
+  }
+  __syncthreads();
+  if (col >= a.n_cols) return;
+  const float mean = a.gamma ? a.stats[col] : 0.f, rstd = a.gamma ? a.stats[a.n_cols + col] : 1.f;
+  const float ga = a.gamma ? a.gamma[col] : 1.f, be = a.gamma ? a.beta[col] : 0.f;
+  const float inv_n = (n > 0) ? 1.f / (float)n : 0.f;
+  const float mb = (a.gamma && a.training) ? s_b[threadIdx.x] * inv_n : 0.f;
+  const float mg = (a.gamma && a.training) ? s_g[threadIdx.x] * inv_n : 0.f;
+  for (int r = blockIdx.x * kTY + threadIdx.y; r < a.n_rows; r += gridDim.x * kTY) {
+    float dy = 0.f, dres = 0.f;
+    if (r < n) {
+      float xhat;
+      const float g1 = masked_grad(a, g, r, col, mean, rstd, ga, be, xhat);
+      float dz = a.gamma ? ga * rstd * (g1 - mb - xhat * mg) : g1;
+      if (a.snorm) dz *= a.snorm[r];
+      dy = dz;
+      dres = g.g_out[(size_t)r * g.ld_go + col];
+    }
+    g.d_y[(size_t)r * g.ld_dy + col] = dy;
+    if (g.d_residual) g.d_residual[(size_t)r * g.ld_dres + col] = dres;
+  }
+}
+
+// ---- readout -------------------------------------------------------------------------------------
+__global__ void readout_fwd_kernel(int n_graphs, const int32_t* __restrict__ gp, int C, const float* __restrict__ h,
+                                   int ld_h, int op, float* __restrict__ out, int ld_o) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  const int gi = blockIdx.y;
+  if (col >= C || gi >= n_graphs) return;
+  const int r0 = gp[gi], r1 = gp[gi + 1];
+  float acc = (op == 2) ? -INFINITY : 0.f;
+  for (int r = r0; r < r1; ++r) {
+    const float v = h[(size_t)r * ld_h + col];
+    acc = (op == 2) ? fmaxf(acc, v) : acc + v;
+  }
+  if (op == 1) acc = acc / (float)max(r1 - r0, 1);
+  if (r1 == r0) acc = 0.f;
+  out[(size_t)gi * ld_o + col] = acc;
+}
+
+__global__ void readout_bwd_kernel(int n_graphs, const int32_t* __restrict__ gp, int C, const float* __restrict__ h,
+                                   int ld_h, const float* __restrict__ out, int ld_o, int op,
+                                   const float* __restrict__ g_out, int ld_go, float* __restrict__ d_h, int ld_dh) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  const int gi = blockIdx.y;
+  if (col >= C || gi >= n_graphs) return;
+  const int r0 = gp[gi], r1 = gp[gi + 1];
+  float g = g_out[(size_t)gi * ld_go + col];
+  if (op == 1) g = g / (float)max(r1 - r0, 1);
+  const float top = (op == 2) ? out[(size_t)gi * ld_o + col] : 0.f;
+  bool given = false;
+  for (int r = r0; r < r1; ++r) {
+    float d = g;
+    if (op == 2) {                                   // first arg-max gets the gradient
+      d = 0.f;
+      if (!given && h[(size_t)r * ld_h + col] == top) { d = g; given = true; }
+    }
+    d_h[(size_t)r * ld_dh + col] = d;
+  }
+}
+
+}  // namespace dgn
+
+using namespace dgn;
+
+extern thread_local cudaError_t g_dgn_last_cuda;
+static int check_launch() {
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { g_dgn_last_cuda = e; return DGN_ERR_CUDA; }
+  return DGN_OK;
+}
+
+static dim3 norm_grid_apply(const DgnNormArgs* a) {
+  int gx = (a->n_rows + kTY - 1) / kTY;
+  if (gx > 592) gx = 592;                               // 4 x 148 SMs: grid-stride beyond that
+  if (gx < 1) gx = 1;
+  return dim3((unsigned)gx, (unsigned)((a->n_cols + kTX - 1) / kTX));
+}
+
+extern "C" int dgn_norm_forward(const DgnNormArgs* a, void* stream) {
+  if (!a || !a->y || !a->out || a->n_rows < 0 || a->n_cols <= 0) return DGN_ERR_INVALID;
+  if (a->gamma && (!a->beta || !a->stats)) return DGN_ERR_INVALID;
+  if (a->gamma && !a->training && (!a->running_mean || !a->running_var)) return DGN_ERR_INVALID;
+  if (a->n_rows == 0) return DGN_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const dim3 block(kTX, kTY);
+  if (a->gamma && a->training) {
+    norm_stats_kernel<<<dim3(kParts, (a->n_cols + kTX - 1) / kTX), block, 0, st>>>(*a);
+    if (int rc = check_launch()) return rc;
+  }
+  norm_apply_kernel<<<norm_grid_apply(a), block, 0, st>>>(*a);
+  return check_launch();
+}
+
+extern "C" int dgn_norm_backward(const DgnNormArgs* a, const DgnNormGrad* g, void* stream) {
+  if (!a || !g || !a->y || !g->g_out || !g->d_y || !g->scratch || a->n_cols <= 0) return DGN_ERR_INVALID;
+  if (a->gamma && !a->stats) return DGN_ERR_INVALID;
+  if (a->n_rows == 0) return DGN_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const dim3 block(kTX, kTY);
+  norm_bwd_reduce_kernel<<<dim3(kParts, (a->n_cols + kTX - 1) / kTX), block, 0, st>>>(*a, *g);
+  if (int rc = check_launch()) return rc;
+  norm_bwd_apply_kernel<<<norm_grid_apply(a), block, 0, st>>>(*a, *g);
+  return check_launch();
+}
+
+extern "C" int dgn_readout_forward(int32_t n_graphs, const int32_t* graph_ptr, int32_t n_cols, const float* h,
+                                   int32_t ld_h, int32_t op, float* out, int32_t ld_o, void* stream) {
+  if (n_graphs < 0 || n_cols <= 0 || !graph_ptr || !h || !out || op < 0 || op > 2) return DGN_ERR_INVALID;
+  if (n_graphs == 0) return DGN_OK;
+  const int block = 64;
+  readout_fwd_kernel<<<dim3((n_cols + block - 1) / block, n_graphs), block, 0, (cudaStream_t)stream>>>(
+      n_graphs, graph_ptr, n_cols, h, ld_h, op, out, ld_o);
+  return check_launch();
+}
+
+extern "C" int dgn_readout_backward(int32_t n_graphs, const int32_t* graph_ptr, int32_t n_cols, const float* h,
+                                    int32_t ld_h, const float* out, int32_t ld_o, int32_t op, const float* g_out,
+                                    int32_t ld_go, float* d_h, int32_t ld_dh, void* stream) {
+  if (n_graphs < 0 || n_cols <= 0 || !graph_ptr || !g_out || !d_h || op < 0 || op > 2) return DGN_ERR_INVALID;
+  if (op == 2 && (!h || !out)) return DGN_ERR_INVALID;
+  if (n_graphs == 0) return DGN_OK;
+  const int block = 64;
+  readout_bwd_kernel<<<dim3((n_cols + block - 1) / block, n_graphs), block, 0, (cudaStream_t)stream>>>(
+      n_graphs, graph_ptr, n_cols, h, ld_h, out, ld_o, op, g_out, ld_go, d_h, ld_dh);
+  return check_launch();
+}

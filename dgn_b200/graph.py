@@ -1,0 +1,211 @@
+"""Batched graph container: destination-major CSR on the device behind a DGL-like surface.
+
+The reference hands its layers a DGL-0.4.2 ``BatchedDGLGraph`` (``dgl.batch`` in
+realworld_benchmark/data/molecules.py:229).  The engine needs from it only the node count,
+the edge list in edge-id order, ``ndata['eig']`` and ``batch_num_nodes``.
+``BatchedGraph`` provides exactly that surface (``ndata`` / ``edata`` / ``number_of_nodes()`` /
+``number_of_edges()`` / ``edges()`` / ``in_degrees()`` / ``batch_num_nodes``) and owns the
+kernel-side layout:
+
+* ``in_ptr [N+1]``, ``in_src [E]``, ``in_eid [E]``  in-edge slots grouped by destination; slots of
+  one node keep edge-id order (the order of the reference's mailbox);
+* ``out_ptr [N+1]``, ``out_slot [E]``                by-source transpose for the backward pass;
+* ``log_deg [N]``, ``snorm_n [N,1]``, ``graph_ptr [B+1]``.
+
+Everything a step needs is packed into ONE pinned host buffer and moved with ONE
+host-to-device copy; the device arrays are views into that single allocation.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_ALIGN = 16
+
+
+def _round_up(x: int, a: int = _ALIGN) -> int:
+    return (x + a - 1) // a * a
+
+
+class _Pack:
+    """Lays named arrays out in one byte buffer (16 B aligned segments)."""
+
+    def __init__(self):
+        self.entries, self.size = {}, 0
+
+    def add(self, name, shape, dtype):
+        dtype = np.dtype(dtype)
+        nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+        self.entries[name] = (self.size, tuple(int(s) for s in shape), dtype)
+        self.size = _round_up(self.size + nbytes)
+
+    def host_views(self, buf: np.ndarray):
+        out = {}
+        for name, (off, shape, dtype) in self.entries.items():
+            n = int(np.prod(shape, dtype=np.int64))
+            out[name] = buf[off:off + n * dtype.itemsize].view(dtype).reshape(shape)
+        return out
+
+    def device_views(self, blob: torch.Tensor):
+        out = {}
+        for name, (off, shape, dtype) in self.entries.items():
+            n = int(np.prod(shape, dtype=np.int64))
+            tdt = {np.dtype(np.int32): torch.int32, np.dtype(np.int64): torch.int64,
+                   np.dtype(np.float32): torch.float32}[dtype]
+            out[name] = blob[off:off + n * dtype.itemsize].view(tdt).reshape(shape)
+        return out
+
+
+class BatchedGraph:
+    """A mini-batch of graphs with contiguous node ranges (block-diagonal adjacency)."""
+
+    _STRUCT = ("in_ptr", "in_src", "in_eid", "out_ptr", "out_slot", "graph_ptr", "src", "dst", "log_deg", "snorm_n")
+
+    def __init__(self, n_nodes, src, dst, batch_num_nodes=None, batch_num_edges=None, ndata=None, edata=None,
+                 pin_memory=None):
+        src = np.ascontiguousarray(np.asarray(src), dtype=np.int32)
+        dst = np.ascontiguousarray(np.asarray(dst), dtype=np.int32)
+        assert src.shape == dst.shape and src.ndim == 1
+        self._n, self._e = int(n_nodes), int(src.shape[0])
+        self.batch_num_nodes = [int(x) for x in (batch_num_nodes if batch_num_nodes is not None else [self._n])]
+        self.batch_num_edges = [int(x) for x in (batch_num_edges if batch_num_edges is not None else [self._e])]
+        assert sum(self.batch_num_nodes) == self._n
+        B = len(self.batch_num_nodes)
+        ndata = dict(ndata or {})
+        edata = dict(edata or {})
+
+        pack = _Pack()
+        N, E = self._n, self._e
+        for name, shape, dt in (("in_ptr", (N + 1,), np.int32), ("in_src", (E,), np.int32), ("in_eid", (E,), np.int32),
+                                ("out_ptr", (N + 1,), np.int32), ("out_slot", (E,), np.int32),
+                                ("graph_ptr", (B + 1,), np.int32), ("src", (E,), np.int32), ("dst", (E,), np.int32),
+                                ("log_deg", (N,), np.float32), ("snorm_n", (N, 1), np.float32)):
+            pack.add(name, shape, dt)
+        for k, v in ndata.items():
+            v = np.asarray(v)
+            pack.add("n:" + k, v.shape, v.dtype)
+        for k, v in edata.items():
+            v = np.asarray(v)
+            pack.add("e:" + k, v.shape, v.dtype)
+        self._pack = pack
+
+        if pin_memory is None:
+            pin_memory = torch.cuda.is_available()
+        self._host_blob = torch.empty(max(pack.size, _ALIGN), dtype=torch.uint8, pin_memory=pin_memory)
+        hv = pack.host_views(self._host_blob.numpy())
+        hv["src"][:] = src
+        hv["dst"][:] = dst
+        hv["graph_ptr"][0] = 0
+        np.cumsum(self.batch_num_nodes, out=hv["graph_ptr"][1:])
+        sizes = np.asarray(self.batch_num_nodes, dtype=np.float32)
+        # collate(): snorm_n = sqrt(1 / n_g) per node  (rb/data/molecules.py:222-224)
+        hv["snorm_n"][:, 0] = np.repeat(np.sqrt(np.float32(1.0) / sizes), self.batch_num_nodes)
+        for k, v in ndata.items():
+            hv["n:" + k][...] = np.asarray(v)
+        for k, v in edata.items():
+            hv["e:" + k][...] = np.asarray(v)
+
+        def p(a):
+            return a.ctypes.data_as(ctypes.c_void_p)
+        _lib.check(_lib.lib.dgn_build_csr_host(N, E, p(hv["src"]), p(hv["dst"]), p(hv["in_ptr"]), p(hv["in_src"]),
+                                               p(hv["in_eid"]), p(hv["out_ptr"]), p(hv["out_slot"]), p(hv["log_deg"])),
+                   "dgn_build_csr_host")
+        self._host = hv
+        self.device = torch.device("cpu")
+        self._bind(pack.device_views(self._host_blob))
+
+    # ------------------------------------------------------------------------------------------
+    def _bind(self, views):
+        self._t = {k: views[k] for k in self._STRUCT}
+        self.ndata = {k[2:]: v for k, v in views.items() if k.startswith("n:")}
+        self.edata = {k[2:]: v for k, v in views.items() if k.startswith("e:")}
+        self._c_graph = None
+
+    def to(self, device, non_blocking=True):
+        """One host-to-device copy of the packed buffer; returns self (like DGLGraph.to in later DGLs)."""
+        device = torch.device(device)
+        if device.type == "cpu":
+            self.device = device
+            self._bind(self._pack.device_views(self._host_blob))
+            return self
+        blob = self._host_blob.to(device, non_blocking=non_blocking)
+        self.device = device
+        self._blob = blob
+        self._bind(self._pack.device_views(blob))
+        return self
+
+    @property
+    def h2d_bytes(self) -> int:
+        return int(self._pack.size)
+
+    # ---- DGL-like surface ----------------------------------------------------------------------
+    def number_of_nodes(self):
+        return self._n
+
+    def number_of_edges(self):
+        return self._e
+
+    @property
+    def batch_size(self):
+        return len(self.batch_num_nodes)
+
+    def edges(self):
+        return self._t["src"].long(), self._t["dst"].long()
+
+    def in_degrees(self):
+        p = self._t["in_ptr"]
+        return (p[1:] - p[:-1]).long()
+
+    # ---- engine-side accessors -----------------------------------------------------------------
+    def __getattr__(self, name):
+        t = self.__dict__.get("_t")
+        if t is not None and name in t:
+            return t[name]
+        raise AttributeError(name)
+
+    def host(self, name):
+        return self._host[name]
+
+    def c_graph(self) -> "_lib.DgnGraph":
+        """DgnGraph struct over the DEVICE arrays (cached)."""
+        if self.device.type != "cuda":
+            raise _lib.DgnError("BatchedGraph is on %s: the aggregation kernels need it on a CUDA device "
+                                "(call .to('cuda')); there is no CPU path" % self.device)
+        if self._c_graph is None:
+            t = self._t
+            self._c_graph = _lib.DgnGraph(self._n, self._e, t["in_ptr"].data_ptr(), t["in_src"].data_ptr(),
+                                          t["in_eid"].data_ptr(), t["out_ptr"].data_ptr(), t["out_slot"].data_ptr(),
+                                          t["log_deg"].data_ptr())
+        return self._c_graph
+
+    @property
+    def max_in_degree(self):
+        p = self._host["in_ptr"]
+        return int((p[1:] - p[:-1]).max()) if self._n else 0
+
+
+def collate(samples, node_key="feat", edge_key="feat", extra_ndata=()):
+    """``dataset.collate`` + ``dgl.batch`` (rb/data/molecules.py:219-230) for synthetic samples.
+
+    Returns ``(graph, labels)``; ``graph.ndata`` holds ``feat`` and ``eig``, ``graph.edata`` holds
+    ``feat``; ``graph.snorm_n`` is the per-node graph-norm factor.
+    """
+    sizes = [int(s["n"]) for s in samples]
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    src = np.concatenate([s["src"].astype(np.int64) + offs[i] for i, s in enumerate(samples)])
+    dst = np.concatenate([s["dst"].astype(np.int64) + offs[i] for i, s in enumerate(samples)])
+    ndata = {node_key: np.concatenate([np.asarray(s["node_feat"]) for s in samples], 0),
+             "eig": np.concatenate([np.asarray(s["eig"], dtype=np.float32) for s in samples], 0)}
+    for k in extra_ndata:
+        ndata[k] = np.concatenate([np.asarray(s[k]) for s in samples], 0)
+    edata = {edge_key: np.concatenate([np.asarray(s["edge_feat"]) for s in samples], 0)}
+    g = BatchedGraph(int(offs[-1]), src, dst, sizes, [len(s["src"]) for s in samples], ndata, edata)
+    if np.ndim(samples[0]["label"]) == 0:
+        labels = torch.from_numpy(np.asarray([s["label"] for s in samples]))
+    else:
+        labels = torch.from_numpy(np.concatenate([np.asarray(s["label"]) for s in samples]))
+    return g, labels

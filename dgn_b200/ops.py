@@ -1,0 +1,245 @@
+"""torch.autograd wrappers around the C-ABI kernels (``include/dgn_b200.h``).
+
+PyTorch is plumbing here: it owns device memory and the CUDA stream, and records the autograd
+graph.  All arithmetic of the hot path happens inside ``libdgn_b200.so``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import lib, check
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise _lib.DgnError("dgn_b200 ops run on CUDA tensors only (got a %s tensor); there is no CPU fallback"
+                                % t.device)
+
+
+def _f32c(t):
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.stride(-1) == 1 and t.dim() == 2 else t.contiguous()
+
+
+class AggSpec:
+    """Aggregator / scaler selection of one layer, frozen into a ``DgnAggSpec``."""
+
+    def __init__(self, aggregators, scalers, avg_log: float, n_feat: int, n_eig: int, group_feat: int = 0):
+        if len(aggregators) > _lib.MAX_AGG or len(scalers) > _lib.MAX_SCALERS:
+            raise _lib.DgnError("at most %d aggregators and %d scalers per layer" % (_lib.MAX_AGG, _lib.MAX_SCALERS))
+        self.aggregators, self.scalers = list(aggregators), list(scalers)
+        self.A, self.S_decl = len(self.aggregators), len(self.scalers)
+        self.S = self.S_decl if self.S_decl > 1 else 1          # rb/nets/dgn_layer.py:95
+        self.F, self.K = int(n_feat), int(n_eig)
+        self.Fg = int(group_feat) if group_feat else self.F
+        self.avg_log = float(avg_log)
+        s = _lib.DgnAggSpec()
+        s.n_feat, s.group_feat, s.n_eig, s.n_agg, s.n_scalers = self.F, self.Fg, self.K, self.A, self.S_decl
+        for i, a in enumerate(self.aggregators):
+            s.agg_kind[i], s.agg_eig[i], s.agg_alpha[i] = a.kind, a.eig_idx, a.alpha
+            if a.kind >= _lib.AGG_DIR_AV and a.eig_idx >= self.K:
+                raise _lib.DgnError("aggregator %r needs eigenvector column %d but ndata['eig'] has %d columns"
+                                    % (a.name, a.eig_idx, self.K))
+        for i, sc in enumerate(self.scalers):
+            s.scaler_kind[i] = sc.kind
+        s.avg_log = self.avg_log
+        self.c = s
+
+    @property
+    def out_width(self) -> int:
+        """Columns of the aggregate per tower: S*A*F_tower."""
+        return self.S * self.A * self.Fg
+
+
+class _Aggregate(torch.autograd.Function):
+    """out = [h_in |] scalers(aggregators(messages)); see dgn_agg_forward / dgn_agg_backward."""
+
+    @staticmethod
+    def forward(ctx, graph, spec, mode, cat_input, x, q, r, h_in, eig):
+        _need_cuda(x, q, r, h_in, eig)
+        x, q, r, h_in, eig = _f32c(x), _f32c(q), _f32c(r), _f32c(h_in), _f32c(eig)
+        N, F, Fg = graph.number_of_nodes(), spec.F, spec.Fg
+        T = F // Fg
+        lead = Fg if cat_input else 0
+        Wt = lead + spec.out_width                     # columns per tower block
+        out = torch.empty((N, T * Wt), device=h_in.device, dtype=torch.float32)
+        io = _lib.DgnAggIO()
+        io.msg_mode = mode
+        if x is not None:
+            io.x, io.ld_x = x.data_ptr(), x.stride(0)
+        if q is not None:
+            io.q, io.ld_q = q.data_ptr(), q.stride(0)
+        if r is not None:
+            io.r, io.ld_r = r.data_ptr(), r.stride(0)
+        io.h_in, io.ld_h = h_in.data_ptr(), h_in.stride(0)
+        if eig is not None:
+            io.eig, io.ld_eig = eig.data_ptr(), eig.stride(0)
+        io.out, io.ld_out, io.out_group_stride = out.data_ptr() + 4 * lead, out.stride(0), Wt
+        if cat_input:
+            io.h_copy, io.ld_hcopy, io.hcopy_group_stride = out.data_ptr(), out.stride(0), Wt
+        check(lib.dgn_agg_forward(C.byref(graph.c_graph()), C.byref(spec.c), C.byref(io), _stream(h_in)),
+              "dgn_agg_forward")
+        ctx.graph, ctx.spec, ctx.mode, ctx.cat_input, ctx.lead, ctx.Wt = graph, spec, mode, cat_input, lead, Wt
+        ctx.save_for_backward(x, q, r, h_in, eig)
+        ctx.same_x_h = x is not None and h_in.data_ptr() == x.data_ptr() and mode == _lib.MSG_SOURCE
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        x, q, r, h_in, eig = ctx.saved_tensors
+        graph, spec, mode = ctx.graph, ctx.spec, ctx.mode
+        g_out = g_out.contiguous()
+        N, E, F = graph.number_of_nodes(), graph.number_of_edges(), spec.F
+        dev = h_in.device
+        need = ctx.needs_input_grad        # (graph, spec, mode, cat_input, x, q, r, h_in, eig)
+        io = _lib.DgnAggIO()
+        io.msg_mode = mode
+        if x is not None:
+            io.x, io.ld_x = x.data_ptr(), x.stride(0)
+        if q is not None:
+            io.q, io.ld_q = q.data_ptr(), q.stride(0)
+        if r is not None:
+            io.r, io.ld_r = r.data_ptr(), r.stride(0)
+        io.h_in, io.ld_h = h_in.data_ptr(), h_in.stride(0)
+        if eig is not None:
+            io.eig, io.ld_eig = eig.data_ptr(), eig.stride(0)
+        io.out, io.ld_out, io.out_group_stride = 0, g_out.stride(0), ctx.Wt
+        io.ld_hcopy, io.hcopy_group_stride = g_out.stride(0), ctx.Wt
+        io.out = g_out.data_ptr() + 4 * ctx.lead          # never written by the backward
+
+        gr = _lib.DgnAggGrad()
+        gr.g_out = g_out.data_ptr() + 4 * ctx.lead
+        if ctx.cat_input:
+            gr.g_hcopy = g_out.data_ptr()
+        fold = ctx.same_x_h                                # simple layer: x and h_in are one tensor
+        d_x = d_q = d_r = d_h = None
+        want_x = x is not None and (need[4] or (fold and need[7]))
+        if want_x:
+            d_x = torch.empty((N, F), device=dev, dtype=torch.float32)
+            ws = torch.empty((max(E, 1), F), device=dev, dtype=torch.float32)
+            gr.d_x, gr.ld_dx, gr.edge_ws = d_x.data_ptr(), F, ws.data_ptr()
+        if q is not None and need[5]:
+            d_q = torch.empty((N, F), device=dev, dtype=torch.float32)
+            gr.d_q, gr.ld_dq = d_q.data_ptr(), F
+        if r is not None and need[6]:
+            d_r = torch.empty((max(E, 1), F), device=dev, dtype=torch.float32)[:E]
+            gr.d_r, gr.ld_dr = d_r.data_ptr(), F
+        if need[7] or fold:
+            d_h = torch.empty((N, F), device=dev, dtype=torch.float32)
+            gr.d_h_in, gr.ld_dh = d_h.data_ptr(), F
+        gr.fold_h_in = 1 if (fold and want_x) else 0
+        check(lib.dgn_agg_backward(C.byref(graph.c_graph()), C.byref(spec.c), C.byref(io), C.byref(gr),
+                                   _stream(h_in)), "dgn_agg_backward")
+        if fold:
+            # x and h_in are the same tensor: its whole gradient was folded into d_x (None counts as zero)
+            return None, None, None, None, d_x, None, None, None, None
+        return None, None, None, None, d_x, d_q, d_r, d_h, None
+
+
+def aggregate(graph, spec: AggSpec, mode: int, h_in, eig, x=None, q=None, r=None, cat_input=False):
+    """Fused directional aggregation.  Returns ``[N, T*((1 if cat_input else 0)*F_t + S*A*F_t)]``."""
+    return _Aggregate.apply(graph, spec, mode, cat_input, x, q, r, h_in, eig)
+
+
+class _NormAct(torch.autograd.Function):
+    """snorm * y -> BatchNorm1d -> ReLU -> + residual (rb/nets/dgn_layer.py:122-130) in the C-ABI kernels."""
+
+    @staticmethod
+    def forward(ctx, y, snorm, gamma, beta, running_mean, running_var, momentum, eps, training, relu, residual):
+        _need_cuda(y)
+        y = _f32c(y)
+        N, Cn = y.shape
+        out = torch.empty((N, Cn), device=y.device, dtype=torch.float32)
+        stats = torch.empty(_lib.NORM_WS_PER_COL * Cn, device=y.device, dtype=torch.float32)
+        a = _lib.DgnNormArgs()
+        a.n_rows, a.n_cols, a.y, a.ld_y = N, Cn, y.data_ptr(), y.stride(0)
+        if snorm is not None:
+            snorm = snorm.reshape(-1).contiguous()
+            a.snorm = snorm.data_ptr()
+        if gamma is not None:
+            a.gamma, a.beta = gamma.data_ptr(), beta.data_ptr()
+            if running_mean is not None:
+                a.running_mean, a.running_var = running_mean.data_ptr(), running_var.data_ptr()
+        a.momentum, a.eps, a.training, a.relu = momentum, eps, int(training), int(relu)
+        if residual is not None:
+            residual = _f32c(residual)
+            a.residual, a.ld_res = residual.data_ptr(), residual.stride(0)
+        a.out, a.ld_o, a.stats = out.data_ptr(), Cn, stats.data_ptr()
+        check(lib.dgn_norm_forward(C.byref(a), _stream(y)), "dgn_norm_forward")
+        ctx.args = a
+        ctx.keep = (y, snorm, gamma, beta, running_mean, running_var, residual, out, stats)
+        ctx.has_res, ctx.has_bn = residual is not None, gamma is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        a = ctx.args
+        y = ctx.keep[0]
+        N, Cn = y.shape
+        g_out = g_out.contiguous()
+        d_y = torch.empty_like(y)
+        scratch = torch.empty(_lib.NORM_WS_PER_COL * Cn, device=y.device, dtype=torch.float32)
+        g = _lib.DgnNormGrad()
+        g.g_out, g.ld_go, g.d_y, g.ld_dy, g.scratch = g_out.data_ptr(), Cn, d_y.data_ptr(), Cn, scratch.data_ptr()
+        d_gamma = d_beta = None
+        if ctx.has_bn:
+            d_gamma = torch.empty(Cn, device=y.device, dtype=torch.float32)
+            d_beta = torch.empty(Cn, device=y.device, dtype=torch.float32)
+            g.d_gamma, g.d_beta = d_gamma.data_ptr(), d_beta.data_ptr()
+        check(lib.dgn_norm_backward(C.byref(a), C.byref(g), _stream(y)), "dgn_norm_backward")
+        d_res = g_out if ctx.has_res else None       # identity branch
+        return d_y, None, d_gamma, d_beta, None, None, None, None, None, None, d_res
+
+
+def norm_act(y, snorm, bn, training, relu, residual):
+    """Fused layer epilogue.  ``bn`` is an ``nn.BatchNorm1d`` (or None when batch_norm is off)."""
+    if bn is not None:
+        if training and bn.track_running_stats and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked += 1
+        use_batch = training or not bn.track_running_stats
+        mom = 0.1 if bn.momentum is None else bn.momentum
+        return _NormAct.apply(y, snorm, bn.weight, bn.bias, bn.running_mean, bn.running_var, mom, bn.eps,
+                              use_batch, relu, residual)
+    return _NormAct.apply(y, snorm, None, None, None, None, 0.1, 1e-5, False, relu, residual)
+
+
+class _Readout(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h, graph, op):
+        _need_cuda(h)
+        h = _f32c(h)
+        B, Cn = graph.batch_size, h.shape[1]
+        out = torch.empty((B, Cn), device=h.device, dtype=torch.float32)
+        check(lib.dgn_readout_forward(B, graph.graph_ptr.data_ptr(), Cn, h.data_ptr(), h.stride(0), op,
+                                      out.data_ptr(), Cn, _stream(h)), "dgn_readout_forward")
+        ctx.graph, ctx.op = graph, op
+        ctx.save_for_backward(h, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        h, out = ctx.saved_tensors
+        g_out = g_out.contiguous()
+        B, Cn = out.shape
+        d_h = torch.empty_like(h)
+        check(lib.dgn_readout_backward(B, ctx.graph.graph_ptr.data_ptr(), Cn, h.data_ptr(), h.stride(0),
+                                       out.data_ptr(), Cn, ctx.op, g_out.data_ptr(), Cn, d_h.data_ptr(),
+                                       d_h.stride(0), _stream(h)), "dgn_readout_backward")
+        return d_h, None, None
+
+
+def readout(graph, h, op: str):
+    """Per-graph ``sum`` / ``mean`` / ``max`` over the node rows (dgl.{sum,mean,max}_nodes)."""
+    code = {"sum": _lib.READOUT_SUM, "mean": _lib.READOUT_MEAN, "max": _lib.READOUT_MAX}[op]
+    return _Readout.apply(h, graph, code)

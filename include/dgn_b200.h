@@ -1,0 +1,214 @@
+/*
+ * dgn_b200.h - C ABI of the B200-native DGN directional-aggregation engine.
+ *
+ * The reference (Saro00/DGN) is pure Python and has no FFI of its own.  The entry points
+ * below are what a binding for its hot path has to call; each one names the reference code
+ * it replaces (paths relative to the reference root, rb/ = realworld_benchmark/):
+ *
+ *   dgn_agg_forward   - rb/nets/dgn_layer.py:86-98 (reduce_func: every AGGREGATORS entry of
+ *                       rb/nets/aggregators.py:8-93 followed by every SCALERS entry of
+ *                       rb/nets/scalers.py:7-21), the message construction of
+ *                       rb/nets/dgn_layer.py:75-84 / :154-159, and the degree-bucketed
+ *                       DGLGraph.update_all of DGL 0.4.2 called at rb/nets/dgn_layer.py:115,186,264.
+ *   dgn_agg_backward  - what torch.autograd derives for the same code.
+ *   dgn_build_csr     - the edge grouping DGL 0.4.2 does inside update_all (degree bucketing)
+ *                       and dgl.batch (rb/data/molecules.py:229).
+ *   dgn_norm_*        - rb/nets/dgn_layer.py:122-130 (graph norm, BatchNorm1d, ReLU, residual).
+ *   dgn_readout_*     - dgl.{mean,sum,max}_nodes at rb/nets/molecules_graph_regression/dgn_net.py:71-86.
+ *
+ * Conventions: plain pointers and sizes only, no ownership transfer, no allocation, no
+ * exceptions.  Every pointer in DgnGraph / DgnAggIO / DgnAggGrad is DEVICE memory unless the
+ * function name ends in _host.  Matrices are row-major fp32 with an explicit leading
+ * dimension counted in floats.  `stream` is a cudaStream_t passed as void* (0 = legacy
+ * default stream).  All launches are stream-ordered, re-entrant and CUDA-graph capturable.
+ * Return value: 0 on success, a negative DgnStatus otherwise (see dgn_status_string).
+ */
+#ifndef DGN_B200_H_
+#define DGN_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DGN_ABI_VERSION 1
+#define DGN_MAX_AGG 32      /* aggregators per layer (the reference registry has 24)        */
+#define DGN_MAX_SCALERS 4   /* scalers per layer (the reference registry has 3)             */
+#define DGN_MAX_SLOTS 8     /* distinct eigen-weighted feature sums one launch can carry    */
+#define DGN_EPS 1e-8f       /* rb/nets/aggregators.py:5                                     */
+#define DGN_NORM_WS_FLOATS(C) (130 * (C)) /* fp32 workspace of dgn_norm_* for C columns         */
+
+typedef enum {
+  DGN_OK = 0,
+  DGN_ERR_INVALID = -1,     /* bad argument (null pointer, negative size, unknown enum)     */
+  DGN_ERR_UNSUPPORTED = -2, /* valid request the kernels cannot serve (too many slots ...)  */
+  DGN_ERR_ALIGNMENT = -3,   /* reserved                                                     */
+  DGN_ERR_CUDA = -4         /* a CUDA runtime call failed; see dgn_last_cuda_error          */
+} DgnStatus;
+
+/* aggregator kinds: rb/nets/aggregators.py */
+typedef enum {
+  DGN_AGG_MEAN = 0,            /* :8   */
+  DGN_AGG_SUM = 1,             /* :31  */
+  DGN_AGG_MAX = 2,             /* :12  */
+  DGN_AGG_MIN = 3,             /* :16  */
+  DGN_AGG_STD = 4,             /* :20  */
+  DGN_AGG_VAR = 5,             /* :24  */
+  DGN_AGG_DIR_AV = 6,          /* :35  dirK-av (alias dirK-smooth)  */
+  DGN_AGG_DIR_DX = 7,          /* :48  dirK-dx ("dx_abs")           */
+  DGN_AGG_DIR_DX_NO_ABS = 8,   /* :55  */
+  DGN_AGG_DIR_DX_BALANCED = 9, /* :62  */
+  DGN_AGG_DIR_SOFTMAX = 10     /* :42  dirK-0.1 / dirK-neg-0.1, alpha in agg_alpha */
+} DgnAggKind;
+
+/* scaler kinds: rb/nets/scalers.py */
+typedef enum {
+  DGN_SCALE_IDENTITY = 0,      /* :7   */
+  DGN_SCALE_AMPLIFICATION = 1, /* :11  h * log(D+1) / avg_log */
+  DGN_SCALE_ATTENUATION = 2    /* :16  h * avg_log / log(D+1) */
+} DgnScalerKind;
+
+/* how the message m_uv of edge u->v is formed */
+typedef enum {
+  DGN_MSG_SOURCE = 0, /* m = X[u]                      DGNLayerSimple, rb/nets/dgn_layer.py:154-155        */
+  DGN_MSG_AFFINE = 1, /* m = X[u] + Q[v] (+ R[eid])    1-layer pretrans split per node, :75-80             */
+  DGN_MSG_DENSE = 2   /* m = R[eid]                    materialised messages (pretrans_layers > 1)         */
+} DgnMsgMode;
+
+/* Batched graph in destination-major CSR ("in-edge slots") plus its by-source transpose. */
+typedef struct {
+  int32_t n_nodes;
+  int32_t n_edges;
+  const int32_t* in_ptr;   /* [n_nodes+1] slot range of every destination node                         */
+  const int32_t* in_src;   /* [n_edges]   source node of every slot; slots of one node keep edge-id order */
+  const int32_t* in_eid;   /* [n_edges]   original edge id of every slot (NULL = identity)              */
+  const int32_t* out_ptr;  /* [n_nodes+1] range of every source node in out_slot (backward only)        */
+  const int32_t* out_slot; /* [n_edges]   in-edge slot of every out-edge, grouped by source             */
+  const float* log_deg;    /* [n_nodes]   (float)log(in_degree + 1), the scalers' per-node factor       */
+} DgnGraph;
+
+/* Which aggregators / scalers to compute: the AGGREGATORS / SCALERS names resolved to op-codes. */
+typedef struct {
+  int32_t n_feat;         /* F: feature columns aggregated (all towers together)                        */
+  int32_t group_feat;     /* columns per tower (== n_feat when there is a single tower)                 */
+  int32_t n_eig;          /* K: columns of eig                                                          */
+  int32_t n_agg;          /* A                                                                          */
+  int32_t n_scalers;      /* S; like rb/nets/dgn_layer.py:95 the scalers are applied only when S > 1    */
+  uint8_t agg_kind[DGN_MAX_AGG];   /* DgnAggKind                                                        */
+  uint8_t agg_eig[DGN_MAX_AGG];    /* eigenvector column for directional kinds                          */
+  float agg_alpha[DGN_MAX_AGG];    /* softmax temperature for DGN_AGG_DIR_SOFTMAX                       */
+  uint8_t scaler_kind[DGN_MAX_SCALERS];
+  float avg_log;          /* avg_d["log"] = mean(log(D+1)) over the training set                        */
+} DgnAggSpec;
+
+/* Operands of one aggregation.  Output row v, tower t, scaler s, aggregator a, column c lives at
+ *   out[v*ld_out + t*out_group_stride + (s*A + a)*group_feat + c]
+ * which for one tower is the reference's [N, S*A*F] layout (scaler-major, then aggregator). */
+typedef struct {
+  int32_t msg_mode;       /* DgnMsgMode                                                                 */
+  const float* x;         /* [N,F] source term: X (SOURCE) or P = h W_src^T (AFFINE); unused for DENSE   */
+  int32_t ld_x;
+  const float* q;         /* [N,F] destination term incl. bias (AFFINE only)                             */
+  int32_t ld_q;
+  const float* r;         /* [E,F] per-edge term in EDGE-ID order: optional for AFFINE, the message for DENSE */
+  int32_t ld_r;
+  const float* h_in;      /* [N,F] destination's own features (the dx aggregators subtract W*h_in)       */
+  int32_t ld_h;
+  const float* eig;       /* [N,K]                                                                       */
+  int32_t ld_eig;
+  float* out;             /* see layout above                                                            */
+  int32_t ld_out;
+  int32_t out_group_stride;
+  float* h_copy;          /* optional: h_in rows copied here (tower t at h_copy[v*ld_hcopy + t*hcopy_group_stride + c]),
+                             fuses the torch.cat([h, agg]) of rb/nets/dgn_layer.py:116                    */
+  int32_t ld_hcopy;
+  int32_t hcopy_group_stride;
+} DgnAggIO;
+
+/* Gradients for dgn_agg_backward.  Any output pointer may be NULL when that gradient is not needed. */
+typedef struct {
+  const float* g_out;     /* gradient of `out`, same layout / ld_out / out_group_stride as the forward  */
+  const float* g_hcopy;   /* gradient of `h_copy` (NULL if h_copy was not used), same layout            */
+  float* d_x;             /* [N,F] gradient of io.x (scatter over out-edges; + d_h_in when fold_h_in)    */
+  int32_t ld_dx;
+  float* d_q;             /* [N,F] gradient of io.q                                                      */
+  int32_t ld_dq;
+  float* d_r;             /* [E,F] gradient of io.r in edge-id order                                     */
+  int32_t ld_dr;
+  float* d_h_in;          /* [N,F] gradient of io.h_in (incl. g_hcopy)                                   */
+  int32_t ld_dh;
+  float* edge_ws;         /* [E,F] workspace (slot order) for the deterministic source-side reduction;
+                             required when d_x != NULL                                                   */
+  int32_t fold_h_in;      /* 1: d_x += d_h_in (SOURCE mode where x and h_in are the same tensor)         */
+} DgnAggGrad;
+
+int dgn_abi_version(void);
+const char* dgn_status_string(int status);
+const char* dgn_last_cuda_error(void);
+
+/* out[N, S*A*F] = scalers(aggregators(messages)) for every destination node.  Replaces
+ * reduce_func + update_all + message construction (see file header). */
+int dgn_agg_forward(const DgnGraph* g, const DgnAggSpec* spec, const DgnAggIO* io, void* stream);
+
+/* Gradients of dgn_agg_forward w.r.t. x, q, r and h_in; recomputes the per-node statistics
+ * instead of saving them.  Deterministic (no atomics). */
+int dgn_agg_backward(const DgnGraph* g, const DgnAggSpec* spec, const DgnAggIO* io, const DgnAggGrad* grad,
+                     void* stream);
+
+/* HOST: group edges by destination (stable, so mailbox order = edge-id order as in DGL 0.4.2
+ * degree bucketing) and build the by-source transpose.  All arrays are host memory sized as in
+ * DgnGraph; log_deg may be NULL. */
+int dgn_build_csr_host(int32_t n_nodes, int32_t n_edges, const int32_t* src, const int32_t* dst,
+                       int32_t* in_ptr, int32_t* in_src, int32_t* in_eid, int32_t* out_ptr, int32_t* out_slot,
+                       float* log_deg);
+
+/* Fused layer epilogue, rb/nets/dgn_layer.py:122-130:
+ *   z = y * snorm_n ; BatchNorm1d(z) (batch statistics, running stats updated) ; ReLU ; + residual.
+ * Two stream-ordered launches.  `stats` is a [DGN_NORM_WS_FLOATS(C)] fp32 workspace: on return it
+ * holds mean[C], rstd[C] (needed by the backward) followed by scratch.  n_rows_dev (optional, device
+ * int32) overrides n_rows so that padded batches can be replayed from a CUDA graph. */
+typedef struct {
+  int32_t n_rows, n_cols;
+  const float* y;          int32_t ld_y;     /* posttrans output                                        */
+  const float* snorm;      /* [n_rows] graph-norm factor per node, NULL = graph_norm off                */
+  const float* gamma;      /* [C] BatchNorm weight, NULL = batch_norm off                               */
+  const float* beta;       /* [C] BatchNorm bias                                                        */
+  float* running_mean;     /* [C] updated in place when training (NULL = skip)                          */
+  float* running_var;      /* [C]                                                                       */
+  float momentum, eps;
+  int32_t training;        /* 1: batch statistics; 0: running statistics                                */
+  int32_t relu;            /* 1: ReLU after the norm (complex/simple), 0: none (tower)                  */
+  const float* residual;   int32_t ld_res;   /* NULL = no residual                                      */
+  float* out;              int32_t ld_o;
+  float* stats;            /* [DGN_NORM_WS_FLOATS(C)] workspace, see above                              */
+  const int32_t* n_rows_dev;
+} DgnNormArgs;
+
+int dgn_norm_forward(const DgnNormArgs* a, void* stream);
+
+/* Backward of dgn_norm_forward: given g_out it writes d_y, d_residual (may alias nothing; NULL to
+ * skip), d_gamma, d_beta.  Needs the forward's `out` (for the ReLU mask) and `stats`. */
+typedef struct {
+  const float* g_out;      int32_t ld_go;
+  float* d_y;              int32_t ld_dy;
+  float* d_residual;       int32_t ld_dres;
+  float* d_gamma;          /* [C] */
+  float* d_beta;           /* [C] */
+  float* scratch;          /* [DGN_NORM_WS_FLOATS(C)] fp32 workspace                                    */
+} DgnNormGrad;
+
+int dgn_norm_backward(const DgnNormArgs* a, const DgnNormGrad* g, void* stream);
+
+/* Per-graph readout over contiguous node segments: op 0 = sum, 1 = mean, 2 = max.
+ * graph_ptr [n_graphs+1] device.  Replaces dgl.sum_nodes / mean_nodes / max_nodes. */
+int dgn_readout_forward(int32_t n_graphs, const int32_t* graph_ptr, int32_t n_cols, const float* h, int32_t ld_h,
+                        int32_t op, float* out, int32_t ld_o, void* stream);
+int dgn_readout_backward(int32_t n_graphs, const int32_t* graph_ptr, int32_t n_cols, const float* h, int32_t ld_h,
+                         const float* out, int32_t ld_o, int32_t op, const float* g_out, int32_t ld_go,
+                         float* d_h, int32_t ld_dh, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DGN_B200_H_ */

@@ -1,0 +1,223 @@
+"""GPU parity: the CUDA aggregation kernels, called through the C ABI, against the oracle and the
+golden vectors produced by the reference.  Tolerance (north star): |a-b| <= 1e-5 * max(1, ||ref||_inf)."""
+import numpy as np
+import pytest
+import torch
+
+from dgn_b200 import _lib
+from dgn_b200.data.synthetic import make_samples, avg_log_degree
+from dgn_b200.graph import BatchedGraph, collate
+from dgn_b200.nets.aggregators import AGGREGATORS
+from dgn_b200.nets.scalers import SCALERS
+from dgn_b200.ops import AggSpec, aggregate
+from tests.helpers import load_golden, assert_close
+from tests.oracle_ops import oracle_aggregate
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+S3 = ["identity", "amplification", "attenuation"]
+FULL = "mean max min std dir1-dx dir2-dx dir1-dx-no-abs dir2-dx-no-abs dir1-av dir2-av".split()
+
+
+@pytest.mark.parametrize("name", sorted(load_golden("aggregators")["names"].tolist()))
+def test_registry_callable_matches_reference_golden(name):
+    """AGGREGATORS[name](h, eig_s, eig_d, h_in) on the mailboxes the reference was run on (fwd + bwd)."""
+    gold = load_golden("aggregators")
+    for si in range(len(gold["shapes"])):
+        m = torch.tensor(gold["in/%d/msg" % si], device=DEV, requires_grad=True)
+        hi = torch.tensor(gold["in/%d/h_in" % si], device=DEV, requires_grad=True)
+        es = torch.tensor(gold["in/%d/eig_s" % si], device=DEV)
+        ed = torch.tensor(gold["in/%d/eig_d" % si], device=DEV)
+        y = AGGREGATORS[name](m, es, ed, hi)
+        y.backward(torch.tensor(gold["in/%d/gy" % si], device=DEV))
+        assert_close(y, gold["out/%d/%s/y" % (si, name)], what="%s y shape %d" % (name, si))
+        assert_close(m.grad, gold["out/%d/%s/dmsg" % (si, name)], what="%s dmsg shape %d" % (name, si))
+        dh = hi.grad if hi.grad is not None else torch.zeros_like(hi)
+        assert_close(dh, gold["out/%d/%s/dh_in" % (si, name)], what="%s dh_in shape %d" % (name, si))
+
+
+def _graph_case(kind, n_graphs, seed, F, K=None, **kw):
+    samples = make_samples(kind, n_graphs, seed=seed, **kw)
+    g, _ = collate(samples)
+    rng = np.random.default_rng(seed + 100)
+    N, E = g.number_of_nodes(), g.number_of_edges()
+    eig = g.ndata["eig"].numpy().copy()
+    if K is not None and eig.shape[1] < K:
+        eig = np.concatenate([eig, rng.standard_normal((N, K - eig.shape[1])).astype(np.float32)], 1)
+    t = lambda *s: torch.tensor(rng.standard_normal(s).astype(np.float32))
+    return g, samples, torch.tensor(eig), t(N, F), t(N, F), t(N, F), t(max(E, 1), F)[:E], avg_log_degree(samples)
+
+
+CASES = [
+    # kind, graphs, F, aggregators, scalers, K
+    ("zinc", 12, 16, FULL, S3, None),
+    ("zinc", 5, 7, ["mean", "sum", "std", "var", "dir1-dx", "dir3-av"], S3, None),               # scalar (VEC=1) path
+    ("cifar", 3, 12, ["mean", "max", "dir1-dx", "dir2-dx", "dir2-av", "dir1-dx-balanced"], ["identity"], None),
+    ("cifar", 2, 8, ["dir1-0.1", "dir2-neg-0.1", "dir1-dx-balanced", "dir2-dx-balanced", "min"], S3, None),
+    ("pattern", 2, 8, ["mean", "dir1-dx", "dir2-dx", "dir3-dx", "dir4-dx"], S3, None),           # long rows, k=4
+    ("zinc", 4, 20, ["mean", "dir1-av", "dir2-av", "dir3-av", "dir4-av", "dir1-dx", "dir2-dx", "dir3-dx",
+                     "dir4-dx-no-abs"], ["amplification"], None),                               # 8 slots, 1 scaler
+]
+
+
+@pytest.mark.parametrize("mode", ["source", "affine", "affine_edge", "dense"])
+@pytest.mark.parametrize("case", range(len(CASES)))
+def test_aggregate_matches_oracle(case, mode):
+    kind, ng, F, aggs, scs, K = CASES[case]
+    kw = dict(n_min=20, n_max=40) if kind in ("cifar", "pattern") else {}
+    g, samples, eig, h, P, Q, R, avg = _graph_case(kind, ng, 50 + case, F, K, **kw)
+    N, E = g.number_of_nodes(), g.number_of_edges()
+    src, dst = g.host("src").astype(np.int64), g.host("dst").astype(np.int64)
+    gy_w = len(aggs) * (len(scs) if len(scs) > 1 else 1) * F
+
+    leaves = {k: v.clone().requires_grad_(True) for k, v in dict(h=h, P=P, Q=Q, R=R).items()}
+    if mode == "source":
+        msg = leaves["h"][src]
+    elif mode == "affine":
+        msg = leaves["P"][src] + leaves["Q"][dst]
+    elif mode == "affine_edge":
+        msg = leaves["P"][src] + leaves["Q"][dst] + leaves["R"]
+    else:
+        msg = leaves["R"]
+    ref = oracle_aggregate(N, src, dst, eig, leaves["h"], msg, aggs, scs, avg)
+    gy = torch.tensor(np.random.default_rng(case).standard_normal((N, gy_w)).astype(np.float32))
+    ref.backward(gy)
+
+    g.to(DEV)
+    spec = AggSpec([AGGREGATORS[a] for a in aggs], [SCALERS[s] for s in scs], avg, F, eig.shape[1])
+    dl = {k: v.detach().clone().to(DEV).requires_grad_(True) for k, v in leaves.items()}
+    eig_d = eig.to(DEV)
+    if mode == "source":
+        out = aggregate(g, spec, _lib.MSG_SOURCE, dl["h"], eig_d, x=dl["h"])
+    elif mode == "affine":
+        out = aggregate(g, spec, _lib.MSG_AFFINE, dl["h"], eig_d, x=dl["P"], q=dl["Q"])
+    elif mode == "affine_edge":
+        out = aggregate(g, spec, _lib.MSG_AFFINE, dl["h"], eig_d, x=dl["P"], q=dl["Q"], r=dl["R"])
+    else:
+        out = aggregate(g, spec, _lib.MSG_DENSE, dl["h"], eig_d, r=dl["R"])
+    out.backward(gy.to(DEV))
+    assert_close(out, ref, what="out")
+    used = {"source": "h", "affine": "hPQ", "affine_edge": "hPQR", "dense": "hR"}[mode]
+    for k in ("h", "P", "Q", "R"):
+        if k in used or (k == "h"):
+            got = dl[k].grad if dl[k].grad is not None else torch.zeros_like(dl[k])
+            exp = leaves[k].grad if leaves[k].grad is not None else torch.zeros_like(leaves[k])
+            assert_close(got, exp, what="d" + k)
+
+
+def test_cat_input_and_isolated_nodes():
+    """h_copy fusion (torch.cat([h, agg])) and DGL's zero rows for in-degree-0 nodes."""
+    g, samples, eig, h, P, Q, R, avg = _graph_case("cifar", 3, 7, 8, n_min=20, n_max=30)
+    deg = np.diff(g.host("in_ptr"))
+    assert (deg == 0).any(), "case must contain isolated destinations"
+    g.to(DEV)
+    spec = AggSpec([AGGREGATORS[a] for a in ("mean", "max", "dir1-dx", "dir2-av")], [SCALERS[s] for s in S3], avg,
+                   8, 3)
+    hd = h.to(DEV).requires_grad_(True)
+    out = aggregate(g, spec, _lib.MSG_SOURCE, hd, eig.to(DEV), x=hd, cat_input=True)
+    assert out.shape == (g.number_of_nodes(), 8 + 3 * 4 * 8)
+    assert torch.equal(out[:, :8], hd.detach())
+    iso = torch.tensor(deg == 0, device=DEV)
+    assert torch.all(out[iso][:, 8:] == 0)
+    gy = torch.randn_like(out)
+    out.backward(gy)
+    # gradient through the copied columns is the identity
+    h2 = h.to(DEV).requires_grad_(True)
+    o2 = aggregate(g, spec, _lib.MSG_SOURCE, h2, eig.to(DEV), x=h2, cat_input=False)
+    o2.backward(gy[:, 8:].contiguous())
+    assert_close(hd.grad, h2.grad + gy[:, :8], what="dh with cat")
+
+
+def test_towers_group_layout_equals_per_tower_calls():
+    g, samples, eig, h, P, Q, R, avg = _graph_case("zinc", 6, 21, 24)
+    g.to(DEV)
+    aggs = [AGGREGATORS[a] for a in ("mean", "max", "min", "dir1-dx", "dir2-dx", "dir1-av", "dir2-av")]
+    T, Ft = 3, 8
+    one = AggSpec(aggs, [SCALERS["identity"]], avg, 24, 6, group_feat=Ft)
+    per = AggSpec(aggs, [SCALERS["identity"]], avg, Ft, 6)
+    hd, Pd, Qd, ed = h.to(DEV), P.to(DEV), Q.to(DEV), eig.to(DEV)
+    fused = aggregate(g, one, _lib.MSG_AFFINE, hd, ed, x=Pd, q=Qd, cat_input=True)
+    W = Ft + 7 * Ft
+    for t in range(T):
+        sl = slice(t * Ft, (t + 1) * Ft)
+        ref = aggregate(g, per, _lib.MSG_AFFINE, hd[:, sl], ed, x=Pd[:, sl], q=Qd[:, sl], cat_input=True)
+        assert torch.equal(fused[:, t * W:(t + 1) * W], ref)
+
+
+@pytest.mark.parametrize("kind,ng,F,aggs,K", [
+    ("zinc", 128, 64, FULL, 6),                                                           # BASELINE cfg2
+    ("cifar", 128, 65, ["mean", "dir1-dx", "dir2-dx"], 3),                                # cfg3 (unaligned F)
+    ("pattern", 24, 48, ["mean", "dir1-dx", "dir2-dx", "dir3-dx", "dir4-dx"], 5),         # cfg5 (reduced batch)
+])
+def test_baseline_shapes_match_oracle(kind, ng, F, aggs, K):
+    scs = ["identity"] if kind == "cifar" else S3
+    g, samples, eig, h, P, Q, R, avg = _graph_case(kind, ng, 5, F, K)
+    N = g.number_of_nodes()
+    src, dst = g.host("src").astype(np.int64), g.host("dst").astype(np.int64)
+    hl, Pl, Ql = (t.clone().requires_grad_(True) for t in (h, P, Q))
+    ref = oracle_aggregate(N, src, dst, eig, hl, Pl[src] + Ql[dst], aggs, scs, avg)
+    gy = torch.randn(ref.shape, generator=torch.Generator().manual_seed(1))
+    ref.backward(gy)
+    g.to(DEV)
+    spec = AggSpec([AGGREGATORS[a] for a in aggs], [SCALERS[s] for s in scs], avg, F, eig.shape[1])
+    hd, Pd, Qd = (t.to(DEV).requires_grad_(True) for t in (h, P, Q))
+    out = aggregate(g, spec, _lib.MSG_AFFINE, hd, eig.to(DEV), x=Pd, q=Qd)
+    out.backward(gy.to(DEV))
+    assert_close(out, ref, what="out")
+    assert_close(hd.grad, hl.grad, what="dh")
+    assert_close(Pd.grad, Pl.grad, what="dP")
+    assert_close(Qd.grad, Ql.grad, what="dQ")
+
+
+def test_full_size_properties_pattern_b256():
+    """BASELINE cfg5 size (1.5 M edges): size-independent properties instead of an oracle run."""
+    samples = make_samples("pattern", 256, seed=0)
+    g, _ = collate(samples)
+    avg = avg_log_degree(samples)
+    N, F = g.number_of_nodes(), 48
+    g.to(DEV)
+    eig = g.ndata["eig"]
+    gen = torch.Generator(device=DEV).manual_seed(0)
+    x1 = torch.randn(N, F, device=DEV, generator=gen)
+    x2 = torch.randn(N, F, device=DEV, generator=gen)
+    lin = [AGGREGATORS[a] for a in ("mean", "sum", "dir1-av", "dir2-dx-no-abs", "dir4-dx-no-abs")]
+    spec = AggSpec(lin, [SCALERS[s] for s in S3], avg, F, 5)
+
+    def run(x):
+        return aggregate(g, spec, _lib.MSG_SOURCE, x, eig, x=x)
+
+    # (1) linearity of the linear aggregators
+    a, b = 0.75, -1.25
+    y12 = run(a * x1 + b * x2)
+    assert_close(y12, a * run(x1) + b * run(x2), rel=2e-5, what="linearity")
+    # (2) scaler identity: amplification slab * attenuation slab == identity slab ^ 2
+    y = run(x1)
+    AF = len(lin) * F
+    assert_close(y[:, AF:2 * AF] * y[:, 2 * AF:], y[:, :AF] ** 2, rel=2e-5, what="amp*att")
+    # (3) mean == sum / D
+    deg = g.in_degrees().clamp(min=1).float().unsqueeze(1)
+    assert_close(y[:, :F], y[:, F:2 * F] / deg, what="mean vs sum")
+    # (4) adjoint identity <g, J v> == <J^T g, v> checks the backward against the forward
+    xv = x1.clone().requires_grad_(True)
+    out = run(xv)
+    gy = torch.randn(out.shape, device=DEV, generator=gen)
+    out.backward(gy)
+    lhs = (gy.double() * run(x2).double()).sum()
+    rhs = (xv.grad.double() * x2.double()).sum()
+    assert abs(lhs - rhs) <= 1e-4 * max(1.0, abs(lhs)), (float(lhs), float(rhs))
+    # (5) determinism: two launches give identical bits (no atomics)
+    xv2 = x1.clone().requires_grad_(True)
+    out2 = run(xv2)
+    out2.backward(gy)
+    assert torch.equal(out, out2) and torch.equal(xv.grad, xv2.grad)
+
+
+def test_too_many_slots_is_reported():
+    aggs = [AGGREGATORS["dir%d-%s" % (k, s)] for k in (1, 2, 3) for s in ("av", "dx", "dx-balanced")]
+    samples = make_samples("zinc", 2, seed=1)
+    g, _ = collate(samples)
+    g.to(DEV)
+    spec = AggSpec(aggs, [SCALERS["identity"]], 1.0, 8, 6)
+    x = torch.randn(g.number_of_nodes(), 8, device=DEV)
+    with pytest.raises(_lib.DgnError, match="unsupported"):
+        aggregate(g, spec, _lib.MSG_SOURCE, x, g.ndata["eig"], x=x)

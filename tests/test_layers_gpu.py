@@ -1,0 +1,124 @@
+"""GPU parity of whole layers / networks against the golden vectors the reference produced."""
+import numpy as np
+import pytest
+import torch
+
+from dgn_b200.graph import collate
+from dgn_b200.nets.dgn_layer import DGNLayer
+from dgn_b200.nets.molecules_graph_regression.dgn_net import DGNNet
+from tests.helpers import load_golden, samples_from_golden, state_from_golden, assert_close
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+LAYER_CASES = ["layer_simple", "layer_complex", "layer_complex_extra", "layer_complex_edge",
+               "layer_complex_1scaler", "layer_towers", "layer_simple_odd"]
+
+
+@pytest.mark.parametrize("case", LAYER_CASES)
+def test_layer_matches_reference_golden(case):
+    gold = load_golden(case)
+    g, _ = collate(samples_from_golden(gold))
+    g.to(DEV)
+    F, ed = int(gold["F"]), int(gold["edge_dim"])
+    layer = DGNLayer(F, F, 0.0, True, True, str(gold["aggregators"]), str(gold["scalers"]),
+                     {"log": torch.tensor(float(gold["avg_log"]))}, str(gold["type_net"]), True,
+                     towers=int(gold["towers"]), edge_features=ed > 0, edge_dim=ed).model
+    layer.load_state_dict(state_from_golden(gold, layer))
+    layer.to(DEV).train()
+    h = torch.tensor(gold["h"], device=DEV, requires_grad=True)
+    e = torch.tensor(gold["e"], device=DEV) if ed > 0 else None
+    y = layer(g, h, e, g.snorm_n)
+    y.backward(torch.tensor(gold["gy"], device=DEV))
+    assert_close(g.snorm_n, gold["snorm_n"], 1e-7, "snorm_n")
+    assert_close(y, gold["y"], what="y")
+    assert_close(h.grad, gold["dh"], what="dh")
+    for k, p in layer.named_parameters():
+        assert_close(p.grad, gold["grad/" + k], what=k)
+    for k, b in layer.named_buffers():
+        if "running" in k:
+            assert_close(b, gold["sd/" + k], what=k)
+        if "num_batches" in k:
+            assert int(b) == int(gold["sd/" + k])
+
+
+@pytest.mark.parametrize("case", ["net_zinc_complex", "net_zinc_simple", "net_zinc_edge"])
+def test_zinc_net_matches_reference_golden(case):
+    gold = load_golden(case)
+    g, _ = collate(samples_from_golden(gold))
+    g.to(DEV)
+    ef = bool(gold["edge_feat_flag"])
+    params = dict(num_atom_type=28, num_bond_type=4, hidden_dim=16, out_dim=16, in_feat_dropout=0.0, dropout=0.0,
+                  L=3, type_net=str(gold["type_net"]), pos_enc_dim=0, readout="mean", graph_norm=True,
+                  batch_norm=True, aggregators=str(gold["aggregators"]),
+                  scalers="identity amplification attenuation",
+                  avg_d={"log": torch.tensor(float(gold["avg_log"]))}, residual=True, edge_feat=ef,
+                  edge_dim=8 if ef else 0, pretrans_layers=1, posttrans_layers=1, device=DEV)
+    torch.manual_seed(int(gold["seed"]))
+    net = DGNNet(params)
+    for k, v in net.state_dict().items():          # same seed + construction order => the reference's init
+        if "running" not in k and "num_batches" not in k:
+            np.testing.assert_array_equal(v.numpy(), gold["sd/" + k], err_msg=k)
+    net.to(DEV).train()
+    scores = net(g, g.ndata["feat"], g.edata["feat"], g.snorm_n, None)
+    loss = net.loss(scores, torch.tensor(gold["targets"], device=DEV))
+    loss.backward()
+    assert_close(scores, gold["scores"], what="scores")
+    assert_close(loss, gold["loss"], what="loss")
+    for k, p in net.named_parameters():
+        got = p.grad if p.grad is not None else torch.zeros_like(p)
+        assert_close(got, gold["grad/" + k], what=k)
+
+
+def test_dense_pretrans_two_layers_matches_oracle():
+    """pretrans_layers=2 takes the materialised-message (DGN_MSG_DENSE) path."""
+    from oracle.directional_layers import DGNLayer as RefLayer
+    from oracle.graphs import collate_standin
+    from dgn_b200.data.synthetic import make_samples, avg_log_degree
+    samples = make_samples("zinc", 5, seed=9)
+    avg = avg_log_degree(samples)
+    args = (12, 12, 0.0, True, True, "mean max dir1-dx dir2-av", "identity amplification attenuation",
+            {"log": torch.tensor(avg)}, "complex", True)
+    torch.manual_seed(3)
+    ref = RefLayer(*args, edge_features=False, edge_dim=0, pretrans_layers=2, posttrans_layers=2).model.train()
+    mine = DGNLayer(*args, edge_features=False, edge_dim=0, pretrans_layers=2, posttrans_layers=2).model
+    mine.load_state_dict(ref.state_dict())
+    mine.to(DEV).train()
+    gs, _, snorm, _ = collate_standin(samples)
+    g, _ = collate(samples)
+    g.to(DEV)
+    h = torch.randn(g.number_of_nodes(), 12)
+    gy = torch.randn(g.number_of_nodes(), 12)
+    hr = h.clone().requires_grad_(True)
+    yr = ref(gs, hr, None, snorm)
+    yr.backward(gy)
+    hm = h.to(DEV).requires_grad_(True)
+    ym = mine(g, hm, None, g.snorm_n)
+    ym.backward(gy.to(DEV))
+    assert_close(ym, yr, what="y")
+    assert_close(hm.grad, hr.grad, what="dh")
+    for (k, p), (_, q) in zip(mine.named_parameters(), ref.named_parameters()):
+        assert_close(p.grad, q.grad, what=k)
+
+
+def test_eval_mode_uses_running_stats():
+    from oracle.directional_layers import DGNLayer as RefLayer
+    from oracle.graphs import collate_standin
+    from dgn_b200.data.synthetic import make_samples
+    samples = make_samples("zinc", 4, seed=2)
+    args = (8, 8, 0.0, True, True, "mean dir1-dx", "identity amplification attenuation", {"log": torch.tensor(1.1)},
+            "complex", True)
+    torch.manual_seed(0)
+    ref = RefLayer(*args, edge_features=False, edge_dim=0).model
+    ref.batchnorm_h.running_mean.uniform_(-0.01, 0.01)
+    ref.batchnorm_h.running_var.uniform_(0.5, 1.5)
+    mine = DGNLayer(*args, edge_features=False, edge_dim=0).model
+    mine.load_state_dict(ref.state_dict())
+    mine.to(DEV).eval()
+    ref.eval()
+    gs, _, snorm, _ = collate_standin(samples)
+    g, _ = collate(samples)
+    g.to(DEV)
+    h = torch.randn(g.number_of_nodes(), 8)
+    with torch.no_grad():
+        assert_close(mine(g, h.to(DEV), None, g.snorm_n), ref(gs, h, None, snorm), what="eval y")
