@@ -64,9 +64,15 @@ static int make_plan(const DgnAggSpec* spec, AggPlan& P) {
   return DGN_OK;
 }
 
-static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+// widest vector (in floats) that divides n / keeps pointer p aligned
+static inline int vw(long long n) { return (n % 4 == 0) ? 4 : (n % 2 == 0) ? 2 : 1; }
+static inline int vwp(const void* p) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  return (a % 16 == 0) ? 4 : (a % 8 == 0) ? 2 : 1;
+}
+static inline int imin(int a, int b) { return a < b ? a : b; }
 
-static int fill_args(const DgnGraph* g, const DgnAggSpec* spec, const DgnAggIO* io, KernelArgs& k, bool& vec4) {
+static int fill_args(const DgnGraph* g, const DgnAggSpec* spec, const DgnAggIO* io, KernelArgs& k, int& vec) {
   if (!g || !spec || !io) return DGN_ERR_INVALID;
   if (g->n_nodes < 0 || g->n_edges < 0 || !g->in_ptr || (g->n_edges > 0 && !g->in_src)) return DGN_ERR_INVALID;
   memset(&k, 0, sizeof(k));
@@ -88,13 +94,13 @@ static int fill_args(const DgnGraph* g, const DgnAggSpec* spec, const DgnAggIO* 
     case DGN_MSG_DENSE: if (!k.r) return DGN_ERR_INVALID; k.x = nullptr; k.q = nullptr; break;
     default: return DGN_ERR_INVALID;
   }
-  // 128-bit path needs every row start and every slab start 16 B aligned
-  vec4 = (P.F % 4 == 0) && (P.Fg % 4 == 0) && (k.ld_h % 4 == 0) && (k.ld_out % 4 == 0) && (k.out_gs % 4 == 0) &&
-         al16(k.h_in) && al16(k.out);
-  if (k.x) vec4 = vec4 && (k.ld_x % 4 == 0) && al16(k.x);
-  if (k.q) vec4 = vec4 && (k.ld_q % 4 == 0) && al16(k.q);
-  if (k.r) vec4 = vec4 && (k.ld_r % 4 == 0) && al16(k.r);
-  if (k.h_copy) vec4 = vec4 && (k.ld_hc % 4 == 0) && (k.hc_gs % 4 == 0) && al16(k.h_copy);
+  // vector width: every row start and every slab start must be aligned to it
+  vec = imin(imin(vw(P.F), vw(P.Fg)), imin(imin(vw(k.ld_h), vw(k.ld_out)), vw(k.out_gs)));
+  vec = imin(vec, imin(vwp(k.h_in), vwp(k.out)));
+  if (k.x) vec = imin(vec, imin(vw(k.ld_x), vwp(k.x)));
+  if (k.q) vec = imin(vec, imin(vw(k.ld_q), vwp(k.q)));
+  if (k.r) vec = imin(vec, imin(vw(k.ld_r), vwp(k.r)));
+  if (k.h_copy) vec = imin(vec, imin(imin(vw(k.ld_hc), vw(k.hc_gs)), vwp(k.h_copy)));
   return DGN_OK;
 }
 
@@ -119,10 +125,11 @@ extern "C" const char* dgn_last_cuda_error(void) { return cudaGetErrorString(g_d
 
 extern "C" int dgn_agg_forward(const DgnGraph* g, const DgnAggSpec* spec, const DgnAggIO* io, void* stream) {
   KernelArgs k;
-  bool vec4 = false;
-  if (int rc = fill_args(g, spec, io, k, vec4)) return rc;
-  k.plan.chunks = vec4 ? k.plan.F / 4 : k.plan.F;
-  const int rc = launch_forward(k, vec4, (cudaStream_t)stream);
+  int vec = 1;
+  if (int rc = fill_args(g, spec, io, k, vec)) return rc;
+  vec = choose_vec(vec, k.N, k.plan.F);
+  k.plan.chunks = k.plan.F / vec;
+  const int rc = launch_forward(k, vec, (cudaStream_t)stream);
   if (rc == DGN_ERR_CUDA) g_dgn_last_cuda = cudaPeekAtLastError();
   return rc;
 }
@@ -130,9 +137,9 @@ extern "C" int dgn_agg_forward(const DgnGraph* g, const DgnAggSpec* spec, const 
 extern "C" int dgn_agg_backward(const DgnGraph* g, const DgnAggSpec* spec, const DgnAggIO* io, const DgnAggGrad* grad,
                                 void* stream) {
   KernelArgs k;
-  bool vec4 = false;
+  int vec = 1;
   if (!grad || !grad->g_out) return DGN_ERR_INVALID;
-  if (int rc = fill_args(g, spec, io, k, vec4)) return rc;
+  if (int rc = fill_args(g, spec, io, k, vec)) return rc;
   k.g_out = grad->g_out;
   k.g_hcopy = grad->g_hcopy;
   k.d_q = grad->d_q; k.ld_dq = grad->ld_dq;
@@ -142,14 +149,15 @@ extern "C" int dgn_agg_backward(const DgnGraph* g, const DgnAggSpec* spec, const
   if (grad->d_x && (!grad->edge_ws || !g->out_ptr || (g->n_edges > 0 && !g->out_slot))) return DGN_ERR_INVALID;
   if (grad->fold_h_in && (!grad->d_x || !grad->d_h_in)) return DGN_ERR_INVALID;
   if (k.g_hcopy && !k.h_copy) { k.ld_hc = io->ld_hcopy; k.hc_gs = io->hcopy_group_stride; }
-  vec4 = vec4 && al16(k.g_out);
-  if (k.g_hcopy) vec4 = vec4 && al16(k.g_hcopy) && (k.ld_hc % 4 == 0) && (k.hc_gs % 4 == 0);
-  if (k.d_q) vec4 = vec4 && al16(k.d_q) && (k.ld_dq % 4 == 0);
-  if (k.d_r) vec4 = vec4 && al16(k.d_r) && (k.ld_dr % 4 == 0);
-  if (k.d_h) vec4 = vec4 && al16(k.d_h) && (k.ld_dh % 4 == 0);
-  if (grad->d_x) vec4 = vec4 && al16(grad->d_x) && (grad->ld_dx % 4 == 0) && al16(grad->edge_ws);
-  k.plan.chunks = vec4 ? k.plan.F / 4 : k.plan.F;
-  const int rc = launch_backward(k, vec4, grad->d_x, grad->ld_dx, grad->fold_h_in ? grad->d_h_in : nullptr,
+  vec = imin(vec, vwp(k.g_out));
+  if (k.g_hcopy) vec = imin(vec, imin(vwp(k.g_hcopy), imin(vw(k.ld_hc), vw(k.hc_gs))));
+  if (k.d_q) vec = imin(vec, imin(vwp(k.d_q), vw(k.ld_dq)));
+  if (k.d_r) vec = imin(vec, imin(vwp(k.d_r), vw(k.ld_dr)));
+  if (k.d_h) vec = imin(vec, imin(vwp(k.d_h), vw(k.ld_dh)));
+  if (grad->d_x) vec = imin(vec, imin(imin(vwp(grad->d_x), vw(grad->ld_dx)), vwp(grad->edge_ws)));
+  vec = choose_vec(vec, k.N, k.plan.F);
+  k.plan.chunks = k.plan.F / vec;
+  const int rc = launch_backward(k, vec, grad->d_x, grad->ld_dx, grad->fold_h_in ? grad->d_h_in : nullptr,
                                  grad->ld_dh, (cudaStream_t)stream);
   if (rc == DGN_ERR_CUDA) g_dgn_last_cuda = cudaPeekAtLastError();
   return rc;

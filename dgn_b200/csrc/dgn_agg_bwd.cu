@@ -66,18 +66,21 @@ __global__ void __launch_bounds__(256) agg_bwd_dst_kernel(const __grid_constant_
   }
 
   // ---- fold the S*A gradient slabs into per-column coefficients -----------------------------------
+  const float rD = __frcp_rn(fD);
   Vec<VEC> c0 = vfill<VEC>(0.f), c1 = vfill<VEC>(0.f), gmx = vfill<VEC>(0.f), gmn = vfill<VEC>(0.f);
   Vec<VEC> cs[NS > 0 ? NS : 1];
 #pragma unroll
   for (int s = 0; s < NS; ++s) cs[s] = vfill<VEC>(0.f);
 
   const float* grow = k.g_out + (size_t)v * k.ld_out + (size_t)tower * k.out_gs + cg;
+  const int scaler_stride = P.A * P.Fg;
   auto slab_grad = [&](int a) {               // G_a = sum_s coef_s * g_out[v, s, a, :]
     Vec<VEC> G = vfill<VEC>(0.f);
+    const float* src = grow + a * P.Fg;
 #pragma unroll
     for (int s = 0; s < DGN_MAX_SCALERS; ++s) {
       if (s < P.S) {
-        const Vec<VEC> gs = vload_stream<VEC>(grow + (size_t)(s * P.A + a) * P.Fg);
+        const Vec<VEC> gs = vload_stream<VEC>(src + s * scaler_stride);
 #pragma unroll
         for (int i = 0; i < VEC; ++i) G.a[i] = fmaf(coef[s], gs.a[i], G.a[i]);
       }
@@ -91,15 +94,15 @@ __global__ void __launch_bounds__(256) agg_bwd_dst_kernel(const __grid_constant_
     const Vec<VEC> G = slab_grad(a);
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
-      if (kind == DGN_AGG_MEAN) c0.a[i] += __fdiv_rn(G.a[i], fD);
+      if (kind == DGN_AGG_MEAN) c0.a[i] += G.a[i] * rD;
       else if (kind == DGN_AGG_SUM) c0.a[i] += G.a[i];
       else if (kind == DGN_AGG_MAX) gmx.a[i] += G.a[i];
       else if (kind == DGN_AGG_MIN) gmn.a[i] += G.a[i];
       else {
         // var = relu(t), t = E[m^2] - E[m]^2 ; dt/dm_u = 2 (m_u - mean) / D ; relu'(0) = 0
         float gv = (var.a[i] > 0.f) ? G.a[i] : 0.f;
-        if (kind == DGN_AGG_STD) gv = __fdiv_rn(gv, 2.f * sqrtf(var.a[i] + DGN_EPS));
-        const float two_over_d = __fdiv_rn(2.f * gv, fD);
+        if (kind == DGN_AGG_STD) gv *= 0.5f * rsqrtf(var.a[i] + DGN_EPS);
+        const float two_over_d = 2.f * gv * rD;
         c1.a[i] += two_over_d;
         c0.a[i] -= two_over_d * mean.a[i];
       }
@@ -118,17 +121,17 @@ __global__ void __launch_bounds__(256) agg_bwd_dst_kernel(const __grid_constant_
       const Vec<VEC>& A1 = R.acc[s];
       const float zw1 = R.zw[s], zabs1 = R.zabs[s];
       if (kind == DGN_AGG_DIR_AV) {
-        const float z = zabs1 + DGN_EPS;
+        const float rz = __frcp_rn(zabs1 + DGN_EPS);
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) cs[s].a[i] += __fdiv_rn(G.a[i], z);
+        for (int i = 0; i < VEC; ++i) cs[s].a[i] = fmaf(G.a[i], rz, cs[s].a[i]);
       } else if (kind == DGN_AGG_DIR_DX || kind == DGN_AGG_DIR_DX_NO_ABS) {
-        const float z = zabs1 + DGN_EPS;
-        const float wsum = __fdiv_rn(zw1, z);
+        const float rz = __frcp_rn(zabs1 + DGN_EPS);
+        const float wsum = zw1 * rz;
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
           float g = G.a[i];
-          if (kind == DGN_AGG_DIR_DX) g *= sign0(__fdiv_rn(A1.a[i], z) - wsum * hv.a[i]);
-          cs[s].a[i] += __fdiv_rn(g, z);
+          if (kind == DGN_AGG_DIR_DX) g *= sign0(A1.a[i] * rz - wsum * hv.a[i]);   // same expression as the forward
+          cs[s].a[i] = fmaf(g, rz, cs[s].a[i]);
           dh.a[i] -= wsum * g;
         }
       } else if (kind == DGN_AGG_DIR_DX_BALANCED) {
@@ -137,20 +140,21 @@ __global__ void __launch_bounds__(256) agg_bwd_dst_kernel(const __grid_constant_
           const int s2 = (s + 1 <= LAST) ? s + 1 : LAST;
           const Vec<VEC>& A2 = R.acc[s2];
           const float zw2 = R.zw[s2];
-          const float zp = zw1 + DGN_EPS, zn = zw2 + DGN_EPS;
-          const float wsum = 0.5f * (__fdiv_rn(zw1, zp) + __fdiv_rn(zw2, zn));
+          const float rp = 0.5f * __frcp_rn(zw1 + DGN_EPS), rn = 0.5f * __frcp_rn(zw2 + DGN_EPS);
+          const float wsum = zw1 * rp + zw2 * rn;
 #pragma unroll
           for (int i = 0; i < VEC; ++i) {
-            const float sv = 0.5f * (__fdiv_rn(A1.a[i], zp) + __fdiv_rn(A2.a[i], zn)) - wsum * hv.a[i];
+            const float sv = A1.a[i] * rp + A2.a[i] * rn - wsum * hv.a[i];
             const float g = G.a[i] * sign0(sv);
-            cs[s].a[i] += __fdiv_rn(0.5f * g, zp);
-            cs[s2].a[i] += __fdiv_rn(0.5f * g, zn);
+            cs[s].a[i] = fmaf(g, rp, cs[s].a[i]);
+            cs[s2].a[i] = fmaf(g, rn, cs[s2].a[i]);
             dh.a[i] -= wsum * g;
           }
         }
       } else {                                 // DGN_AGG_DIR_SOFTMAX
+        const float rz = __frcp_rn(zw1);
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) cs[s].a[i] += __fdiv_rn(G.a[i], zw1);
+        for (int i = 0; i < VEC; ++i) cs[s].a[i] = fmaf(G.a[i], rz, cs[s].a[i]);
       }
     }
   }
@@ -242,30 +246,32 @@ static int dispatch_slots(const KernelArgs& k, bool iso, cudaStream_t st) {
   return launch_dst<MODE, VEC, 8, false, false>(k, st);
 }
 
-int launch_backward(const KernelArgs& k, bool vec4, float* d_x, int ld_dx, const float* addend, int ld_add,
+template <int VEC>
+static int dispatch_mode(const KernelArgs& k, bool iso, cudaStream_t st) {
+  if (k.mode == DGN_MSG_SOURCE) return dispatch_slots<DGN_MSG_SOURCE, VEC>(k, iso, st);
+  if (k.mode == DGN_MSG_AFFINE) return dispatch_slots<DGN_MSG_AFFINE, VEC>(k, iso, st);
+  return dispatch_slots<DGN_MSG_DENSE, VEC>(k, iso, st);
+}
+
+int launch_backward(const KernelArgs& k, int vec, float* d_x, int ld_dx, const float* addend, int ld_add,
                     cudaStream_t st) {
   bool iso = false;
   for (int a = 0; a < k.plan.A; ++a) {
     const int kd = k.plan.agg_kind[a];
     iso |= (kd == DGN_AGG_MAX || kd == DGN_AGG_MIN || kd == DGN_AGG_STD || kd == DGN_AGG_VAR);
   }
-  int rc;
-  if (vec4) {
-    if (k.mode == DGN_MSG_SOURCE) rc = dispatch_slots<DGN_MSG_SOURCE, 4>(k, iso, st);
-    else if (k.mode == DGN_MSG_AFFINE) rc = dispatch_slots<DGN_MSG_AFFINE, 4>(k, iso, st);
-    else rc = dispatch_slots<DGN_MSG_DENSE, 4>(k, iso, st);
-  } else {
-    if (k.mode == DGN_MSG_SOURCE) rc = dispatch_slots<DGN_MSG_SOURCE, 1>(k, iso, st);
-    else if (k.mode == DGN_MSG_AFFINE) rc = dispatch_slots<DGN_MSG_AFFINE, 1>(k, iso, st);
-    else rc = dispatch_slots<DGN_MSG_DENSE, 1>(k, iso, st);
-  }
+  const int rc = vec == 4 ? dispatch_mode<4>(k, iso, st) : vec == 2 ? dispatch_mode<2>(k, iso, st)
+                                                                     : dispatch_mode<1>(k, iso, st);
   if (rc != DGN_OK || !d_x) return rc;
   const long long threads = (long long)k.N * k.plan.chunks;
   if (threads == 0) return DGN_OK;
   const int block = 256;
   const unsigned grid = (unsigned)((threads + block - 1) / block);
-  if (vec4)
+  if (vec == 4)
     agg_bwd_src_kernel<4><<<grid, block, 0, st>>>(k.N, k.plan.F, k.plan.chunks, k.out_ptr, k.out_slot, k.edge_ws, d_x,
+                                                  ld_dx, addend, ld_add);
+  else if (vec == 2)
+    agg_bwd_src_kernel<2><<<grid, block, 0, st>>>(k.N, k.plan.F, k.plan.chunks, k.out_ptr, k.out_slot, k.edge_ws, d_x,
                                                   ld_dx, addend, ld_add);
   else
     agg_bwd_src_kernel<1><<<grid, block, 0, st>>>(k.N, k.plan.F, k.plan.chunks, k.out_ptr, k.out_slot, k.edge_ws, d_x,

@@ -11,6 +11,8 @@
 // HBM roofline: compulsory bytes per node are  4*(r*F + K_u + 1) read  +  4*S*A*F written
 // (SURVEY.md 8(d)); the output stores dominate, so they are issued as streaming (evict-first)
 // 128-bit stores while the gathered operand rows stay L2-resident.
+#include <stdlib.h>
+
 #include "dgn_plan.cuh"
 
 namespace dgn {
@@ -55,6 +57,8 @@ __global__ void __launch_bounds__(256) agg_fwd_kernel(const __grid_constant__ Ke
   Vec<VEC> mean, var;
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
+    // IEEE division (not a reciprocal multiply): keeps var == 0 exactly for constant mailboxes, where
+    // the reference's relu / sqrt gradient is discontinuous
     mean.a[i] = __fdiv_rn(R.sum.a[i], fD);
     if constexpr (ISO) {
       const float msq = __fdiv_rn(R.sq.a[i], fD);
@@ -64,14 +68,16 @@ __global__ void __launch_bounds__(256) agg_fwd_kernel(const __grid_constant__ Ke
     }
   }
 
+  const int scaler_stride = P.A * P.Fg;            // distance between the slabs of two scalers
   auto store_scaled = [&](int a, const Vec<VEC>& y) {
+    float* dst = orow + a * P.Fg;
 #pragma unroll
     for (int s = 0; s < DGN_MAX_SCALERS; ++s) {
       if (s < P.S) {
         Vec<VEC> o;
 #pragma unroll
         for (int i = 0; i < VEC; ++i) o.a[i] = y.a[i] * coef[s];
-        vstore_stream<VEC>(orow + (size_t)(s * P.A + a) * P.Fg, o);
+        vstore_stream<VEC>(dst + s * scaler_stride, o);
       }
     }
   };
@@ -108,15 +114,15 @@ __global__ void __launch_bounds__(256) agg_fwd_kernel(const __grid_constant__ Ke
       const float zw1 = R.zw[s], zabs1 = R.zabs[s];
       Vec<VEC> y;
       if (kind == DGN_AGG_DIR_AV) {
-        const float z = zabs1 + DGN_EPS;
+        const float rz = __frcp_rn(zabs1 + DGN_EPS);
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) y.a[i] = __fdiv_rn(A1.a[i], z);
+        for (int i = 0; i < VEC; ++i) y.a[i] = A1.a[i] * rz;
       } else if (kind == DGN_AGG_DIR_DX || kind == DGN_AGG_DIR_DX_NO_ABS) {
-        const float z = zabs1 + DGN_EPS;
-        const float wsum = __fdiv_rn(zw1, z);
+        const float rz = __frcp_rn(zabs1 + DGN_EPS);
+        const float wsum = zw1 * rz;
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
-          const float sv = __fdiv_rn(A1.a[i], z) - wsum * hv.a[i];
+          const float sv = A1.a[i] * rz - wsum * hv.a[i];
           y.a[i] = (kind == DGN_AGG_DIR_DX) ? fabsf(sv) : sv;
         }
       } else if (kind == DGN_AGG_DIR_DX_BALANCED) {
@@ -125,17 +131,17 @@ __global__ void __launch_bounds__(256) agg_fwd_kernel(const __grid_constant__ Ke
           const int s2 = (s + 1 <= LAST) ? s + 1 : LAST;
           const Vec<VEC>& A2 = R.acc[s2];
           const float zw2 = R.zw[s2];
-          const float zp = zw1 + DGN_EPS, zn = zw2 + DGN_EPS;
-          const float wsum = 0.5f * (__fdiv_rn(zw1, zp) + __fdiv_rn(zw2, zn));
+          const float rp = 0.5f * __frcp_rn(zw1 + DGN_EPS), rn = 0.5f * __frcp_rn(zw2 + DGN_EPS);
+          const float wsum = zw1 * rp + zw2 * rn;
 #pragma unroll
-          for (int i = 0; i < VEC; ++i)
-            y.a[i] = fabsf(0.5f * (__fdiv_rn(A1.a[i], zp) + __fdiv_rn(A2.a[i], zn)) - wsum * hv.a[i]);
+          for (int i = 0; i < VEC; ++i) y.a[i] = fabsf(A1.a[i] * rp + A2.a[i] * rn - wsum * hv.a[i]);
         } else {
           y = vfill<VEC>(0.f);
         }
       } else {                                         // DGN_AGG_DIR_SOFTMAX
+        const float rz = __frcp_rn(zw1);
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) y.a[i] = __fdiv_rn(A1.a[i], zw1);
+        for (int i = 0; i < VEC; ++i) y.a[i] = A1.a[i] * rz;
       }
       store_scaled(a, y);
     }
@@ -176,17 +182,27 @@ static bool needs_iso(const AggPlan& P) {
   return false;
 }
 
-int launch_forward(const KernelArgs& k, bool vec4, cudaStream_t st) {
+template <int VEC>
+static int dispatch_mode(const KernelArgs& k, bool iso, cudaStream_t st) {
+  if (k.mode == DGN_MSG_SOURCE) return dispatch_slots<DGN_MSG_SOURCE, VEC>(k, iso, st);
+  if (k.mode == DGN_MSG_AFFINE) return dispatch_slots<DGN_MSG_AFFINE, VEC>(k, iso, st);
+  return dispatch_slots<DGN_MSG_DENSE, VEC>(k, iso, st);
+}
+
+int launch_forward(const KernelArgs& k, int vec, cudaStream_t st) {
   const bool iso = needs_iso(k.plan);
-  const int mode = k.mode;
-  if (vec4) {
-    if (mode == DGN_MSG_SOURCE) return dispatch_slots<DGN_MSG_SOURCE, 4>(k, iso, st);
-    if (mode == DGN_MSG_AFFINE) return dispatch_slots<DGN_MSG_AFFINE, 4>(k, iso, st);
-    return dispatch_slots<DGN_MSG_DENSE, 4>(k, iso, st);
-  }
-  if (mode == DGN_MSG_SOURCE) return dispatch_slots<DGN_MSG_SOURCE, 1>(k, iso, st);
-  if (mode == DGN_MSG_AFFINE) return dispatch_slots<DGN_MSG_AFFINE, 1>(k, iso, st);
-  return dispatch_slots<DGN_MSG_DENSE, 1>(k, iso, st);
+  if (vec == 4) return dispatch_mode<4>(k, iso, st);
+  if (vec == 2) return dispatch_mode<2>(k, iso, st);
+  return dispatch_mode<1>(k, iso, st);
+}
+
+int choose_vec(int max_vec, long long n_nodes, int n_feat) {
+  static const int forced = [] { const char* e = getenv("DGN_FORCE_VEC"); return e ? atoi(e) : 0; }();
+  if (forced == 1 || forced == 2 || forced == 4) return forced <= max_vec ? forced : max_vec;
+  const long long want = 148LL * 1536;                    // ~75 % of the resident-thread capacity
+  int vec = max_vec;
+  while (vec > 1 && n_nodes * n_feat / vec < want) vec >>= 1;
+  return vec;
 }
 
 }  // namespace dgn

@@ -68,16 +68,36 @@ __global__ void __launch_bounds__(kTX * kTY) norm_stats_kernel(const DgnNormArgs
   }
 }
 
-// merges the slab partials of one column in slab order; returns batch mean / biased variance
-__device__ __forceinline__ void merged_stats(const DgnNormArgs& a, int n, int col, float& mean, float& var) {
-  float cnt = 0.f, m2 = 0.f;
-  mean = 0.f;
-  for (int p = 0; p < kParts; ++p) {
+// Merges the kParts slab partials of the block's 32 columns: every (tx, ty) thread first folds the
+// partials ty, ty+kTY, ... (independent loads, issued together), then ty == 0 folds the kTY results
+// in a fixed order.  Result: batch mean / biased variance in s_mean / s_var (valid for ty == 0 readers
+// after the __syncthreads inside).
+__device__ __forceinline__ void merged_stats(const DgnNormArgs& a, int n, int col, float (&s_cnt)[kTY][kTX],
+                                             float (&s_mu)[kTY][kTX], float (&s_m2)[kTY][kTX], float& mean,
+                                             float& var) {
+  constexpr int PER = kParts / kTY;
+  float pm[PER], p2[PER], pn[PER];
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const int p = threadIdx.y + j * kTY;
     int r0, r1;
     slab(n, p, r0, r1);
     const float* part = a.stats + 2 * a.n_cols + (size_t)p * 2 * a.n_cols;
-    welford_merge(cnt, mean, m2, (float)(r1 - r0), part[col], part[a.n_cols + col]);
+    pn[j] = (float)(r1 - r0);
+    pm[j] = (col < a.n_cols) ? part[col] : 0.f;
+    p2[j] = (col < a.n_cols) ? part[a.n_cols + col] : 0.f;
   }
+  float cnt = 0.f, mu = 0.f, m2 = 0.f;
+#pragma unroll
+  for (int j = 0; j < PER; ++j) welford_merge(cnt, mu, m2, pn[j], pm[j], p2[j]);
+  s_cnt[threadIdx.y][threadIdx.x] = cnt;
+  s_mu[threadIdx.y][threadIdx.x] = mu;
+  s_m2[threadIdx.y][threadIdx.x] = m2;
+  __syncthreads();
+  if (threadIdx.y == 0) {
+    for (int j = 1; j < kTY; ++j) welford_merge(cnt, mu, m2, s_cnt[j][threadIdx.x], s_mu[j][threadIdx.x], s_m2[j][threadIdx.x]);
+  }
+  mean = mu;
   var = (cnt > 0.f) ? m2 / cnt : 0.f;
 }
 
@@ -85,25 +105,28 @@ __global__ void __launch_bounds__(kTX * kTY) norm_apply_kernel(const DgnNormArgs
   const int n = rows_of(a);
   const int col = blockIdx.y * kTX + threadIdx.x;
   __shared__ float s_mean[kTX], s_rstd[kTX];
-  if (threadIdx.y == 0 && col < a.n_cols && a.gamma) {
-    float mean, var;
-    if (a.training) {
-      merged_stats(a, n, col, mean, var);
-      if (blockIdx.x == 0 && a.running_mean) {        // nn.BatchNorm1d: unbiased variance in the running estimate
-        const float unb = (n > 1) ? var * ((float)n / (float)(n - 1)) : var;
-        a.running_mean[col] = (1.f - a.momentum) * a.running_mean[col] + a.momentum * mean;
-        a.running_var[col] = (1.f - a.momentum) * a.running_var[col] + a.momentum * unb;
+  __shared__ float s_cnt[kTY][kTX], s_mu[kTY][kTX], s_m2[kTY][kTX];
+  if (a.gamma) {
+    float mean = 0.f, var = 1.f;
+    if (a.training) merged_stats(a, n, col, s_cnt, s_mu, s_m2, mean, var);     // all threads (has a barrier)
+    if (threadIdx.y == 0 && col < a.n_cols) {
+      if (a.training) {
+        if (blockIdx.x == 0 && a.running_mean) {      // nn.BatchNorm1d: unbiased variance in the running estimate
+          const float unb = (n > 1) ? var * ((float)n / (float)(n - 1)) : var;
+          a.running_mean[col] = (1.f - a.momentum) * a.running_mean[col] + a.momentum * mean;
+          a.running_var[col] = (1.f - a.momentum) * a.running_var[col] + a.momentum * unb;
+        }
+      } else {
+        mean = a.running_mean[col];
+        var = a.running_var[col];
       }
-    } else {
-      mean = a.running_mean[col];
-      var = a.running_var[col];
-    }
-    const float rstd = 1.f / sqrtf(var + a.eps);
-    s_mean[threadIdx.x] = mean;
-    s_rstd[threadIdx.x] = rstd;
-    if (blockIdx.x == 0) {
-      a.stats[col] = mean;
-      a.stats[a.n_cols + col] = rstd;
+      const float rstd = 1.f / sqrtf(var + a.eps);
+      s_mean[threadIdx.x] = mean;
+      s_rstd[threadIdx.x] = rstd;
+      if (blockIdx.x == 0) {
+        a.stats[col] = mean;
+        a.stats[a.n_cols + col] = rstd;
+      }
     }
   }
   __syncthreads();
@@ -168,18 +191,32 @@ __global__ void __launch_bounds__(kTX * kTY) norm_bwd_apply_kernel(const DgnNorm
   const int n = rows_of(a);
   const int col = blockIdx.y * kTX + threadIdx.x;
   __shared__ float s_b[kTX], s_g[kTX];
-  if (threadIdx.y == 0 && col < a.n_cols) {
+  __shared__ float p_b[kTY][kTX], p_g[kTY][kTX];
+  {
+    constexpr int PER = kParts / kTY;
     float sb = 0.f, sg = 0.f;
-    for (int p = 0; p < kParts; ++p) {
-      const float* part = g.scratch + 2 * a.n_cols + (size_t)p * 2 * a.n_cols;
-      sb += part[col];
-      sg += part[a.n_cols + col];
+    if (col < a.n_cols) {
+      float vb[PER], vg[PER];
+#pragma unroll
+      for (int j = 0; j < PER; ++j) {                  // independent loads, fixed summation order
+        const float* part = g.scratch + 2 * a.n_cols + (size_t)(threadIdx.y + j * kTY) * 2 * a.n_cols;
+        vb[j] = part[col];
+        vg[j] = part[a.n_cols + col];
+      }
+#pragma unroll
+      for (int j = 0; j < PER; ++j) { sb += vb[j]; sg += vg[j]; }
     }
-    s_b[threadIdx.x] = sb;
-    s_g[threadIdx.x] = sg;
-    if (blockIdx.x == 0 && a.gamma) {
-      if (g.d_beta) g.d_beta[col] = sb;
-      if (g.d_gamma) g.d_gamma[col] = sg;
+    p_b[threadIdx.y][threadIdx.x] = sb;
+    p_g[threadIdx.y][threadIdx.x] = sg;
+    __syncthreads();
+    if (threadIdx.y == 0 && col < a.n_cols) {
+      for (int j = 1; j < kTY; ++j) { sb += p_b[j][threadIdx.x]; sg += p_g[j][threadIdx.x]; }
+      s_b[threadIdx.x] = sb;
+      s_g[threadIdx.x] = sg;
+      if (blockIdx.x == 0 && a.gamma) {
+        if (g.d_beta) g.d_beta[col] = sb;
+        if (g.d_gamma) g.d_gamma[col] = sg;
+      }
     }
   }
   __syncthreads();

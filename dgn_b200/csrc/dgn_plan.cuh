@@ -75,6 +75,9 @@ template <int VEC> __device__ __forceinline__ Vec<VEC> vload(const float* __rest
   if constexpr (VEC == 4) {
     const float4 t = __ldg(reinterpret_cast<const float4*>(p));
     r.a[0] = t.x; r.a[1] = t.y; r.a[2] = t.z; r.a[3] = t.w;
+  } else if constexpr (VEC == 2) {
+    const float2 t = __ldg(reinterpret_cast<const float2*>(p));
+    r.a[0] = t.x; r.a[1] = t.y;
   } else {
 #pragma unroll
     for (int i = 0; i < VEC; ++i) r.a[i] = __ldg(p + i);
@@ -88,6 +91,9 @@ template <int VEC> __device__ __forceinline__ Vec<VEC> vload_stream(const float*
   if constexpr (VEC == 4) {
     const float4 t = __ldcs(reinterpret_cast<const float4*>(p));
     r.a[0] = t.x; r.a[1] = t.y; r.a[2] = t.z; r.a[3] = t.w;
+  } else if constexpr (VEC == 2) {
+    const float2 t = __ldcs(reinterpret_cast<const float2*>(p));
+    r.a[0] = t.x; r.a[1] = t.y;
   } else {
 #pragma unroll
     for (int i = 0; i < VEC; ++i) r.a[i] = __ldcs(p + i);
@@ -98,6 +104,8 @@ template <int VEC> __device__ __forceinline__ Vec<VEC> vload_stream(const float*
 template <int VEC> __device__ __forceinline__ void vstore(float* __restrict__ p, const Vec<VEC>& v) {
   if constexpr (VEC == 4) {
     *reinterpret_cast<float4*>(p) = make_float4(v.a[0], v.a[1], v.a[2], v.a[3]);
+  } else if constexpr (VEC == 2) {
+    *reinterpret_cast<float2*>(p) = make_float2(v.a[0], v.a[1]);
   } else {
 #pragma unroll
     for (int i = 0; i < VEC; ++i) p[i] = v.a[i];
@@ -108,6 +116,8 @@ template <int VEC> __device__ __forceinline__ void vstore(float* __restrict__ p,
 template <int VEC> __device__ __forceinline__ void vstore_stream(float* __restrict__ p, const Vec<VEC>& v) {
   if constexpr (VEC == 4) {
     __stcs(reinterpret_cast<float4*>(p), make_float4(v.a[0], v.a[1], v.a[2], v.a[3]));
+  } else if constexpr (VEC == 2) {
+    __stcs(reinterpret_cast<float2*>(p), make_float2(v.a[0], v.a[1]));
   } else {
 #pragma unroll
     for (int i = 0; i < VEC; ++i) __stcs(p + i, v.a[i]);
@@ -238,8 +248,13 @@ __device__ __forceinline__ void scaler_coefs(const KernelArgs& k, int v, float (
 }
 
 // host side: kernels.cu
-int launch_forward(const KernelArgs& k, bool vec4, cudaStream_t st);
-int launch_backward(const KernelArgs& k, bool vec4, float* d_x, int ld_dx, const float* addend, int ld_add,
+// vec = columns per thread (4, 2 or 1): 4 needs 16 B alignment of every row/slab start, 2 needs 8 B
+int launch_forward(const KernelArgs& k, int vec, cudaStream_t st);
+int launch_backward(const KernelArgs& k, int vec, float* d_x, int ld_dx, const float* addend, int ld_add,
                     cudaStream_t st);
+
+// Picks the vector width: the widest the operands' alignment allows, narrowed while the launch would
+// not fill the 148 SMs (small batches are latency bound: more, shorter threads win).
+int choose_vec(int max_vec, long long n_nodes, int n_feat);
 
 }  // namespace dgn

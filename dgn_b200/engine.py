@@ -1,0 +1,99 @@
+"""Training-step runner: eager, or the whole step captured once into a CUDA graph.
+
+At the headline configuration (ZINC, 128 graphs, ~3 k nodes / ~6.4 k edges) a DGN step is a chain
+of ~100 small kernels: it is launch-latency bound, not bandwidth bound (hard part 1).
+``TrainStep(graphed=True)`` therefore records ``zero_grad -> forward -> loss -> backward ->
+(all-reduce) -> Adam`` ONCE and replays it per batch:
+
+* every batch is padded to a fixed ``capacity=(N_cap, E_cap)`` (``BatchedGraph(capacity=...)``): padding
+  nodes have no edges, the real node count travels with the batch in device memory
+  (``graph.meta``) and the fused norm kernels read it there, so BatchNorm statistics and all
+  gradients are those of the unpadded batch;
+* the packed batch is ONE host buffer; a step is one H2D copy into the static device buffer, one
+  graph launch and (optionally) one 4-byte D2H read of the loss.
+
+torch.cuda.graphs / torch.optim are plumbing; the captured kernels are the C-ABI kernels of
+``libdgn_b200.so`` plus the library GEMMs.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from .parallel import allreduce_mean_, flatten_parameters
+
+
+class TrainStep:
+    def __init__(self, net, template_graph, targets_like, lr=1e-3, weight_decay=0.0, graphed=True,
+                 node_key="feat", edge_key="feat", warmup_iters=3):
+        """``template_graph``: a (padded, for graphed=True) host ``BatchedGraph`` defining the batch layout."""
+        self.net = net
+        self.dev = next(net.parameters()).device
+        self.graphed = graphed
+        self.node_key, self.edge_key = node_key, edge_key
+        self.flat_p, self.flat_g = flatten_parameters(net)
+        self.opt = torch.optim.Adam([self.flat_p], lr=lr, weight_decay=weight_decay, fused=True,
+                                    capturable=graphed)
+        if graphed and not template_graph.padded:
+            raise ValueError("graphed=True needs batches padded to a fixed capacity (BatchedGraph(capacity=...))")
+        # static device-side batch: the graph object is re-bound onto this buffer once
+        self.blob = torch.empty(template_graph._host_blob.numel(), dtype=torch.uint8, device=self.dev)
+        template_graph.copy_into(self.blob, non_blocking=False)
+        self.g = template_graph.bind_device_blob(self.blob)
+        self.targets = torch.zeros(targets_like.shape, dtype=targets_like.dtype, device=self.dev)
+        self.targets.copy_(targets_like)
+        self.loss = torch.zeros((), device=self.dev)
+        self.launches_per_step = 0
+        self.cuda_graph = None
+        if graphed:
+            self._capture(warmup_iters)
+
+    # one optimisation step on whatever currently sits in the static batch buffers
+    def _step_body(self):
+        g = self.g
+        self.flat_g.zero_()
+        scores = self.net(g, g.ndata[self.node_key], g.edata[self.edge_key], g.snorm_n, None)
+        loss = self.net.loss(scores, self.targets)
+        loss.backward()
+        allreduce_mean_(self.flat_g)
+        self.opt.step()
+        return loss
+
+    def _capture(self, warmup_iters):
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(side):                 # lazy initialisation (cuBLAS, autograd) outside capture
+            for _ in range(warmup_iters):
+                self._step_body()
+        torch.cuda.current_stream(self.dev).wait_stream(side)
+        torch.cuda.synchronize(self.dev)
+        self.cuda_graph = torch.cuda.CUDAGraph()
+        before = ops.LAUNCHES
+        with torch.cuda.graph(self.cuda_graph):
+            loss = self._step_body()
+            self.loss.copy_(loss.detach())
+        self.launches_per_step = ops.LAUNCHES - before
+
+    # ------------------------------------------------------------------------------------------------
+    def load(self, host_graph, host_targets):
+        """Stage a batch: one H2D copy of the packed graph + the targets (pinned host memory)."""
+        if host_graph._host_blob.numel() != self.blob.numel():
+            raise ValueError("batch layout differs from the template (capacity / feature keys must match)")
+        self.blob.copy_(host_graph._host_blob, non_blocking=True)
+        self.targets.copy_(host_targets, non_blocking=True)
+
+    def load_device(self, device_blob, device_targets):
+        """Stage a batch that is already resident in HBM (device-to-device copy)."""
+        self.blob.copy_(device_blob, non_blocking=True)
+        self.targets.copy_(device_targets, non_blocking=True)
+
+    def run(self):
+        """One training step on the staged batch; returns the loss as a device scalar."""
+        if self.cuda_graph is not None:
+            self.cuda_graph.replay()
+            return self.loss
+        before = ops.LAUNCHES
+        loss = self._step_body()
+        self.launches_per_step = ops.LAUNCHES - before
+        self.loss.copy_(loss.detach())
+        return self.loss

@@ -63,18 +63,33 @@ class _Pack:
 class BatchedGraph:
     """A mini-batch of graphs with contiguous node ranges (block-diagonal adjacency)."""
 
-    _STRUCT = ("in_ptr", "in_src", "in_eid", "out_ptr", "out_slot", "graph_ptr", "src", "dst", "log_deg", "snorm_n")
+    _STRUCT = ("in_ptr", "in_src", "in_eid", "out_ptr", "out_slot", "graph_ptr", "src", "dst", "log_deg", "snorm_n",
+               "meta")
 
     def __init__(self, n_nodes, src, dst, batch_num_nodes=None, batch_num_edges=None, ndata=None, edata=None,
-                 pin_memory=None):
+                 pin_memory=None, capacity=None):
+        """``capacity=(N_cap, E_cap)`` pads the arrays to a fixed size (isolated padding nodes, unused
+        padding slots) so that batches of different sizes share one memory layout - the shape a
+        captured CUDA graph is replayed with.  ``number_of_nodes()`` then returns ``N_cap`` (the row
+        count every node tensor must have); ``n_real_nodes`` / ``n_real_edges`` are the true sizes and
+        ``meta`` = ``[n_real_nodes, n_real_edges, n_graphs, 0]`` travels to the device with the batch."""
         src = np.ascontiguousarray(np.asarray(src), dtype=np.int32)
         dst = np.ascontiguousarray(np.asarray(dst), dtype=np.int32)
         assert src.shape == dst.shape and src.ndim == 1
-        self._n, self._e = int(n_nodes), int(src.shape[0])
+        self.n_real_nodes, self.n_real_edges = int(n_nodes), int(src.shape[0])
+        self.padded = capacity is not None
+        if self.padded:
+            if capacity[0] < self.n_real_nodes or capacity[1] < self.n_real_edges:
+                raise ValueError("batch (%d nodes, %d edges) exceeds capacity %r"
+                                 % (self.n_real_nodes, self.n_real_edges, tuple(capacity)))
+            self._n, self._e = int(capacity[0]), int(capacity[1])
+        else:
+            self._n, self._e = self.n_real_nodes, self.n_real_edges
         self.batch_num_nodes = [int(x) for x in (batch_num_nodes if batch_num_nodes is not None else [self._n])]
         self.batch_num_edges = [int(x) for x in (batch_num_edges if batch_num_edges is not None else [self._e])]
-        assert sum(self.batch_num_nodes) == self._n
+        assert sum(self.batch_num_nodes) == self.n_real_nodes
         B = len(self.batch_num_nodes)
+        Nr, Er = self.n_real_nodes, self.n_real_edges
         ndata = dict(ndata or {})
         edata = dict(edata or {})
 
@@ -83,37 +98,45 @@ class BatchedGraph:
         for name, shape, dt in (("in_ptr", (N + 1,), np.int32), ("in_src", (E,), np.int32), ("in_eid", (E,), np.int32),
                                 ("out_ptr", (N + 1,), np.int32), ("out_slot", (E,), np.int32),
                                 ("graph_ptr", (B + 1,), np.int32), ("src", (E,), np.int32), ("dst", (E,), np.int32),
-                                ("log_deg", (N,), np.float32), ("snorm_n", (N, 1), np.float32)):
+                                ("log_deg", (N,), np.float32), ("snorm_n", (N, 1), np.float32),
+                                ("meta", (4,), np.int32)):
             pack.add(name, shape, dt)
         for k, v in ndata.items():
             v = np.asarray(v)
-            pack.add("n:" + k, v.shape, v.dtype)
+            pack.add("n:" + k, (N,) + v.shape[1:], v.dtype)
         for k, v in edata.items():
             v = np.asarray(v)
-            pack.add("e:" + k, v.shape, v.dtype)
+            pack.add("e:" + k, (E,) + v.shape[1:], v.dtype)
         self._pack = pack
 
         if pin_memory is None:
             pin_memory = torch.cuda.is_available()
         self._host_blob = torch.empty(max(pack.size, _ALIGN), dtype=torch.uint8, pin_memory=pin_memory)
+        if self.padded:
+            self._host_blob.zero_()
         hv = pack.host_views(self._host_blob.numpy())
-        hv["src"][:] = src
-        hv["dst"][:] = dst
+        hv["src"][:Er] = src
+        hv["dst"][:Er] = dst
         hv["graph_ptr"][0] = 0
         np.cumsum(self.batch_num_nodes, out=hv["graph_ptr"][1:])
         sizes = np.asarray(self.batch_num_nodes, dtype=np.float32)
         # collate(): snorm_n = sqrt(1 / n_g) per node  (rb/data/molecules.py:222-224)
-        hv["snorm_n"][:, 0] = np.repeat(np.sqrt(np.float32(1.0) / sizes), self.batch_num_nodes)
+        hv["snorm_n"][:Nr, 0] = np.repeat(np.sqrt(np.float32(1.0) / sizes), self.batch_num_nodes)
+        hv["meta"][:] = (Nr, Er, B, 0)
         for k, v in ndata.items():
-            hv["n:" + k][...] = np.asarray(v)
+            hv["n:" + k][:Nr] = np.asarray(v)
         for k, v in edata.items():
-            hv["e:" + k][...] = np.asarray(v)
+            hv["e:" + k][:Er] = np.asarray(v)
 
         def p(a):
             return a.ctypes.data_as(ctypes.c_void_p)
-        _lib.check(_lib.lib.dgn_build_csr_host(N, E, p(hv["src"]), p(hv["dst"]), p(hv["in_ptr"]), p(hv["in_src"]),
+        # the CSR is built over the REAL edges; padding nodes get empty in/out ranges at the end
+        _lib.check(_lib.lib.dgn_build_csr_host(Nr, Er, p(hv["src"]), p(hv["dst"]), p(hv["in_ptr"]), p(hv["in_src"]),
                                                p(hv["in_eid"]), p(hv["out_ptr"]), p(hv["out_slot"]), p(hv["log_deg"])),
                    "dgn_build_csr_host")
+        if self.padded:
+            hv["in_ptr"][Nr + 1:] = Er
+            hv["out_ptr"][Nr + 1:] = Er
         self._host = hv
         self.device = torch.device("cpu")
         self._bind(pack.device_views(self._host_blob))
@@ -138,9 +161,26 @@ class BatchedGraph:
         self._bind(self._pack.device_views(blob))
         return self
 
+    def copy_into(self, device_blob: torch.Tensor, non_blocking=True):
+        """H2D copy of this batch into an existing device buffer of the same (padded) layout."""
+        device_blob.copy_(self._host_blob, non_blocking=non_blocking)
+
+    def bind_device_blob(self, blob: torch.Tensor):
+        """Make the device-side views point into ``blob`` (a static buffer replayed by a CUDA graph)."""
+        assert blob.numel() == self._host_blob.numel()
+        self.device = blob.device
+        self._blob = blob
+        self._bind(self._pack.device_views(blob))
+        return self
+
     @property
     def h2d_bytes(self) -> int:
         return int(self._pack.size)
+
+    @property
+    def n_rows_dev(self):
+        """Device pointer to the real node count (None when the batch is not padded)."""
+        return self._t["meta"] if (self.padded and self.device.type == "cuda") else None
 
     # ---- DGL-like surface ----------------------------------------------------------------------
     def number_of_nodes(self):
@@ -188,7 +228,7 @@ class BatchedGraph:
         return int((p[1:] - p[:-1]).max()) if self._n else 0
 
 
-def collate(samples, node_key="feat", edge_key="feat", extra_ndata=()):
+def collate(samples, node_key="feat", edge_key="feat", extra_ndata=(), capacity=None):
     """``dataset.collate`` + ``dgl.batch`` (rb/data/molecules.py:219-230) for synthetic samples.
 
     Returns ``(graph, labels)``; ``graph.ndata`` holds ``feat`` and ``eig``, ``graph.edata`` holds
@@ -203,7 +243,8 @@ def collate(samples, node_key="feat", edge_key="feat", extra_ndata=()):
     for k in extra_ndata:
         ndata[k] = np.concatenate([np.asarray(s[k]) for s in samples], 0)
     edata = {edge_key: np.concatenate([np.asarray(s["edge_feat"]) for s in samples], 0)}
-    g = BatchedGraph(int(offs[-1]), src, dst, sizes, [len(s["src"]) for s in samples], ndata, edata)
+    g = BatchedGraph(int(offs[-1]), src, dst, sizes, [len(s["src"]) for s in samples], ndata, edata,
+                     capacity=capacity)
     if np.ndim(samples[0]["label"]) == 0:
         labels = torch.from_numpy(np.asarray([s["label"] for s in samples]))
     else:

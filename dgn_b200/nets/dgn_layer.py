@@ -77,9 +77,9 @@ class _FusedConv(nn.Module):
         M = self.pretrans(torch.cat(parts, dim=1))                # [E, F] in edge-id order
         return aggregate(g, spec, _lib.MSG_DENSE, h, eig, r=M, cat_input=cat_input)
 
-    def _epilogue(self, y, snorm_n, relu, residual):
+    def _epilogue(self, g, y, snorm_n, relu, residual):
         out = norm_act(y, snorm_n if self.graph_norm else None, self.batchnorm_h if self.batch_norm else None,
-                       self.training, relu, residual)
+                       self.training, relu, residual, getattr(g, "n_rows_dev", None))
         if self.dropout and self.training:
             out = F.dropout(out, self.dropout, training=True)
         return out
@@ -102,7 +102,7 @@ class DGNLayerComplex(_FusedConv):
 
     def forward(self, g, h, e, snorm_n):
         y = self.posttrans(self._pretrans_aggregate(g, h, e, cat_input=True))
-        return self._epilogue(y, snorm_n, relu=True, residual=h if self.residual else None)
+        return self._epilogue(g, y, snorm_n, relu=True, residual=h if self.residual else None)
 
 
 class DGNLayerSimple(_FusedConv):
@@ -121,7 +121,7 @@ class DGNLayerSimple(_FusedConv):
         eig = self._eig(g, h)
         agg = aggregate(g, self._spec(eig.shape[1]), _lib.MSG_SOURCE, h, eig, x=h)   # message = h[src]
         y = self.posttrans(agg)
-        return self._epilogue(y, snorm_n, relu=True, residual=h if self.residual else None)
+        return self._epilogue(g, y, snorm_n, relu=True, residual=h if self.residual else None)
 
 
 class DGNTower(_FusedConv):
@@ -138,7 +138,7 @@ class DGNTower(_FusedConv):
 
     def forward(self, g, h, e, snorm_n):
         y = self.posttrans(self._pretrans_aggregate(g, h, e, cat_input=True))
-        return self._epilogue(y, snorm_n, relu=False, residual=None)     # no ReLU / residual inside a tower
+        return self._epilogue(g, y, snorm_n, relu=False, residual=None)     # no ReLU / residual inside a tower
 
 
 class DGNLayerTower(nn.Module):

@@ -13,6 +13,14 @@ from . import _lib
 from ._lib import lib, check
 
 
+LAUNCHES = 0        # kernels of libdgn_b200.so launched so far (bench.py reports it as gpu_launches)
+
+
+def _count(n: int) -> None:
+    global LAUNCHES
+    LAUNCHES += n
+
+
 def _stream(t: torch.Tensor) -> int:
     return torch.cuda.current_stream(t.device).cuda_stream
 
@@ -62,6 +70,60 @@ class AggSpec:
         return self.S * self.A * self.Fg
 
 
+def _agg_io(mode, x, q, r, h_in, eig, out, lead, Wt, cat_input):
+    io = _lib.DgnAggIO()
+    io.msg_mode = mode
+    if x is not None:
+        io.x, io.ld_x = x.data_ptr(), x.stride(0)
+    if q is not None:
+        io.q, io.ld_q = q.data_ptr(), q.stride(0)
+    if r is not None:
+        io.r, io.ld_r = r.data_ptr(), r.stride(0)
+    io.h_in, io.ld_h = h_in.data_ptr(), h_in.stride(0)
+    if eig is not None:
+        io.eig, io.ld_eig = eig.data_ptr(), eig.stride(0)
+    io.out, io.ld_out, io.out_group_stride = out.data_ptr() + 4 * lead, out.stride(0), Wt
+    io.ld_hcopy, io.hcopy_group_stride = out.stride(0), Wt
+    if cat_input:
+        io.h_copy = out.data_ptr()
+    return io
+
+
+def agg_forward_raw(graph, spec, mode, x, q, r, h_in, eig, out, cat_input):
+    """dgn_agg_forward on pre-allocated tensors (fp32, unit inner stride).  ``out`` is
+    ``[N, T*((F_t if cat_input else 0) + S*A*F_t)]``."""
+    lead = spec.Fg if cat_input else 0
+    Wt = lead + spec.out_width
+    io = _agg_io(mode, x, q, r, h_in, eig, out, lead, Wt, cat_input)
+    check(lib.dgn_agg_forward(C.byref(graph.c_graph()), C.byref(spec.c), C.byref(io), _stream(h_in)),
+          "dgn_agg_forward")
+    _count(1)
+
+
+def agg_backward_raw(graph, spec, mode, x, q, r, h_in, eig, g_out, cat_input, d_x=None, d_q=None, d_r=None,
+                     d_h=None, edge_ws=None, fold_h_in=False):
+    """dgn_agg_backward on pre-allocated tensors; any of the d_* outputs may be None."""
+    lead = spec.Fg if cat_input else 0
+    Wt = lead + spec.out_width
+    io = _agg_io(mode, x, q, r, h_in, eig, g_out, lead, Wt, False)     # io.out is never written here
+    gr = _lib.DgnAggGrad()
+    gr.g_out = g_out.data_ptr() + 4 * lead
+    if cat_input:
+        gr.g_hcopy = g_out.data_ptr()
+    if d_x is not None:
+        gr.d_x, gr.ld_dx, gr.edge_ws = d_x.data_ptr(), d_x.stride(0), edge_ws.data_ptr()
+    if d_q is not None:
+        gr.d_q, gr.ld_dq = d_q.data_ptr(), d_q.stride(0)
+    if d_r is not None:
+        gr.d_r, gr.ld_dr = d_r.data_ptr(), d_r.stride(0)
+    if d_h is not None:
+        gr.d_h_in, gr.ld_dh = d_h.data_ptr(), d_h.stride(0)
+    gr.fold_h_in = 1 if fold_h_in else 0
+    check(lib.dgn_agg_backward(C.byref(graph.c_graph()), C.byref(spec.c), C.byref(io), C.byref(gr), _stream(h_in)),
+          "dgn_agg_backward")
+    _count(2 if d_x is not None else 1)
+
+
 class _Aggregate(torch.autograd.Function):
     """out = [h_in |] scalers(aggregators(messages)); see dgn_agg_forward / dgn_agg_backward."""
 
@@ -69,28 +131,11 @@ class _Aggregate(torch.autograd.Function):
     def forward(ctx, graph, spec, mode, cat_input, x, q, r, h_in, eig):
         _need_cuda(x, q, r, h_in, eig)
         x, q, r, h_in, eig = _f32c(x), _f32c(q), _f32c(r), _f32c(h_in), _f32c(eig)
-        N, F, Fg = graph.number_of_nodes(), spec.F, spec.Fg
-        T = F // Fg
-        lead = Fg if cat_input else 0
-        Wt = lead + spec.out_width                     # columns per tower block
+        N, T = graph.number_of_nodes(), spec.F // spec.Fg
+        Wt = (spec.Fg if cat_input else 0) + spec.out_width            # columns per tower block
         out = torch.empty((N, T * Wt), device=h_in.device, dtype=torch.float32)
-        io = _lib.DgnAggIO()
-        io.msg_mode = mode
-        if x is not None:
-            io.x, io.ld_x = x.data_ptr(), x.stride(0)
-        if q is not None:
-            io.q, io.ld_q = q.data_ptr(), q.stride(0)
-        if r is not None:
-            io.r, io.ld_r = r.data_ptr(), r.stride(0)
-        io.h_in, io.ld_h = h_in.data_ptr(), h_in.stride(0)
-        if eig is not None:
-            io.eig, io.ld_eig = eig.data_ptr(), eig.stride(0)
-        io.out, io.ld_out, io.out_group_stride = out.data_ptr() + 4 * lead, out.stride(0), Wt
-        if cat_input:
-            io.h_copy, io.ld_hcopy, io.hcopy_group_stride = out.data_ptr(), out.stride(0), Wt
-        check(lib.dgn_agg_forward(C.byref(graph.c_graph()), C.byref(spec.c), C.byref(io), _stream(h_in)),
-              "dgn_agg_forward")
-        ctx.graph, ctx.spec, ctx.mode, ctx.cat_input, ctx.lead, ctx.Wt = graph, spec, mode, cat_input, lead, Wt
+        agg_forward_raw(graph, spec, mode, x, q, r, h_in, eig, out, cat_input)
+        ctx.graph, ctx.spec, ctx.mode, ctx.cat_input = graph, spec, mode, cat_input
         ctx.save_for_backward(x, q, r, h_in, eig)
         ctx.same_x_h = x is not None and h_in.data_ptr() == x.data_ptr() and mode == _lib.MSG_SOURCE
         return out
@@ -103,44 +148,19 @@ class _Aggregate(torch.autograd.Function):
         N, E, F = graph.number_of_nodes(), graph.number_of_edges(), spec.F
         dev = h_in.device
         need = ctx.needs_input_grad        # (graph, spec, mode, cat_input, x, q, r, h_in, eig)
-        io = _lib.DgnAggIO()
-        io.msg_mode = mode
-        if x is not None:
-            io.x, io.ld_x = x.data_ptr(), x.stride(0)
-        if q is not None:
-            io.q, io.ld_q = q.data_ptr(), q.stride(0)
-        if r is not None:
-            io.r, io.ld_r = r.data_ptr(), r.stride(0)
-        io.h_in, io.ld_h = h_in.data_ptr(), h_in.stride(0)
-        if eig is not None:
-            io.eig, io.ld_eig = eig.data_ptr(), eig.stride(0)
-        io.out, io.ld_out, io.out_group_stride = 0, g_out.stride(0), ctx.Wt
-        io.ld_hcopy, io.hcopy_group_stride = g_out.stride(0), ctx.Wt
-        io.out = g_out.data_ptr() + 4 * ctx.lead          # never written by the backward
-
-        gr = _lib.DgnAggGrad()
-        gr.g_out = g_out.data_ptr() + 4 * ctx.lead
-        if ctx.cat_input:
-            gr.g_hcopy = g_out.data_ptr()
-        fold = ctx.same_x_h                                # simple layer: x and h_in are one tensor
-        d_x = d_q = d_r = d_h = None
-        want_x = x is not None and (need[4] or (fold and need[7]))
-        if want_x:
+        fold = ctx.same_x_h                # simple layer: x and h_in are one tensor
+        d_x = d_q = d_r = d_h = ws = None
+        if x is not None and (need[4] or (fold and need[7])):
             d_x = torch.empty((N, F), device=dev, dtype=torch.float32)
             ws = torch.empty((max(E, 1), F), device=dev, dtype=torch.float32)
-            gr.d_x, gr.ld_dx, gr.edge_ws = d_x.data_ptr(), F, ws.data_ptr()
         if q is not None and need[5]:
             d_q = torch.empty((N, F), device=dev, dtype=torch.float32)
-            gr.d_q, gr.ld_dq = d_q.data_ptr(), F
         if r is not None and need[6]:
             d_r = torch.empty((max(E, 1), F), device=dev, dtype=torch.float32)[:E]
-            gr.d_r, gr.ld_dr = d_r.data_ptr(), F
         if need[7] or fold:
             d_h = torch.empty((N, F), device=dev, dtype=torch.float32)
-            gr.d_h_in, gr.ld_dh = d_h.data_ptr(), F
-        gr.fold_h_in = 1 if (fold and want_x) else 0
-        check(lib.dgn_agg_backward(C.byref(graph.c_graph()), C.byref(spec.c), C.byref(io), C.byref(gr),
-                                   _stream(h_in)), "dgn_agg_backward")
+        agg_backward_raw(graph, spec, mode, x, q, r, h_in, eig, g_out, ctx.cat_input, d_x, d_q, d_r, d_h, ws,
+                         fold_h_in=fold and d_x is not None)
         if fold:
             # x and h_in are the same tensor: its whole gradient was folded into d_x (None counts as zero)
             return None, None, None, None, d_x, None, None, None, None
@@ -156,7 +176,8 @@ class _NormAct(torch.autograd.Function):
     """snorm * y -> BatchNorm1d -> ReLU -> + residual (rb/nets/dgn_layer.py:122-130) in the C-ABI kernels."""
 
     @staticmethod
-    def forward(ctx, y, snorm, gamma, beta, running_mean, running_var, momentum, eps, training, relu, residual):
+    def forward(ctx, y, snorm, gamma, beta, running_mean, running_var, momentum, eps, training, relu, residual,
+                n_rows_dev=None):
         _need_cuda(y)
         y = _f32c(y)
         N, Cn = y.shape
@@ -176,9 +197,12 @@ class _NormAct(torch.autograd.Function):
             residual = _f32c(residual)
             a.residual, a.ld_res = residual.data_ptr(), residual.stride(0)
         a.out, a.ld_o, a.stats = out.data_ptr(), Cn, stats.data_ptr()
+        if n_rows_dev is not None:
+            a.n_rows_dev = n_rows_dev.data_ptr()
         check(lib.dgn_norm_forward(C.byref(a), _stream(y)), "dgn_norm_forward")
+        _count(2 if (gamma is not None and training) else 1)
         ctx.args = a
-        ctx.keep = (y, snorm, gamma, beta, running_mean, running_var, residual, out, stats)
+        ctx.keep = (y, snorm, gamma, beta, running_mean, running_var, residual, out, stats, n_rows_dev)
         ctx.has_res, ctx.has_bn = residual is not None, gamma is not None
         return out
 
@@ -198,20 +222,24 @@ class _NormAct(torch.autograd.Function):
             d_beta = torch.empty(Cn, device=y.device, dtype=torch.float32)
             g.d_gamma, g.d_beta = d_gamma.data_ptr(), d_beta.data_ptr()
         check(lib.dgn_norm_backward(C.byref(a), C.byref(g), _stream(y)), "dgn_norm_backward")
+        _count(2)
         d_res = g_out if ctx.has_res else None       # identity branch
-        return d_y, None, d_gamma, d_beta, None, None, None, None, None, None, d_res
+        return d_y, None, d_gamma, d_beta, None, None, None, None, None, None, d_res, None
 
 
-def norm_act(y, snorm, bn, training, relu, residual):
-    """Fused layer epilogue.  ``bn`` is an ``nn.BatchNorm1d`` (or None when batch_norm is off)."""
+def norm_act(y, snorm, bn, training, relu, residual, n_rows_dev=None):
+    """Fused layer epilogue.  ``bn`` is an ``nn.BatchNorm1d`` (or None when batch_norm is off).
+
+    ``n_rows_dev`` (device int32, optional) is the number of REAL rows of a padded batch: statistics
+    run over those rows only and the padding rows of the output are written as zeros."""
     if bn is not None:
         if training and bn.track_running_stats and bn.num_batches_tracked is not None:
             bn.num_batches_tracked += 1
         use_batch = training or not bn.track_running_stats
         mom = 0.1 if bn.momentum is None else bn.momentum
         return _NormAct.apply(y, snorm, bn.weight, bn.bias, bn.running_mean, bn.running_var, mom, bn.eps,
-                              use_batch, relu, residual)
-    return _NormAct.apply(y, snorm, None, None, None, None, 0.1, 1e-5, False, relu, residual)
+                              use_batch, relu, residual, n_rows_dev)
+    return _NormAct.apply(y, snorm, None, None, None, None, 0.1, 1e-5, False, relu, residual, n_rows_dev)
 
 
 class _Readout(torch.autograd.Function):
@@ -223,6 +251,7 @@ class _Readout(torch.autograd.Function):
         out = torch.empty((B, Cn), device=h.device, dtype=torch.float32)
         check(lib.dgn_readout_forward(B, graph.graph_ptr.data_ptr(), Cn, h.data_ptr(), h.stride(0), op,
                                       out.data_ptr(), Cn, _stream(h)), "dgn_readout_forward")
+        _count(1)
         ctx.graph, ctx.op = graph, op
         ctx.save_for_backward(h, out)
         return out
@@ -236,6 +265,7 @@ class _Readout(torch.autograd.Function):
         check(lib.dgn_readout_backward(B, ctx.graph.graph_ptr.data_ptr(), Cn, h.data_ptr(), h.stride(0),
                                        out.data_ptr(), Cn, ctx.op, g_out.data_ptr(), Cn, d_h.data_ptr(),
                                        d_h.stride(0), _stream(h)), "dgn_readout_backward")
+        _count(1)
         return d_h, None, None
 
 
