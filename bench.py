@@ -243,7 +243,7 @@ def run_gpu_arm(args):
     from dgn_b200.data.synthetic import make_samples, avg_log_degree
     from dgn_b200.engine import TrainStep
     from dgn_b200.graph import collate
-    from dgn_b200.nets.molecules_graph_regression.dgn_net import DGNNet
+    from dgn_b200.task_nets.molecules_graph_regression import DGNNet
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

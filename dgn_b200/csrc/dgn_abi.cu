@@ -127,7 +127,7 @@ extern "C" int dgn_agg_forward(const DgnGraph* g, const DgnAggSpec* spec, const 
   KernelArgs k;
   int vec = 1;
   if (int rc = fill_args(g, spec, io, k, vec)) return rc;
-  vec = choose_vec(vec, k.N, k.plan.F);
+  vec = choose_vec(vec, k.N, k.plan.F, true);
   k.plan.chunks = k.plan.F / vec;
   const int rc = launch_forward(k, vec, (cudaStream_t)stream);
   if (rc == DGN_ERR_CUDA) g_dgn_last_cuda = cudaPeekAtLastError();
@@ -155,7 +155,7 @@ extern "C" int dgn_agg_backward(const DgnGraph* g, const DgnAggSpec* spec, const
   if (k.d_r) vec = imin(vec, imin(vwp(k.d_r), vw(k.ld_dr)));
   if (k.d_h) vec = imin(vec, imin(vwp(k.d_h), vw(k.ld_dh)));
   if (grad->d_x) vec = imin(vec, imin(imin(vwp(grad->d_x), vw(grad->ld_dx)), vwp(grad->edge_ws)));
-  vec = choose_vec(vec, k.N, k.plan.F);
+  vec = choose_vec(vec, k.N, k.plan.F, false);
   k.plan.chunks = k.plan.F / vec;
   const int rc = launch_backward(k, vec, grad->d_x, grad->ld_dx, grad->fold_h_in ? grad->d_h_in : nullptr,
                                  grad->ld_dh, (cudaStream_t)stream);

@@ -196,12 +196,13 @@ int launch_forward(const KernelArgs& k, int vec, cudaStream_t st) {
   return dispatch_mode<1>(k, iso, st);
 }
 
-int choose_vec(int max_vec, long long n_nodes, int n_feat) {
+int choose_vec(int max_vec, long long n_nodes, int n_feat, bool narrow_small) {
   static const int forced = [] { const char* e = getenv("DGN_FORCE_VEC"); return e ? atoi(e) : 0; }();
   if (forced == 1 || forced == 2 || forced == 4) return forced <= max_vec ? forced : max_vec;
-  const long long want = 148LL * 1536;                    // ~75 % of the resident-thread capacity
+  // Measured on B200 (profiles/README.md, cfg2 N*F = 190 k): the forward is fastest with 8 B lanes when
+  // 16 B lanes would leave most SMs with a single block; the backward always prefers the widest lanes.
   int vec = max_vec;
-  while (vec > 1 && n_nodes * n_feat / vec < want) vec >>= 1;
+  if (narrow_small && vec == 4 && n_nodes * n_feat / 4 < 148LL * 512) vec = 2;
   return vec;
 }
 

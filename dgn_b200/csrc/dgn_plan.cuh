@@ -253,8 +253,8 @@ int launch_forward(const KernelArgs& k, int vec, cudaStream_t st);
 int launch_backward(const KernelArgs& k, int vec, float* d_x, int ld_dx, const float* addend, int ld_add,
                     cudaStream_t st);
 
-// Picks the vector width: the widest the operands' alignment allows, narrowed while the launch would
-// not fill the 148 SMs (small batches are latency bound: more, shorter threads win).
-int choose_vec(int max_vec, long long n_nodes, int n_feat);
+// Picks the vector width: the widest the operands' alignment allows; `narrow_small` lets small launches
+// (that would not fill the 148 SMs) use 8 B lanes for more, shorter threads.  DGN_FORCE_VEC overrides.
+int choose_vec(int max_vec, long long n_nodes, int n_feat, bool narrow_small);
 
 }  // namespace dgn

@@ -5,7 +5,7 @@ Mirrors realworld_benchmark/nets/SBMs_node_classification/dgn_net.py:8-81.
 import torch
 import torch.nn as nn
 
-from dgn_b200.nets._task_common import build_layers
+from dgn_b200.task_nets._common import build_layers
 from dgn_b200.nets.mlp_readout_layer import MLPReadout
 
 

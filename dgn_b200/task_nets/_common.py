@@ -6,7 +6,7 @@ import torch.nn as nn
 
 from dgn_b200.ops import readout
 
-from .dgn_layer import DGNLayer
+from dgn_b200.nets.dgn_layer import DGNLayer
 
 
 def build_layers(net_params, **extra):

@@ -6,7 +6,7 @@ runs unmodified on top of ``nets.dgn_layer`` from this package, see INTEGRATION.
 """
 import torch.nn as nn
 
-from dgn_b200.nets._task_common import build_layers, graph_readout
+from dgn_b200.task_nets._common import build_layers, graph_readout
 from dgn_b200.nets.mlp_readout_layer import MLPReadout
 
 

@@ -4,7 +4,7 @@ Mirrors realworld_benchmark/nets/superpixels_graph_classification/dgn_net.py:7-7
 """
 import torch.nn as nn
 
-from dgn_b200.nets._task_common import build_layers, graph_readout
+from dgn_b200.task_nets._common import build_layers, graph_readout
 from dgn_b200.nets.mlp_readout_layer import MLPReadout
 
 

@@ -5,7 +5,7 @@ import torch
 from dgn_b200.data.synthetic import make_samples, avg_log_degree
 from dgn_b200.engine import TrainStep
 from dgn_b200.graph import collate
-from dgn_b200.nets.molecules_graph_regression.dgn_net import DGNNet
+from dgn_b200.task_nets.molecules_graph_regression import DGNNet
 from tests.helpers import assert_close
 
 pytestmark = pytest.mark.gpu
@@ -32,8 +32,12 @@ def test_graphed_padded_step_equals_eager_step(type_net):
     eager_net = _net(avg, type_net)
     eager = TrainStep(eager_net, collate(pools[0])[0], tg[0], lr=1e-3, graphed=False)
     graphed_net = _net(avg, type_net)
-    graphed = TrainStep(graphed_net, collate(pools[0], capacity=cap)[0], tg[0], lr=1e-3, graphed=True, warmup_iters=0)
+    # capture needs eager warm-up steps (lazy cuBLAS / autograd initialisation); they are real optimizer
+    # steps on batch 0 (2 warm-up + the captured one), so the eager model takes the same 3 steps first
+    graphed = TrainStep(graphed_net, collate(pools[0], capacity=cap)[0], tg[0], lr=1e-3, graphed=True, warmup_iters=2)
     assert graphed.launches_per_step > 0
+    for _ in range(3):
+        eager.run()
 
     losses = []
     for i in range(6):

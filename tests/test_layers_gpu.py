@@ -5,7 +5,7 @@ import torch
 
 from dgn_b200.graph import collate
 from dgn_b200.nets.dgn_layer import DGNLayer
-from dgn_b200.nets.molecules_graph_regression.dgn_net import DGNNet
+from dgn_b200.task_nets.molecules_graph_regression import DGNNet
 from tests.helpers import load_golden, samples_from_golden, state_from_golden, assert_close
 
 pytestmark = pytest.mark.gpu
