@@ -12,8 +12,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdgn_b200.so")
 
 MAX_AGG, MAX_SCALERS, MAX_SLOTS = 32, 4, 8
-ABI_VERSION = 1
-NORM_WS_PER_COL = 130
+ABI_VERSION = 2
+NORM_WS_PER_COL = 320
 
 # DgnAggKind / DgnScalerKind / DgnMsgMode
 AGG_MEAN, AGG_SUM, AGG_MAX, AGG_MIN, AGG_STD, AGG_VAR = 0, 1, 2, 3, 4, 5
@@ -39,7 +39,7 @@ class DgnAggSpec(C.Structure):
 
 class DgnAggIO(C.Structure):
     _fields_ = [("msg_mode", C.c_int32), ("x", C.c_void_p), ("ld_x", C.c_int32), ("q", C.c_void_p),
-                ("ld_q", C.c_int32), ("r", C.c_void_p), ("ld_r", C.c_int32), ("h_in", C.c_void_p),
+                ("ld_q", C.c_int32), ("q_bias", C.c_void_p), ("r", C.c_void_p), ("ld_r", C.c_int32), ("h_in", C.c_void_p),
                 ("ld_h", C.c_int32), ("eig", C.c_void_p), ("ld_eig", C.c_int32), ("out", C.c_void_p),
                 ("ld_out", C.c_int32), ("out_group_stride", C.c_int32), ("h_copy", C.c_void_p),
                 ("ld_hcopy", C.c_int32), ("hcopy_group_stride", C.c_int32)]
@@ -48,12 +48,13 @@ class DgnAggIO(C.Structure):
 class DgnAggGrad(C.Structure):
     _fields_ = [("g_out", C.c_void_p), ("g_hcopy", C.c_void_p), ("d_x", C.c_void_p), ("ld_dx", C.c_int32),
                 ("d_q", C.c_void_p), ("ld_dq", C.c_int32), ("d_r", C.c_void_p), ("ld_dr", C.c_int32),
-                ("d_h_in", C.c_void_p), ("ld_dh", C.c_int32), ("edge_ws", C.c_void_p), ("fold_h_in", C.c_int32)]
+                ("d_h_in", C.c_void_p), ("ld_dh", C.c_int32), ("d_h_addend", C.c_void_p), ("ld_dha", C.c_int32),
+                ("edge_ws", C.c_void_p), ("fold_h_in", C.c_int32)]
 
 
 class DgnNormArgs(C.Structure):
     _fields_ = [("n_rows", C.c_int32), ("n_cols", C.c_int32), ("y", C.c_void_p), ("ld_y", C.c_int32),
-                ("snorm", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("running_mean", C.c_void_p),
+                ("y_bias", C.c_void_p), ("snorm", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("running_mean", C.c_void_p),
                 ("running_var", C.c_void_p), ("momentum", C.c_float), ("eps", C.c_float), ("training", C.c_int32),
                 ("relu", C.c_int32), ("residual", C.c_void_p), ("ld_res", C.c_int32), ("out", C.c_void_p),
                 ("ld_o", C.c_int32), ("stats", C.c_void_p), ("n_rows_dev", C.c_void_p)]
@@ -62,7 +63,7 @@ class DgnNormArgs(C.Structure):
 class DgnNormGrad(C.Structure):
     _fields_ = [("g_out", C.c_void_p), ("ld_go", C.c_int32), ("d_y", C.c_void_p), ("ld_dy", C.c_int32),
                 ("d_residual", C.c_void_p), ("ld_dres", C.c_int32), ("d_gamma", C.c_void_p), ("d_beta", C.c_void_p),
-                ("scratch", C.c_void_p)]
+                ("d_bias", C.c_void_p), ("accumulate", C.c_int32), ("scratch", C.c_void_p)]
 
 
 # name -> (restype, argtypes); the CPU test-suite checks this table against include/dgn_b200.h
@@ -77,11 +78,13 @@ SIGNATURES = {
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dgn_norm_forward": (C.c_int, [C.POINTER(DgnNormArgs), C.c_void_p]),
     "dgn_norm_backward": (C.c_int, [C.POINTER(DgnNormArgs), C.POINTER(DgnNormGrad), C.c_void_p]),
+    "dgn_embedding_backward": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
+                                         C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "dgn_readout_forward": (C.c_int, [C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
                                       C.c_void_p, C.c_int32, C.c_void_p]),
     "dgn_readout_backward": (C.c_int, [C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
                                        C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
-                                       C.c_void_p]),
+                                       C.c_int32, C.c_void_p]),
 }
 
 

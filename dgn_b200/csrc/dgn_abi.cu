@@ -83,6 +83,7 @@ static int fill_args(const DgnGraph* g, const DgnAggSpec* spec, const DgnAggIO* 
   k.out_ptr = g->out_ptr; k.out_slot = g->out_slot; k.log_deg = g->log_deg;
   if (P.S > 1 && !g->log_deg) return DGN_ERR_INVALID;
   k.x = io->x; k.ld_x = io->ld_x; k.q = io->q; k.ld_q = io->ld_q; k.r = io->r; k.ld_r = io->ld_r;
+  k.q_bias = (io->msg_mode == DGN_MSG_AFFINE) ? io->q_bias : nullptr;
   k.h_in = io->h_in; k.ld_h = io->ld_h; k.eig = io->eig; k.ld_eig = io->ld_eig;
   k.out = io->out; k.ld_out = io->ld_out; k.out_gs = io->out_group_stride;
   k.h_copy = io->h_copy; k.ld_hc = io->ld_hcopy; k.hc_gs = io->hcopy_group_stride;
@@ -99,6 +100,7 @@ static int fill_args(const DgnGraph* g, const DgnAggSpec* spec, const DgnAggIO* 
   vec = imin(vec, imin(vwp(k.h_in), vwp(k.out)));
   if (k.x) vec = imin(vec, imin(vw(k.ld_x), vwp(k.x)));
   if (k.q) vec = imin(vec, imin(vw(k.ld_q), vwp(k.q)));
+  if (k.q_bias) vec = imin(vec, vwp(k.q_bias));
   if (k.r) vec = imin(vec, imin(vw(k.ld_r), vwp(k.r)));
   if (k.h_copy) vec = imin(vec, imin(imin(vw(k.ld_hc), vw(k.hc_gs)), vwp(k.h_copy)));
   return DGN_OK;
@@ -145,6 +147,7 @@ extern "C" int dgn_agg_backward(const DgnGraph* g, const DgnAggSpec* spec, const
   k.d_q = grad->d_q; k.ld_dq = grad->ld_dq;
   k.d_r = grad->d_r; k.ld_dr = grad->ld_dr;
   k.d_h = grad->d_h_in; k.ld_dh = grad->ld_dh;
+  k.d_h_add = grad->d_h_in ? grad->d_h_addend : nullptr; k.ld_dha = grad->ld_dha;
   k.edge_ws = grad->d_x ? grad->edge_ws : nullptr;
   if (grad->d_x && (!grad->edge_ws || !g->out_ptr || (g->n_edges > 0 && !g->out_slot))) return DGN_ERR_INVALID;
   if (grad->fold_h_in && (!grad->d_x || !grad->d_h_in)) return DGN_ERR_INVALID;
@@ -154,6 +157,7 @@ extern "C" int dgn_agg_backward(const DgnGraph* g, const DgnAggSpec* spec, const
   if (k.d_q) vec = imin(vec, imin(vwp(k.d_q), vw(k.ld_dq)));
   if (k.d_r) vec = imin(vec, imin(vwp(k.d_r), vw(k.ld_dr)));
   if (k.d_h) vec = imin(vec, imin(vwp(k.d_h), vw(k.ld_dh)));
+  if (k.d_h_add) vec = imin(vec, imin(vwp(k.d_h_add), vw(k.ld_dha)));
   if (grad->d_x) vec = imin(vec, imin(imin(vwp(grad->d_x), vw(grad->ld_dx)), vwp(grad->edge_ws)));
   vec = choose_vec(vec, k.N, k.plan.F, false);
   k.plan.chunks = k.plan.F / vec;

@@ -31,6 +31,11 @@ __global__ void __launch_bounds__(256) agg_bwd_dst_kernel(const __grid_constant_
 
   Vec<VEC> dh = vfill<VEC>(0.f);
   if (k.g_hcopy) dh = vload_stream<VEC>(k.g_hcopy + (size_t)v * k.ld_hc + (size_t)tower * k.hc_gs + cg);
+  if (k.d_h_add) {
+    const Vec<VEC> t = vload_stream<VEC>(k.d_h_add + (size_t)v * k.ld_dha + c);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) dh.a[i] += t.a[i];
+  }
 
   if (D == 0) {                      // isolated node: the forward wrote zeros, no gradient flows
     if (k.d_h) vstore<VEC>(k.d_h + (size_t)v * k.ld_dh + c, dh);
@@ -40,7 +45,14 @@ __global__ void __launch_bounds__(256) agg_bwd_dst_kernel(const __grid_constant_
 
   const Vec<VEC> hv = vload<VEC>(k.h_in + (size_t)v * k.ld_h + c);
   Vec<VEC> qv = vfill<VEC>(0.f);
-  if constexpr (MODE == DGN_MSG_AFFINE) qv = vload<VEC>(k.q + (size_t)v * k.ld_q + c);
+  if constexpr (MODE == DGN_MSG_AFFINE) {
+    qv = vload<VEC>(k.q + (size_t)v * k.ld_q + c);
+    if (k.q_bias) {
+      const Vec<VEC> bv = vload<VEC>(k.q_bias + c);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) qv.a[i] += bv.a[i];
+    }
+  }
 
   float ev[NS > 0 ? NS : 1], shift[NS > 0 ? NS : 1];
 #pragma unroll

@@ -41,7 +41,14 @@ __global__ void __launch_bounds__(256) agg_fwd_kernel(const __grid_constant__ Ke
   }
 
   Vec<VEC> qv = vfill<VEC>(0.f);
-  if constexpr (MODE == DGN_MSG_AFFINE) qv = vload<VEC>(k.q + (size_t)v * k.ld_q + c);
+  if constexpr (MODE == DGN_MSG_AFFINE) {
+    qv = vload<VEC>(k.q + (size_t)v * k.ld_q + c);
+    if (k.q_bias) {
+      const Vec<VEC> bv = vload<VEC>(k.q_bias + c);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) qv.a[i] += bv.a[i];
+    }
+  }
 
   float ev[NS > 0 ? NS : 1], shift[NS > 0 ? NS : 1];
 #pragma unroll

@@ -46,8 +46,9 @@ __global__ void __launch_bounds__(kTX * kTY) norm_stats_kernel(const DgnNormArgs
   slab(n, blockIdx.x, r0, r1);
   float cnt = 0.f, mean = 0.f, m2 = 0.f;
   if (col < a.n_cols) {
+    const float yb = a.y_bias ? a.y_bias[col] : 0.f;
     for (int r = r0 + threadIdx.y; r < r1; r += kTY) {
-      float z = a.y[(size_t)r * a.ld_y + col];
+      float z = a.y[(size_t)r * a.ld_y + col] + yb;
       if (a.snorm) z *= a.snorm[r];
       cnt += 1.f;
       const float d = z - mean;
@@ -134,11 +135,12 @@ __global__ void __launch_bounds__(kTX * kTY) norm_apply_kernel(const DgnNormArgs
   const float mean = a.gamma ? s_mean[threadIdx.x] : 0.f;
   const float rstd = a.gamma ? s_rstd[threadIdx.x] : 1.f;
   const float ga = a.gamma ? a.gamma[col] : 1.f, be = a.gamma ? a.beta[col] : 0.f;
+  const float yb = a.y_bias ? a.y_bias[col] : 0.f;
   const int rows_cap = a.n_rows;
   for (int r = blockIdx.x * kTY + threadIdx.y; r < rows_cap; r += gridDim.x * kTY) {
     float o = 0.f;
     if (r < n) {
-      float z = a.y[(size_t)r * a.ld_y + col];
+      float z = a.y[(size_t)r * a.ld_y + col] + yb;
       if (a.snorm) z *= a.snorm[r];
       o = (z - mean) * rstd * ga + be;
       if (a.relu) o = fmaxf(o, 0.f);
@@ -150,8 +152,8 @@ __global__ void __launch_bounds__(kTX * kTY) norm_apply_kernel(const DgnNormArgs
 
 // g1 = g_out * relu'(.) ; partial sums of g1 and g1 * xhat per (row slab, column)
 __device__ __forceinline__ float masked_grad(const DgnNormArgs& a, const DgnNormGrad& g, int r, int col, float mean,
-                                             float rstd, float ga, float be, float& xhat) {
-  float z = a.y[(size_t)r * a.ld_y + col];
+                                             float rstd, float ga, float be, float yb, float& xhat) {
+  float z = a.y[(size_t)r * a.ld_y + col] + yb;
   if (a.snorm) z *= a.snorm[r];
   xhat = (z - mean) * rstd;
   float go = g.g_out[(size_t)r * g.ld_go + col];
@@ -159,31 +161,41 @@ __device__ __forceinline__ float masked_grad(const DgnNormArgs& a, const DgnNorm
   return go;
 }
 
+constexpr int kBwdSums = 5;   // sum g1, sum g1*xhat, sum s*g1, sum s, sum s*xhat   (s = snorm_n)
+
 __global__ void __launch_bounds__(kTX * kTY) norm_bwd_reduce_kernel(const DgnNormArgs a, const DgnNormGrad g) {
   const int n = rows_of(a);
   const int col = blockIdx.y * kTX + threadIdx.x;
   int r0, r1;
   slab(n, blockIdx.x, r0, r1);
-  float sb = 0.f, sg = 0.f;
+  float acc[kBwdSums] = {0.f, 0.f, 0.f, 0.f, 0.f};
   if (col < a.n_cols) {
     const float mean = a.gamma ? a.stats[col] : 0.f, rstd = a.gamma ? a.stats[a.n_cols + col] : 1.f;
     const float ga = a.gamma ? a.gamma[col] : 1.f, be = a.gamma ? a.beta[col] : 0.f;
+    const float yb = a.y_bias ? a.y_bias[col] : 0.f;
     for (int r = r0 + threadIdx.y; r < r1; r += kTY) {
       float xhat;
-      const float g1 = masked_grad(a, g, r, col, mean, rstd, ga, be, xhat);
-      sb += g1;
-      sg = fmaf(g1, xhat, sg);
+      const float g1 = masked_grad(a, g, r, col, mean, rstd, ga, be, yb, xhat);
+      const float sn = a.snorm ? a.snorm[r] : 1.f;
+      acc[0] += g1;
+      acc[1] = fmaf(g1, xhat, acc[1]);
+      acc[2] = fmaf(sn, g1, acc[2]);
+      acc[3] += sn;
+      acc[4] = fmaf(sn, xhat, acc[4]);
     }
   }
-  __shared__ float s1[kTY][kTX], s2[kTY][kTX];
-  s1[threadIdx.y][threadIdx.x] = sb;
-  s2[threadIdx.y][threadIdx.x] = sg;
+  __shared__ float sh[kBwdSums][kTY][kTX];
+#pragma unroll
+  for (int q = 0; q < kBwdSums; ++q) sh[q][threadIdx.y][threadIdx.x] = acc[q];
   __syncthreads();
   if (threadIdx.y == 0 && col < a.n_cols) {
-    for (int j = 1; j < kTY; ++j) { sb += s1[j][threadIdx.x]; sg += s2[j][threadIdx.x]; }
-    float* part = g.scratch + 2 * a.n_cols + (size_t)blockIdx.x * 2 * a.n_cols;
-    part[col] = sb;
-    part[a.n_cols + col] = sg;
+    float* part = g.scratch + (size_t)blockIdx.x * kBwdSums * a.n_cols;
+#pragma unroll
+    for (int q = 0; q < kBwdSums; ++q) {
+      float t = acc[q];
+      for (int j = 1; j < kTY; ++j) t += sh[q][j][threadIdx.x];
+      part[q * a.n_cols + col] = t;
+    }
   }
 }
 
@@ -191,31 +203,49 @@ __global__ void __launch_bounds__(kTX * kTY) norm_bwd_apply_kernel(const DgnNorm
   const int n = rows_of(a);
   const int col = blockIdx.y * kTX + threadIdx.x;
   __shared__ float s_b[kTX], s_g[kTX];
-  __shared__ float p_b[kTY][kTX], p_g[kTY][kTX];
+  __shared__ float sh[kBwdSums][kTY][kTX];
   {
     constexpr int PER = kParts / kTY;
-    float sb = 0.f, sg = 0.f;
+    float acc[kBwdSums] = {0.f, 0.f, 0.f, 0.f, 0.f};
     if (col < a.n_cols) {
-      float vb[PER], vg[PER];
+      float v[PER][kBwdSums];
 #pragma unroll
       for (int j = 0; j < PER; ++j) {                  // independent loads, fixed summation order
-        const float* part = g.scratch + 2 * a.n_cols + (size_t)(threadIdx.y + j * kTY) * 2 * a.n_cols;
-        vb[j] = part[col];
-        vg[j] = part[a.n_cols + col];
+        const float* part = g.scratch + (size_t)(threadIdx.y + j * kTY) * kBwdSums * a.n_cols;
+#pragma unroll
+        for (int q = 0; q < kBwdSums; ++q) v[j][q] = part[q * a.n_cols + col];
       }
 #pragma unroll
-      for (int j = 0; j < PER; ++j) { sb += vb[j]; sg += vg[j]; }
+      for (int j = 0; j < PER; ++j)
+#pragma unroll
+        for (int q = 0; q < kBwdSums; ++q) acc[q] += v[j][q];
     }
-    p_b[threadIdx.y][threadIdx.x] = sb;
-    p_g[threadIdx.y][threadIdx.x] = sg;
+#pragma unroll
+    for (int q = 0; q < kBwdSums; ++q) sh[q][threadIdx.y][threadIdx.x] = acc[q];
     __syncthreads();
     if (threadIdx.y == 0 && col < a.n_cols) {
-      for (int j = 1; j < kTY; ++j) { sb += p_b[j][threadIdx.x]; sg += p_g[j][threadIdx.x]; }
-      s_b[threadIdx.x] = sb;
-      s_g[threadIdx.x] = sg;
-      if (blockIdx.x == 0 && a.gamma) {
-        if (g.d_beta) g.d_beta[col] = sb;
-        if (g.d_gamma) g.d_gamma[col] = sg;
+#pragma unroll
+      for (int q = 0; q < kBwdSums; ++q)
+        for (int j = 1; j < kTY; ++j) acc[q] += sh[q][j][threadIdx.x];
+      s_b[threadIdx.x] = acc[0];
+      s_g[threadIdx.x] = acc[1];
+      if (blockIdx.x == 0) {
+        const float keep = g.accumulate ? 1.f : 0.f;
+        if (a.gamma) {
+          if (g.d_beta) g.d_beta[col] = keep * g.d_beta[col] + acc[0];
+          if (g.d_gamma) g.d_gamma[col] = keep * g.d_gamma[col] + acc[1];
+        }
+        if (g.d_bias) {
+          // d_bias = sum_r d_y[r] with d_y = s * ga*rstd*(g1 - mb - xhat*mg) (training BN), s*ga*rstd*g1 (eval), s*g1 (no BN)
+          float db = acc[2];
+          if (a.gamma) {
+            const float ga = a.gamma[col], rstd = a.stats[a.n_cols + col];
+            const float inv_n = (n > 0) ? 1.f / (float)n : 0.f;
+            if (a.training) db = acc[2] - (acc[0] * inv_n) * acc[3] - (acc[1] * inv_n) * acc[4];
+            db *= ga * rstd;
+          }
+          g.d_bias[col] = keep * g.d_bias[col] + db;
+        }
       }
     }
   }
@@ -223,6 +253,7 @@ __global__ void __launch_bounds__(kTX * kTY) norm_bwd_apply_kernel(const DgnNorm
   if (col >= a.n_cols) return;
   const float mean = a.gamma ? a.stats[col] : 0.f, rstd = a.gamma ? a.stats[a.n_cols + col] : 1.f;
   const float ga = a.gamma ? a.gamma[col] : 1.f, be = a.gamma ? a.beta[col] : 0.f;
+  const float yb = a.y_bias ? a.y_bias[col] : 0.f;
   const float inv_n = (n > 0) ? 1.f / (float)n : 0.f;
   const float mb = (a.gamma && a.training) ? s_b[threadIdx.x] * inv_n : 0.f;
   const float mg = (a.gamma && a.training) ? s_g[threadIdx.x] * inv_n : 0.f;
@@ -230,7 +261,7 @@ __global__ void __launch_bounds__(kTX * kTY) norm_bwd_apply_kernel(const DgnNorm
     float dy = 0.f, dres = 0.f;
     if (r < n) {
       float xhat;
-      const float g1 = masked_grad(a, g, r, col, mean, rstd, ga, be, xhat);
+      const float g1 = masked_grad(a, g, r, col, mean, rstd, ga, be, yb, xhat);
       float dz = a.gamma ? ga * rstd * (g1 - mb - xhat * mg) : g1;
       if (a.snorm) dz *= a.snorm[r];
       dy = dz;
@@ -238,6 +269,35 @@ __global__ void __launch_bounds__(kTX * kTY) norm_bwd_apply_kernel(const DgnNorm
     }
     g.d_y[(size_t)r * g.ld_dy + col] = dy;
     if (g.d_residual) g.d_residual[(size_t)r * g.ld_dres + col] = dres;
+  }
+}
+
+// ---- embedding gradient --------------------------------------------------------------------------
+// block = 32 columns x 8 row-lanes; every (row-lane, vocab entry, column) cell of the shared tile is owned by
+// exactly one thread, so the accumulation order is fixed (row order per lane, then lanes 0..7).
+__global__ void __launch_bounds__(kTX * kTY) embedding_bwd_kernel(int n_rows, int C, int vocab,
+                                                                  const long long* __restrict__ idx,
+                                                                  const float* __restrict__ gsrc, int ld_g,
+                                                                  float* __restrict__ dw, int ld_w,
+                                                                  const int32_t* __restrict__ n_rows_dev) {
+  extern __shared__ float tile[];                      // [kTY][vocab][kTX]
+  const int n = n_rows_dev ? *n_rows_dev : n_rows;
+  const int col = blockIdx.x * kTX + threadIdx.x;
+  float* mine = tile + (size_t)threadIdx.y * vocab * kTX + threadIdx.x;
+  for (int t = 0; t < vocab; ++t) mine[t * kTX] = 0.f;
+  if (col < C) {
+    for (int r = threadIdx.y; r < n; r += kTY) {
+      const long long t = idx[r];
+      if (t >= 0 && t < vocab) mine[(int)t * kTX] += gsrc[(size_t)r * ld_g + col];
+    }
+  }
+  __syncthreads();
+  if (col < C) {
+    for (int t = threadIdx.y; t < vocab; t += kTY) {
+      float acc = 0.f;
+      for (int j = 0; j < kTY; ++j) acc += tile[((size_t)j * vocab + t) * kTX + threadIdx.x];
+      dw[(size_t)t * ld_w + col] += acc;
+    }
   }
 }
 
@@ -260,10 +320,15 @@ __global__ void readout_fwd_kernel(int n_graphs, const int32_t* __restrict__ gp,
 
 __global__ void readout_bwd_kernel(int n_graphs, const int32_t* __restrict__ gp, int C, const float* __restrict__ h,
                                    int ld_h, const float* __restrict__ out, int ld_o, int op,
-                                   const float* __restrict__ g_out, int ld_go, float* __restrict__ d_h, int ld_dh) {
+                                   const float* __restrict__ g_out, int ld_go, float* __restrict__ d_h, int ld_dh,
+                                   int n_rows_total) {
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
   const int gi = blockIdx.y;
-  if (col >= C || gi >= n_graphs) return;
+  if (col >= C) return;
+  if (gi == n_graphs) {                               // padding rows after the last graph get a zero gradient
+    for (int r = gp[n_graphs]; r < n_rows_total; ++r) d_h[(size_t)r * ld_dh + col] = 0.f;
+    return;
+  }
   const int r0 = gp[gi], r1 = gp[gi + 1];
   float g = g_out[(size_t)gi * ld_go + col];
   if (op == 1) g = g / (float)max(r1 - r0, 1);
@@ -324,6 +389,23 @@ extern "C" int dgn_norm_backward(const DgnNormArgs* a, const DgnNormGrad* g, voi
   return check_launch();
 }
 
+extern "C" int dgn_embedding_backward(int32_t n_rows, int32_t n_cols, int32_t vocab, const int64_t* idx,
+                                      const float* g, int32_t ld_g, float* d_weight, int32_t ld_w,
+                                      const int32_t* n_rows_dev, void* stream) {
+  if (n_rows < 0 || n_cols <= 0 || vocab <= 0 || !idx || !g || !d_weight) return DGN_ERR_INVALID;
+  const size_t smem = (size_t)kTY * vocab * kTX * sizeof(float);
+  if (smem > 200 * 1024) return DGN_ERR_UNSUPPORTED;
+  if (n_rows == 0) return DGN_OK;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(embedding_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_set = true;
+  }
+  embedding_bwd_kernel<<<(n_cols + kTX - 1) / kTX, dim3(kTX, kTY), smem, (cudaStream_t)stream>>>(
+      n_rows, n_cols, vocab, reinterpret_cast<const long long*>(idx), g, ld_g, d_weight, ld_w, n_rows_dev);
+  return check_launch();
+}
+
 extern "C" int dgn_readout_forward(int32_t n_graphs, const int32_t* graph_ptr, int32_t n_cols, const float* h,
                                    int32_t ld_h, int32_t op, float* out, int32_t ld_o, void* stream) {
   if (n_graphs < 0 || n_cols <= 0 || !graph_ptr || !h || !out || op < 0 || op > 2) return DGN_ERR_INVALID;
@@ -336,12 +418,12 @@ extern "C" int dgn_readout_forward(int32_t n_graphs, const int32_t* graph_ptr, i
 
 extern "C" int dgn_readout_backward(int32_t n_graphs, const int32_t* graph_ptr, int32_t n_cols, const float* h,
                                     int32_t ld_h, const float* out, int32_t ld_o, int32_t op, const float* g_out,
-                                    int32_t ld_go, float* d_h, int32_t ld_dh, void* stream) {
+                                    int32_t ld_go, float* d_h, int32_t ld_dh, int32_t n_rows_total, void* stream) {
   if (n_graphs < 0 || n_cols <= 0 || !graph_ptr || !g_out || !d_h || op < 0 || op > 2) return DGN_ERR_INVALID;
   if (op == 2 && (!h || !out)) return DGN_ERR_INVALID;
   if (n_graphs == 0) return DGN_OK;
   const int block = 64;
-  readout_bwd_kernel<<<dim3((n_cols + block - 1) / block, n_graphs), block, 0, (cudaStream_t)stream>>>(
-      n_graphs, graph_ptr, n_cols, h, ld_h, out, ld_o, op, g_out, ld_go, d_h, ld_dh);
+  readout_bwd_kernel<<<dim3((n_cols + block - 1) / block, n_graphs + 1), block, 0, (cudaStream_t)stream>>>(
+      n_graphs, graph_ptr, n_cols, h, ld_h, out, ld_o, op, g_out, ld_go, d_h, ld_dh, n_rows_total);
   return check_launch();
 }

@@ -45,6 +45,7 @@ struct KernelArgs {
   // forward operands
   const float* x; int ld_x;
   const float* q; int ld_q;
+  const float* q_bias;
   const float* r; int ld_r;
   const float* h_in; int ld_h;
   const float* eig; int ld_eig;
@@ -56,6 +57,7 @@ struct KernelArgs {
   float* d_q; int ld_dq;
   float* d_r; int ld_dr;
   float* d_h; int ld_dh;
+  const float* d_h_add; int ld_dha;
   float* edge_ws;
 };
 

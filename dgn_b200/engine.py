@@ -63,7 +63,7 @@ class TrainStep:
         side = torch.cuda.Stream(device=self.dev)
         side.wait_stream(torch.cuda.current_stream(self.dev))
         with torch.cuda.stream(side):                 # lazy initialisation (cuBLAS, autograd) outside capture
-            for _ in range(warmup_iters):
+            for _ in range(max(1, warmup_iters)):   # >= 1: lazy library initialisation must not be captured
                 self._step_body()
         torch.cuda.current_stream(self.dev).wait_stream(side)
         torch.cuda.synchronize(self.dev)

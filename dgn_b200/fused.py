@@ -1,0 +1,170 @@
+"""Whole-layer autograd node for the default DGN layer configuration.
+
+``pretrans_layers == posttrans_layers == 1`` (all five reference configs, rb/configs/*.json) makes a DGN
+layer a fixed chain
+
+    P = h W_src^T, Q = h W_dst^T                         2 library GEMMs (node level)
+    cat = [h | scalers(aggregators(P[u] + Q[v] + b))]    dgn_agg_forward      (b fused as q_bias)
+    y = cat W_post^T                                     1 library GEMM
+    out = relu(BN((y + b_post) * snorm_n)) + h           dgn_norm_forward     (b_post fused as y_bias)
+
+Running that chain through generic autograd costs ~50 kernels per layer and direction in glue: slice
+backward, gradient accumulation adds, bias-gradient reductions, fills.  This node owns the whole chain
+instead: 6 launches forward, ~11 backward, every GEMM writes (beta = 1) straight into its destination and -
+when the parameters already own ``.grad`` buffers, as under ``engine.TrainStep`` - parameter gradients are
+accumulated in place so autograd has nothing left to add.
+
+Same arithmetic as the op-level path in ``nets/dgn_layer.py`` (tests compare both against the golden
+vectors of the reference).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from .ops import (agg_backward_raw, agg_forward_raw, norm_backward_raw, norm_forward_raw, _f32c, _need_cuda)
+
+_ONES = {}
+
+
+def _ones(n, device):
+    key = (n, str(device))
+    t = _ONES.get(key)
+    if t is None:
+        t = torch.ones(n, device=device, dtype=torch.float32)
+        _ONES[key] = t
+    return t
+
+
+class LayerConfig:
+    """Non-tensor state of one fused layer call."""
+    __slots__ = ("graph", "spec", "eig", "snorm", "bn", "training", "relu", "residual", "direct", "in_dim",
+                 "has_pretrans", "params")
+
+    def __init__(self, graph, spec, eig, snorm, bn, training, relu, residual, direct, in_dim, has_pretrans, params):
+        self.graph, self.spec, self.eig, self.snorm, self.bn = graph, spec, eig, snorm, bn
+        self.training, self.relu, self.residual, self.direct = training, relu, residual, direct
+        self.in_dim, self.has_pretrans, self.params = in_dim, has_pretrans, params
+
+
+class _FusedLayer(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cfg, h, R, W_pre, b_pre, W_post, b_post, gamma, beta):
+        _need_cuda(h)
+        h = _f32c(h)
+        g, spec, Fi = cfg.graph, cfg.spec, cfg.in_dim
+        N, dev = h.shape[0], h.device
+        P = Q = None
+        if cfg.has_pretrans:
+            P = torch.mm(h, W_pre[:, :Fi].t())
+            Q = torch.mm(h, W_pre[:, Fi:2 * Fi].t())
+            cat = torch.empty((N, Fi + spec.out_width), device=dev, dtype=torch.float32)
+            agg_forward_raw(g, spec, _lib.MSG_AFFINE, P, Q, R, h, cfg.eig, cat, True, q_bias=b_pre)
+        else:                                            # simple layer: message = h[src], no h block
+            cat = torch.empty((N, spec.out_width), device=dev, dtype=torch.float32)
+            agg_forward_raw(g, spec, _lib.MSG_SOURCE, h, None, None, h, cfg.eig, cat, False)
+        y = torch.mm(cat, W_post.t())
+        Co = y.shape[1]
+        out = torch.empty((N, Co), device=dev, dtype=torch.float32)
+        stats = torch.empty(_lib.NORM_WS_PER_COL * Co, device=dev, dtype=torch.float32)
+        bn = cfg.bn
+        use_batch = True
+        if bn is not None:
+            if cfg.training and bn.track_running_stats and bn.num_batches_tracked is not None:
+                bn.num_batches_tracked += 1
+            use_batch = cfg.training or not bn.track_running_stats
+        nargs = norm_forward_raw(
+            y, out, stats, snorm=cfg.snorm, y_bias=b_post,
+            gamma=gamma if bn is not None else None, beta=beta if bn is not None else None,
+            running_mean=bn.running_mean if bn is not None else None,
+            running_var=bn.running_var if bn is not None else None,
+            momentum=(0.1 if bn is None or bn.momentum is None else bn.momentum),
+            eps=(1e-5 if bn is None else bn.eps), training=use_batch, relu=cfg.relu,
+            residual=h if cfg.residual else None, n_rows_dev=getattr(g, "n_rows_dev", None))
+        ctx.cfg, ctx.nargs = cfg, nargs
+        ctx.save_for_backward(h, R, P, Q, cat, y, stats, W_pre, b_pre, W_post, b_post, gamma, beta)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        cfg = ctx.cfg
+        h, R, P, Q, cat, y, stats, W_pre, b_pre, W_post, b_post, gamma, beta = ctx.saved_tensors
+        g, spec, Fi = cfg.graph, cfg.spec, cfg.in_dim
+        N, E, dev = h.shape[0], g.number_of_edges(), h.device
+        g_out = g_out.contiguous()
+        Co = y.shape[1]
+        pW_pre, pb_pre, pW_post, pb_post, pgamma, pbeta = cfg.params
+        direct = cfg.direct and all(p is None or p.grad is not None for p in cfg.params)
+
+        # ---- norm / BN / ReLU / residual ---------------------------------------------------------------------------
+        d_y = torch.empty_like(y)
+        scratch = torch.empty(_lib.NORM_WS_PER_COL * Co, device=dev, dtype=torch.float32)
+        has_bn = cfg.bn is not None
+        if direct:
+            d_gamma, d_beta, d_bpost = (pgamma.grad if has_bn else None), (pbeta.grad if has_bn else None), pb_post.grad
+        else:
+            d_gamma = torch.empty(Co, device=dev) if has_bn else None
+            d_beta = torch.empty(Co, device=dev) if has_bn else None
+            d_bpost = torch.empty(Co, device=dev)
+        norm_backward_raw(ctx.nargs, g_out, d_y, scratch, d_gamma, d_beta, d_bpost, accumulate=direct)
+
+        # ---- posttrans GEMM --------------------------------------------------------------------------------------------
+        d_cat = torch.mm(d_y, W_post)
+        if direct:
+            pW_post.grad.addmm_(d_y.t(), cat)
+            d_Wpost = None
+        else:
+            d_Wpost = torch.mm(d_y.t(), cat)
+
+        # ---- aggregation -----------------------------------------------------------------------------------------------
+        d_h = torch.empty((N, Fi), device=dev, dtype=torch.float32)
+        ws = torch.empty((max(E, 1), Fi), device=dev, dtype=torch.float32)
+        d_R = d_Wpre = d_bpre = None
+        resid = g_out if cfg.residual else None
+        if cfg.has_pretrans:
+            d_P = torch.empty((N, Fi), device=dev, dtype=torch.float32)
+            d_Q = torch.empty((N, Fi), device=dev, dtype=torch.float32)
+            if R is not None:
+                d_R = torch.empty((max(E, 1), Fi), device=dev, dtype=torch.float32)[:E]
+            agg_backward_raw(g, spec, _lib.MSG_AFFINE, P, Q, R, h, cfg.eig, d_cat, True, d_x=d_P, d_q=d_Q, d_r=d_R,
+                             d_h=d_h, edge_ws=ws, q_bias=b_pre, d_h_addend=resid)
+            d_h.addmm_(d_P, W_pre[:, :Fi])
+            d_h.addmm_(d_Q, W_pre[:, Fi:2 * Fi])
+            if direct:
+                gW = pW_pre.grad
+                gW[:, :Fi].addmm_(d_P.t(), h)
+                gW[:, Fi:2 * Fi].addmm_(d_Q.t(), h)
+                pb_pre.grad.addmv_(d_Q.t(), _ones(N, dev))
+            else:
+                d_Wpre = torch.zeros_like(W_pre)          # columns past 2F (edge features) get theirs via R
+                d_Wpre[:, :Fi] = torch.mm(d_P.t(), h)
+                d_Wpre[:, Fi:2 * Fi] = torch.mm(d_Q.t(), h)
+                d_bpre = torch.mv(d_Q.t(), _ones(N, dev))
+        else:
+            # x and h_in are the same tensor: the kernel folds d_h_in (+ residual) into the scattered gradient
+            d_x = torch.empty((N, Fi), device=dev, dtype=torch.float32)
+            agg_backward_raw(g, spec, _lib.MSG_SOURCE, h, None, None, h, cfg.eig, d_cat, False, d_x=d_x, d_h=d_h,
+                             edge_ws=ws, fold_h_in=True, d_h_addend=resid)
+            d_h = d_x
+        if direct:
+            return None, d_h, d_R, None, None, None, None, None, None
+        return None, d_h, d_R, d_Wpre, d_bpre, d_Wpost, d_bpost, d_gamma, d_beta
+
+
+def fused_layer(graph, spec, eig, h, R, pretrans_lin, posttrans_lin, bn, snorm, training, relu, residual, in_dim,
+                direct_grads=True):
+    """One DGN layer (complex / tower when ``pretrans_lin`` is given, simple otherwise) as a single autograd node.
+
+    ``direct_grads``: accumulate parameter gradients in place when every parameter already has ``.grad``."""
+    has_pre = pretrans_lin is not None
+    W_pre = pretrans_lin.weight if has_pre else None
+    b_pre = pretrans_lin.bias if has_pre else None
+    gamma = bn.weight if bn is not None else None
+    beta = bn.bias if bn is not None else None
+    params = (W_pre, b_pre, posttrans_lin.weight, posttrans_lin.bias, gamma, beta)
+    if snorm is not None:
+        snorm = snorm.reshape(-1)
+        if not snorm.is_contiguous():
+            snorm = snorm.contiguous()
+    cfg = LayerConfig(graph, spec, eig, snorm, bn, training, relu, residual, direct_grads, in_dim, has_pre, params)
+    return _FusedLayer.apply(cfg, h, R, W_pre, b_pre, posttrans_lin.weight, posttrans_lin.bias, gamma, beta)

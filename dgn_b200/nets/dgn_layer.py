@@ -23,6 +23,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from dgn_b200 import _lib
+from dgn_b200.fused import fused_layer
 from dgn_b200.ops import AggSpec, aggregate, norm_act, readout
 
 from .aggregators import AGGREGATORS
@@ -57,6 +58,32 @@ class _FusedConv(nn.Module):
     def _eig(g, like):
         eig = g.ndata["eig"]
         return eig if eig.device == like.device else eig.to(like.device)
+
+    @staticmethod
+    def _affine(mlp):
+        """The single Linear of a 1-layer MLP without activation / dropout / batch-norm, else None."""
+        fcs = mlp.fully_connected
+        if len(fcs) == 1 and fcs[0].activation is None and fcs[0].dropout is None and fcs[0].b_norm is None \
+                and fcs[0].linear.bias is not None:
+            return fcs[0].linear
+        return None
+
+    def _fused_forward(self, g, h, e, snorm_n, relu, residual):
+        """Whole layer as one autograd node (dgn_b200/fused.py) when pre/posttrans are single Linears."""
+        post = self._affine(self.posttrans)
+        pre = self._affine(self.pretrans) if hasattr(self, "pretrans") else None
+        if post is None or (hasattr(self, "pretrans") and pre is None) or not h.is_cuda:
+            return None
+        eig = self._eig(g, h)
+        R = None
+        if pre is not None and self.edge_features:
+            R = F.linear(e, pre.weight[:, 2 * self.in_dim:])            # per-edge term W_e ef, edge-id order
+        out = fused_layer(g, self._spec(eig.shape[1]), eig, h, R, pre, post,
+                          self.batchnorm_h if self.batch_norm else None, snorm_n if self.graph_norm else None,
+                          self.training, relu, residual, self.in_dim)
+        if self.dropout and self.training:
+            out = F.dropout(out, self.dropout, training=True)
+        return out
 
     def _pretrans_aggregate(self, g, h, e, cat_input=True):
         """messages = pretrans(cat(h_u, h_v[, ef])) (rb/nets/dgn_layer.py:75-80), then all aggregators."""
@@ -101,6 +128,9 @@ class DGNLayerComplex(_FusedConv):
             self.residual = False
 
     def forward(self, g, h, e, snorm_n):
+        out = self._fused_forward(g, h, e, snorm_n, relu=True, residual=bool(self.residual))
+        if out is not None:
+            return out
         y = self.posttrans(self._pretrans_aggregate(g, h, e, cat_input=True))
         return self._epilogue(g, y, snorm_n, relu=True, residual=h if self.residual else None)
 
@@ -118,6 +148,9 @@ class DGNLayerSimple(_FusedConv):
             self.residual = False
 
     def forward(self, g, h, e, snorm_n):
+        out = self._fused_forward(g, h, e, snorm_n, relu=True, residual=bool(self.residual))
+        if out is not None:
+            return out
         eig = self._eig(g, h)
         agg = aggregate(g, self._spec(eig.shape[1]), _lib.MSG_SOURCE, h, eig, x=h)   # message = h[src]
         y = self.posttrans(agg)
@@ -137,8 +170,11 @@ class DGNTower(_FusedConv):
                              out_size=out_dim, layers=posttrans_layers, mid_activation="relu", last_activation="none")
 
     def forward(self, g, h, e, snorm_n):
+        out = self._fused_forward(g, h, e, snorm_n, relu=False, residual=False)   # no ReLU / residual in a tower
+        if out is not None:
+            return out
         y = self.posttrans(self._pretrans_aggregate(g, h, e, cat_input=True))
-        return self._epilogue(g, y, snorm_n, relu=False, residual=None)     # no ReLU / residual inside a tower
+        return self._epilogue(g, y, snorm_n, relu=False, residual=None)
 
 
 class DGNLayerTower(nn.Module):

@@ -70,9 +70,11 @@ class AggSpec:
         return self.S * self.A * self.Fg
 
 
-def _agg_io(mode, x, q, r, h_in, eig, out, lead, Wt, cat_input):
+def _agg_io(mode, x, q, r, h_in, eig, out, lead, Wt, cat_input, q_bias=None):
     io = _lib.DgnAggIO()
     io.msg_mode = mode
+    if q_bias is not None:
+        io.q_bias = q_bias.data_ptr()
     if x is not None:
         io.x, io.ld_x = x.data_ptr(), x.stride(0)
     if q is not None:
@@ -89,23 +91,23 @@ def _agg_io(mode, x, q, r, h_in, eig, out, lead, Wt, cat_input):
     return io
 
 
-def agg_forward_raw(graph, spec, mode, x, q, r, h_in, eig, out, cat_input):
+def agg_forward_raw(graph, spec, mode, x, q, r, h_in, eig, out, cat_input, q_bias=None):
     """dgn_agg_forward on pre-allocated tensors (fp32, unit inner stride).  ``out`` is
     ``[N, T*((F_t if cat_input else 0) + S*A*F_t)]``."""
     lead = spec.Fg if cat_input else 0
     Wt = lead + spec.out_width
-    io = _agg_io(mode, x, q, r, h_in, eig, out, lead, Wt, cat_input)
+    io = _agg_io(mode, x, q, r, h_in, eig, out, lead, Wt, cat_input, q_bias)
     check(lib.dgn_agg_forward(C.byref(graph.c_graph()), C.byref(spec.c), C.byref(io), _stream(h_in)),
           "dgn_agg_forward")
     _count(1)
 
 
 def agg_backward_raw(graph, spec, mode, x, q, r, h_in, eig, g_out, cat_input, d_x=None, d_q=None, d_r=None,
-                     d_h=None, edge_ws=None, fold_h_in=False):
+                     d_h=None, edge_ws=None, fold_h_in=False, q_bias=None, d_h_addend=None):
     """dgn_agg_backward on pre-allocated tensors; any of the d_* outputs may be None."""
     lead = spec.Fg if cat_input else 0
     Wt = lead + spec.out_width
-    io = _agg_io(mode, x, q, r, h_in, eig, g_out, lead, Wt, False)     # io.out is never written here
+    io = _agg_io(mode, x, q, r, h_in, eig, g_out, lead, Wt, False, q_bias)     # io.out is never written here
     gr = _lib.DgnAggGrad()
     gr.g_out = g_out.data_ptr() + 4 * lead
     if cat_input:
@@ -118,6 +120,8 @@ def agg_backward_raw(graph, spec, mode, x, q, r, h_in, eig, g_out, cat_input, d_
         gr.d_r, gr.ld_dr = d_r.data_ptr(), d_r.stride(0)
     if d_h is not None:
         gr.d_h_in, gr.ld_dh = d_h.data_ptr(), d_h.stride(0)
+        if d_h_addend is not None:
+            gr.d_h_addend, gr.ld_dha = d_h_addend.data_ptr(), d_h_addend.stride(0)
     gr.fold_h_in = 1 if fold_h_in else 0
     check(lib.dgn_agg_backward(C.byref(graph.c_graph()), C.byref(spec.c), C.byref(io), C.byref(gr), _stream(h_in)),
           "dgn_agg_backward")
@@ -172,6 +176,46 @@ def aggregate(graph, spec: AggSpec, mode: int, h_in, eig, x=None, q=None, r=None
     return _Aggregate.apply(graph, spec, mode, cat_input, x, q, r, h_in, eig)
 
 
+def norm_forward_raw(y, out, stats, snorm=None, y_bias=None, gamma=None, beta=None, running_mean=None,
+                     running_var=None, momentum=0.1, eps=1e-5, training=True, relu=True, residual=None,
+                     n_rows_dev=None):
+    """dgn_norm_forward on pre-allocated tensors; returns the filled DgnNormArgs (needed by the backward)."""
+    N, Cn = y.shape
+    a = _lib.DgnNormArgs()
+    a.n_rows, a.n_cols, a.y, a.ld_y = N, Cn, y.data_ptr(), y.stride(0)
+    if y_bias is not None:
+        a.y_bias = y_bias.data_ptr()
+    if snorm is not None:
+        a.snorm = snorm.data_ptr()
+    if gamma is not None:
+        a.gamma, a.beta = gamma.data_ptr(), beta.data_ptr()
+        if running_mean is not None:
+            a.running_mean, a.running_var = running_mean.data_ptr(), running_var.data_ptr()
+    a.momentum, a.eps, a.training, a.relu = momentum, eps, int(training), int(relu)
+    if residual is not None:
+        a.residual, a.ld_res = residual.data_ptr(), residual.stride(0)
+    a.out, a.ld_o, a.stats = out.data_ptr(), out.stride(0), stats.data_ptr()
+    if n_rows_dev is not None:
+        a.n_rows_dev = n_rows_dev.data_ptr()
+    check(lib.dgn_norm_forward(C.byref(a), _stream(y)), "dgn_norm_forward")
+    _count(2 if (gamma is not None and training) else 1)
+    return a
+
+
+def norm_backward_raw(a, g_out, d_y, scratch, d_gamma=None, d_beta=None, d_bias=None, accumulate=False):
+    g = _lib.DgnNormGrad()
+    g.g_out, g.ld_go, g.d_y, g.ld_dy, g.scratch = (g_out.data_ptr(), g_out.stride(0), d_y.data_ptr(), d_y.stride(0),
+                                                  scratch.data_ptr())
+    if d_gamma is not None:
+        g.d_gamma, g.d_beta = d_gamma.data_ptr(), d_beta.data_ptr()
+    if d_bias is not None:
+        g.d_bias = d_bias.data_ptr()
+    g.accumulate = int(accumulate)
+    check(lib.dgn_norm_backward(C.byref(a), C.byref(g), torch.cuda.current_stream(d_y.device).cuda_stream),
+          "dgn_norm_backward")
+    _count(2)
+
+
 class _NormAct(torch.autograd.Function):
     """snorm * y -> BatchNorm1d -> ReLU -> + residual (rb/nets/dgn_layer.py:122-130) in the C-ABI kernels."""
 
@@ -183,24 +227,12 @@ class _NormAct(torch.autograd.Function):
         N, Cn = y.shape
         out = torch.empty((N, Cn), device=y.device, dtype=torch.float32)
         stats = torch.empty(_lib.NORM_WS_PER_COL * Cn, device=y.device, dtype=torch.float32)
-        a = _lib.DgnNormArgs()
-        a.n_rows, a.n_cols, a.y, a.ld_y = N, Cn, y.data_ptr(), y.stride(0)
         if snorm is not None:
             snorm = snorm.reshape(-1).contiguous()
-            a.snorm = snorm.data_ptr()
-        if gamma is not None:
-            a.gamma, a.beta = gamma.data_ptr(), beta.data_ptr()
-            if running_mean is not None:
-                a.running_mean, a.running_var = running_mean.data_ptr(), running_var.data_ptr()
-        a.momentum, a.eps, a.training, a.relu = momentum, eps, int(training), int(relu)
         if residual is not None:
             residual = _f32c(residual)
-            a.residual, a.ld_res = residual.data_ptr(), residual.stride(0)
-        a.out, a.ld_o, a.stats = out.data_ptr(), Cn, stats.data_ptr()
-        if n_rows_dev is not None:
-            a.n_rows_dev = n_rows_dev.data_ptr()
-        check(lib.dgn_norm_forward(C.byref(a), _stream(y)), "dgn_norm_forward")
-        _count(2 if (gamma is not None and training) else 1)
+        a = norm_forward_raw(y, out, stats, snorm, None, gamma, beta, running_mean, running_var, momentum, eps,
+                             training, relu, residual, n_rows_dev)
         ctx.args = a
         ctx.keep = (y, snorm, gamma, beta, running_mean, running_var, residual, out, stats, n_rows_dev)
         ctx.has_res, ctx.has_bn = residual is not None, gamma is not None
@@ -208,21 +240,16 @@ class _NormAct(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_out):
-        a = ctx.args
         y = ctx.keep[0]
         N, Cn = y.shape
         g_out = g_out.contiguous()
         d_y = torch.empty_like(y)
         scratch = torch.empty(_lib.NORM_WS_PER_COL * Cn, device=y.device, dtype=torch.float32)
-        g = _lib.DgnNormGrad()
-        g.g_out, g.ld_go, g.d_y, g.ld_dy, g.scratch = g_out.data_ptr(), Cn, d_y.data_ptr(), Cn, scratch.data_ptr()
         d_gamma = d_beta = None
         if ctx.has_bn:
             d_gamma = torch.empty(Cn, device=y.device, dtype=torch.float32)
             d_beta = torch.empty(Cn, device=y.device, dtype=torch.float32)
-            g.d_gamma, g.d_beta = d_gamma.data_ptr(), d_beta.data_ptr()
-        check(lib.dgn_norm_backward(C.byref(a), C.byref(g), _stream(y)), "dgn_norm_backward")
-        _count(2)
+        norm_backward_raw(ctx.args, g_out, d_y, scratch, d_gamma, d_beta)
         d_res = g_out if ctx.has_res else None       # identity branch
         return d_y, None, d_gamma, d_beta, None, None, None, None, None, None, d_res, None
 
@@ -264,7 +291,7 @@ class _Readout(torch.autograd.Function):
         d_h = torch.empty_like(h)
         check(lib.dgn_readout_backward(B, ctx.graph.graph_ptr.data_ptr(), Cn, h.data_ptr(), h.stride(0),
                                        out.data_ptr(), Cn, ctx.op, g_out.data_ptr(), Cn, d_h.data_ptr(),
-                                       d_h.stride(0), _stream(h)), "dgn_readout_backward")
+                                       d_h.stride(0), h.shape[0], _stream(h)), "dgn_readout_backward")
         _count(1)
         return d_h, None, None
 
@@ -273,3 +300,40 @@ def readout(graph, h, op: str):
     """Per-graph ``sum`` / ``mean`` / ``max`` over the node rows (dgl.{sum,mean,max}_nodes)."""
     code = {"sum": _lib.READOUT_SUM, "mean": _lib.READOUT_MEAN, "max": _lib.READOUT_MAX}[op]
     return _Readout.apply(h, graph, code)
+
+
+class _Embedding(torch.autograd.Function):
+    """nn.Embedding lookup whose weight gradient is the deterministic dgn_embedding_backward kernel."""
+
+    @staticmethod
+    def forward(ctx, weight, idx, n_rows_dev, direct):
+        ctx.save_for_backward(idx)
+        ctx.wref, ctx.n_rows_dev, ctx.direct = weight, n_rows_dev, direct
+        return weight.index_select(0, idx)
+
+    @staticmethod
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        w = ctx.wref
+        g = g.contiguous()
+        direct = ctx.direct and w.grad is not None and w.grad.is_contiguous()
+        dw = w.grad if direct else torch.zeros_like(w)
+        nd = ctx.n_rows_dev
+        check(lib.dgn_embedding_backward(g.shape[0], g.shape[1], w.shape[0], idx.data_ptr(), g.data_ptr(),
+                                         g.stride(0), dw.data_ptr(), dw.stride(0),
+                                         nd.data_ptr() if nd is not None else None, _stream(g)),
+              "dgn_embedding_backward")
+        _count(1)
+        return (None if direct else dw), None, None, None
+
+
+def embedding(weight, idx, n_rows_dev=None, direct_grad=False):
+    """``weight[idx]`` (rb/nets/molecules_graph_regression/dgn_net.py:58) with a deterministic backward.
+
+    ``direct_grad=True`` accumulates straight into ``weight.grad`` (which must already exist) instead of
+    returning a gradient tensor - the engine's flat gradient buffer makes autograd's extra add redundant.
+    Falls back to torch's own embedding when the vocabulary does not fit the kernel's shared-memory tile."""
+    _need_cuda(weight, idx)
+    if weight.shape[0] > 200:            # tile would not fit in shared memory: library op (still on the GPU)
+        return torch.nn.functional.embedding(idx, weight)
+    return _Embedding.apply(weight, idx, n_rows_dev, direct_grad)

@@ -5,6 +5,7 @@ Mirrors realworld_benchmark/nets/SBMs_node_classification/dgn_net.py:8-81.
 import torch
 import torch.nn as nn
 
+from dgn_b200.ops import embedding
 from dgn_b200.task_nets._common import build_layers
 from dgn_b200.nets.mlp_readout_layer import MLPReadout
 
@@ -22,7 +23,7 @@ class DGNNet(nn.Module):
         self.MLP_layer = MLPReadout(p["out_dim"], p["n_classes"])
 
     def forward(self, g, h, e, snorm_n, snorm_e):
-        h = self.in_feat_dropout(self.embedding_h(h))
+        h = self.in_feat_dropout(embedding(self.embedding_h.weight, h, getattr(g, "n_rows_dev", None), True))
         if self.pos_enc_dim > 0:
             h = h + self.embedding_pos_enc(g.ndata["pos_enc"].to(h.device))
         for conv in self.layers:

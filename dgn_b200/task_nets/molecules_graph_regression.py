@@ -6,6 +6,7 @@ runs unmodified on top of ``nets.dgn_layer`` from this package, see INTEGRATION.
 """
 import torch.nn as nn
 
+from dgn_b200.ops import embedding
 from dgn_b200.task_nets._common import build_layers, graph_readout
 from dgn_b200.nets.mlp_readout_layer import MLPReadout
 
@@ -27,7 +28,7 @@ class DGNNet(nn.Module):
         self.MLP_layer = MLPReadout((2 if wide else 1) * p["out_dim"], 1)
 
     def forward(self, g, h, e, snorm_n, snorm_e):
-        h = self.in_feat_dropout(self.embedding_h(h))
+        h = self.in_feat_dropout(embedding(self.embedding_h.weight, h, getattr(g, "n_rows_dev", None), True))
         if self.pos_enc_dim > 0:
             h = h + self.embedding_pos_enc(g.ndata["pos_enc"].to(h.device))
         if self.edge_feat:

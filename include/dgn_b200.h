@@ -32,12 +32,12 @@
 extern "C" {
 #endif
 
-#define DGN_ABI_VERSION 1
+#define DGN_ABI_VERSION 2
 #define DGN_MAX_AGG 32      /* aggregators per layer (the reference registry has 24)        */
 #define DGN_MAX_SCALERS 4   /* scalers per layer (the reference registry has 3)             */
 #define DGN_MAX_SLOTS 8     /* distinct eigen-weighted feature sums one launch can carry    */
 #define DGN_EPS 1e-8f       /* rb/nets/aggregators.py:5                                     */
-#define DGN_NORM_WS_FLOATS(C) (130 * (C)) /* fp32 workspace of dgn_norm_* for C columns         */
+#define DGN_NORM_WS_FLOATS(C) (320 * (C)) /* fp32 workspace of dgn_norm_* for C columns         */
 
 typedef enum {
   DGN_OK = 0,
@@ -109,8 +109,9 @@ typedef struct {
   int32_t msg_mode;       /* DgnMsgMode                                                                 */
   const float* x;         /* [N,F] source term: X (SOURCE) or P = h W_src^T (AFFINE); unused for DENSE   */
   int32_t ld_x;
-  const float* q;         /* [N,F] destination term incl. bias (AFFINE only)                             */
+  const float* q;         /* [N,F] destination term (AFFINE only)                                        */
   int32_t ld_q;
+  const float* q_bias;    /* [F] optional bias added to every message (AFFINE only): m = X[u] + Q[v] + q_bias */
   const float* r;         /* [E,F] per-edge term in EDGE-ID order: optional for AFFINE, the message for DENSE */
   int32_t ld_r;
   const float* h_in;      /* [N,F] destination's own features (the dx aggregators subtract W*h_in)       */
@@ -136,8 +137,10 @@ typedef struct {
   int32_t ld_dq;
   float* d_r;             /* [E,F] gradient of io.r in edge-id order                                     */
   int32_t ld_dr;
-  float* d_h_in;          /* [N,F] gradient of io.h_in (incl. g_hcopy)                                   */
+  float* d_h_in;          /* [N,F] gradient of io.h_in (incl. g_hcopy and d_h_addend)                    */
   int32_t ld_dh;
+  const float* d_h_addend;/* [N,F] optional: added into d_h_in (e.g. the residual branch's gradient)     */
+  int32_t ld_dha;
   float* edge_ws;         /* [E,F] workspace (slot order) for the deterministic source-side reduction;
                              required when d_x != NULL                                                   */
   int32_t fold_h_in;      /* 1: d_x += d_h_in (SOURCE mode where x and h_in are the same tensor)         */
@@ -171,6 +174,7 @@ int dgn_build_csr_host(int32_t n_nodes, int32_t n_edges, const int32_t* src, con
 typedef struct {
   int32_t n_rows, n_cols;
   const float* y;          int32_t ld_y;     /* posttrans output                                        */
+  const float* y_bias;     /* [C] optional: z = (y + y_bias) * snorm_n (the posttrans bias, fused)      */
   const float* snorm;      /* [n_rows] graph-norm factor per node, NULL = graph_norm off                */
   const float* gamma;      /* [C] BatchNorm weight, NULL = batch_norm off                               */
   const float* beta;       /* [C] BatchNorm bias                                                        */
@@ -195,6 +199,8 @@ typedef struct {
   float* d_residual;       int32_t ld_dres;
   float* d_gamma;          /* [C] */
   float* d_beta;           /* [C] */
+  float* d_bias;           /* [C] optional: gradient of y_bias = column sums of d_y                     */
+  int32_t accumulate;      /* 1: d_gamma / d_beta / d_bias are accumulated (+=) instead of overwritten  */
   float* scratch;          /* [DGN_NORM_WS_FLOATS(C)] fp32 workspace                                    */
 } DgnNormGrad;
 
@@ -202,11 +208,18 @@ int dgn_norm_backward(const DgnNormArgs* a, const DgnNormGrad* g, void* stream);
 
 /* Per-graph readout over contiguous node segments: op 0 = sum, 1 = mean, 2 = max.
  * graph_ptr [n_graphs+1] device.  Replaces dgl.sum_nodes / mean_nodes / max_nodes. */
+/* d_weight[idx[r], :] += g[r, :] for r < n_rows: gradient of an embedding lookup
+ * (nn.Embedding at rb/nets/molecules_graph_regression/dgn_net.py:36,58).  Deterministic (no atomics);
+ * vocab * 1 KiB of shared memory must fit (vocab <= 200).  idx is int64 (torch.long). */
+int dgn_embedding_backward(int32_t n_rows, int32_t n_cols, int32_t vocab, const int64_t* idx, const float* g,
+                           int32_t ld_g, float* d_weight, int32_t ld_w, const int32_t* n_rows_dev, void* stream);
+
 int dgn_readout_forward(int32_t n_graphs, const int32_t* graph_ptr, int32_t n_cols, const float* h, int32_t ld_h,
                         int32_t op, float* out, int32_t ld_o, void* stream);
+/* d_h has n_rows_total rows: rows past graph_ptr[n_graphs] (padding of a fixed-capacity batch) are zeroed. */
 int dgn_readout_backward(int32_t n_graphs, const int32_t* graph_ptr, int32_t n_cols, const float* h, int32_t ld_h,
                          const float* out, int32_t ld_o, int32_t op, const float* g_out, int32_t ld_go,
-                         float* d_h, int32_t ld_dh, void* stream);
+                         float* d_h, int32_t ld_dh, int32_t n_rows_total, void* stream);
 
 #ifdef __cplusplus
 }

@@ -33,10 +33,10 @@ def test_graphed_padded_step_equals_eager_step(type_net):
     eager = TrainStep(eager_net, collate(pools[0])[0], tg[0], lr=1e-3, graphed=False)
     graphed_net = _net(avg, type_net)
     # capture needs eager warm-up steps (lazy cuBLAS / autograd initialisation); they are real optimizer
-    # steps on batch 0 (2 warm-up + the captured one), so the eager model takes the same 3 steps first
+    # steps on batch 0 (capture itself only records), so the eager model takes the same 2 steps first
     graphed = TrainStep(graphed_net, collate(pools[0], capacity=cap)[0], tg[0], lr=1e-3, graphed=True, warmup_iters=2)
     assert graphed.launches_per_step > 0
-    for _ in range(3):
+    for _ in range(2):
         eager.run()
 
     losses = []
