@@ -79,7 +79,9 @@ SIGNATURES = {
     "dgn_norm_forward": (C.c_int, [C.POINTER(DgnNormArgs), C.c_void_p]),
     "dgn_norm_backward": (C.c_int, [C.POINTER(DgnNormArgs), C.POINTER(DgnNormGrad), C.c_void_p]),
     "dgn_embedding_backward": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
-                                         C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+                                         C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dgn_adam_step": (C.c_int, [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
+                                C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
     "dgn_readout_forward": (C.c_int, [C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
                                       C.c_void_p, C.c_int32, C.c_void_p]),
     "dgn_readout_backward": (C.c_int, [C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,

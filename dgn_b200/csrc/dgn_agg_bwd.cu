@@ -43,6 +43,33 @@ __global__ void __launch_bounds__(256) agg_bwd_dst_kernel(const __grid_constant_
     return;
   }
 
+  // ---- phase 1: G_a = sum_s coef_s * g_out[v, s, a, :] for every aggregator, staged in shared memory.
+  // The S*A slab loads are the dominant traffic of this kernel and independent of everything else, so they
+  // are issued first and back to back (unroll 4 => 4*S loads in flight per thread) instead of three at a
+  // time inside the per-aggregator switch.  Each thread only ever reads its own entries: no barrier needed.
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Vec<VEC>* sG = reinterpret_cast<Vec<VEC>*>(smem_raw);
+  float coef[DGN_MAX_SCALERS];
+  scaler_coefs(k, v, coef);
+  {
+    const float* grow = k.g_out + (size_t)v * k.ld_out + (size_t)tower * k.out_gs + cg;
+    const int scaler_stride = P.A * P.Fg;
+#pragma unroll 4
+    for (int a = 0; a < P.A; ++a) {
+      Vec<VEC> G = vfill<VEC>(0.f);
+      const float* src = grow + a * P.Fg;
+#pragma unroll
+      for (int s = 0; s < DGN_MAX_SCALERS; ++s) {
+        if (s < P.S) {
+          const Vec<VEC> gs = vload_stream<VEC>(src + s * scaler_stride);
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) G.a[i] = fmaf(coef[s], gs.a[i], G.a[i]);
+        }
+      }
+      sG[a * (int)blockDim.x + (int)threadIdx.x] = G;
+    }
+  }
+
   const Vec<VEC> hv = vload<VEC>(k.h_in + (size_t)v * k.ld_h + c);
   Vec<VEC> qv = vfill<VEC>(0.f);
   if constexpr (MODE == DGN_MSG_AFFINE) {
@@ -60,9 +87,6 @@ __global__ void __launch_bounds__(256) agg_bwd_dst_kernel(const __grid_constant_
 
   RowAcc<VEC, NS, ISO> R;
   accumulate_row<MODE, VEC, NS, ISO, EXP>(k, v, c, e0, e1, qv, ev, shift, R);
-
-  float coef[DGN_MAX_SCALERS];
-  scaler_coefs(k, v, coef);
 
   const float fD = (float)D;
   Vec<VEC> mean, var;
@@ -84,21 +108,7 @@ __global__ void __launch_bounds__(256) agg_bwd_dst_kernel(const __grid_constant_
 #pragma unroll
   for (int s = 0; s < NS; ++s) cs[s] = vfill<VEC>(0.f);
 
-  const float* grow = k.g_out + (size_t)v * k.ld_out + (size_t)tower * k.out_gs + cg;
-  const int scaler_stride = P.A * P.Fg;
-  auto slab_grad = [&](int a) {               // G_a = sum_s coef_s * g_out[v, s, a, :]
-    Vec<VEC> G = vfill<VEC>(0.f);
-    const float* src = grow + a * P.Fg;
-#pragma unroll
-    for (int s = 0; s < DGN_MAX_SCALERS; ++s) {
-      if (s < P.S) {
-        const Vec<VEC> gs = vload_stream<VEC>(src + s * scaler_stride);
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) G.a[i] = fmaf(coef[s], gs.a[i], G.a[i]);
-      }
-    }
-    return G;
-  };
+  auto slab_grad = [&](int a) { return sG[a * (int)blockDim.x + (int)threadIdx.x]; };
 
   for (int a = 0; a < P.A; ++a) {             // isotropic aggregators
     const int kind = P.agg_kind[a];
@@ -238,7 +248,15 @@ static int launch_dst(const KernelArgs& k, cudaStream_t st) {
   if (threads == 0) return DGN_OK;
   const int block = 256;
   const long long grid = (threads + block - 1) / block;
-  agg_bwd_dst_kernel<MODE, VEC, NS, ISO, EXP><<<(unsigned)grid, block, 0, st>>>(k);
+  const size_t smem = (size_t)k.plan.A * block * VEC * sizeof(float);     // staged G_a, <= 128 KB (A <= 32)
+  static bool big_smem_enabled = false;                                    // per template instantiation
+  if (smem > 48 * 1024 && !big_smem_enabled) {
+    if (cudaFuncSetAttribute(agg_bwd_dst_kernel<MODE, VEC, NS, ISO, EXP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             DGN_MAX_AGG * block * VEC * (int)sizeof(float)) != cudaSuccess)
+      return DGN_ERR_CUDA;
+    big_smem_enabled = true;
+  }
+  agg_bwd_dst_kernel<MODE, VEC, NS, ISO, EXP><<<(unsigned)grid, block, smem, st>>>(k);
   return cudaGetLastError() == cudaSuccess ? DGN_OK : DGN_ERR_CUDA;
 }
 

@@ -273,31 +273,54 @@ __global__ void __launch_bounds__(kTX * kTY) norm_bwd_apply_kernel(const DgnNorm
 }
 
 // ---- embedding gradient --------------------------------------------------------------------------
-// block = 32 columns x 8 row-lanes; every (row-lane, vocab entry, column) cell of the shared tile is owned by
-// exactly one thread, so the accumulation order is fixed (row order per lane, then lanes 0..7).
+// grid = (column tiles of 32, kEmbSlabs row slabs); block = 32 columns x 8 row-lanes.  Every (row-lane, vocab
+// entry, column) cell of the shared tile is owned by exactly one thread and the slab partials are merged in
+// slab order by the last block of each column tile: the result does not depend on scheduling.
+constexpr int kEmbSlabs = 32;
+
 __global__ void __launch_bounds__(kTX * kTY) embedding_bwd_kernel(int n_rows, int C, int vocab,
                                                                   const long long* __restrict__ idx,
                                                                   const float* __restrict__ gsrc, int ld_g,
                                                                   float* __restrict__ dw, int ld_w,
-                                                                  const int32_t* __restrict__ n_rows_dev) {
+                                                                  const int32_t* __restrict__ n_rows_dev,
+                                                                  float* __restrict__ ws, unsigned* __restrict__ counters) {
   extern __shared__ float tile[];                      // [kTY][vocab][kTX]
+  __shared__ bool is_last;
   const int n = n_rows_dev ? *n_rows_dev : n_rows;
   const int col = blockIdx.x * kTX + threadIdx.x;
+  const int per = (n + kEmbSlabs - 1) / kEmbSlabs;
+  const int r0 = min((int)blockIdx.y * per, n), r1 = min(r0 + per, n);
   float* mine = tile + (size_t)threadIdx.y * vocab * kTX + threadIdx.x;
   for (int t = 0; t < vocab; ++t) mine[t * kTX] = 0.f;
   if (col < C) {
-    for (int r = threadIdx.y; r < n; r += kTY) {
+    for (int r = r0 + threadIdx.y; r < r1; r += kTY) {
       const long long t = idx[r];
       if (t >= 0 && t < vocab) mine[(int)t * kTX] += gsrc[(size_t)r * ld_g + col];
     }
   }
   __syncthreads();
+  float* part = ws + (size_t)blockIdx.y * vocab * C;
   if (col < C) {
     for (int t = threadIdx.y; t < vocab; t += kTY) {
       float acc = 0.f;
       for (int j = 0; j < kTY; ++j) acc += tile[((size_t)j * vocab + t) * kTX + threadIdx.x];
-      dw[(size_t)t * ld_w + col] += acc;
+      part[(size_t)t * C + col] = acc;
     }
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
+    const unsigned done = atomicAdd(&counters[blockIdx.x], 1u);
+    is_last = (done == kEmbSlabs - 1);
+    if (is_last) counters[blockIdx.x] = 0u;            // ready for the next launch
+  }
+  __syncthreads();
+  if (!is_last || col >= C) return;
+  __threadfence();
+  for (int t = threadIdx.y; t < vocab; t += kTY) {
+    float acc = 0.f;
+    for (int sl = 0; sl < kEmbSlabs; ++sl) acc += __ldcg(ws + ((size_t)sl * vocab + t) * C + col);
+    dw[(size_t)t * ld_w + col] += acc;
   }
 }
 
@@ -344,6 +367,47 @@ __global__ void readout_bwd_kernel(int n_graphs, const int32_t* __restrict__ gp,
   }
 }
 
+// ---- Adam over one flat parameter buffer ---------------------------------------------------------
+// torch.optim.Adam semantics (L2 weight decay folded into the gradient, bias-corrected moments).  The step
+// counter lives in device memory so the launch can be replayed from a CUDA graph: every block reads it on
+// entry, the last block to finish increments it.
+__global__ void __launch_bounds__(256) adam_kernel(long long n, float* __restrict__ p, const float* __restrict__ g,
+                                                   float* __restrict__ m, float* __restrict__ v, float lr, float b1,
+                                                   float b2, float eps, float wd, int* __restrict__ state) {
+  const int t = state[0] + 1;
+  const float c1 = 1.f - powf(b1, (float)t), c2 = 1.f - powf(b2, (float)t);
+  const float step_size = lr / c1, inv_sqrt_c2 = rsqrtf(c2);
+  const long long i4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i4 + 3 < n) {
+    float4 pp = *reinterpret_cast<float4*>(p + i4), mm = *reinterpret_cast<float4*>(m + i4),
+           vv = *reinterpret_cast<float4*>(v + i4);
+    const float4 gg = *reinterpret_cast<const float4*>(g + i4);
+    float* pa = &pp.x; float* ma = &mm.x; float* va = &vv.x; const float* ga = &gg.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float gr = fmaf(wd, pa[j], ga[j]);
+      ma[j] = fmaf(b1, ma[j], (1.f - b1) * gr);
+      va[j] = fmaf(b2, va[j], (1.f - b2) * gr * gr);
+      pa[j] -= step_size * ma[j] / (sqrtf(va[j]) * inv_sqrt_c2 + eps);
+    }
+    *reinterpret_cast<float4*>(p + i4) = pp;
+    *reinterpret_cast<float4*>(m + i4) = mm;
+    *reinterpret_cast<float4*>(v + i4) = vv;
+  } else {
+    for (long long i = i4; i < n; ++i) {
+      const float gr = fmaf(wd, p[i], g[i]);
+      m[i] = fmaf(b1, m[i], (1.f - b1) * gr);
+      v[i] = fmaf(b2, v[i], (1.f - b2) * gr * gr);
+      p[i] -= step_size * m[i] / (sqrtf(v[i]) * inv_sqrt_c2 + eps);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int done = atomicAdd(&state[1], 1);
+    if (done == (int)gridDim.x - 1) { state[1] = 0; state[0] = t; }
+  }
+}
+
 }  // namespace dgn
 
 using namespace dgn;
@@ -356,10 +420,14 @@ static int check_launch() {
 }
 
 static dim3 norm_grid_apply(const DgnNormArgs* a) {
+  // every block pays a fixed prologue (merging the 64 slab partials of its 32 columns), so the grid is
+  // sized to ~2 blocks per SM and the rows are covered by a grid-stride loop
+  const int col_tiles = (a->n_cols + kTX - 1) / kTX;
   int gx = (a->n_rows + kTY - 1) / kTY;
-  if (gx > 592) gx = 592;                               // 4 x 148 SMs: grid-stride beyond that
+  const int cap = (296 + col_tiles - 1) / col_tiles;
+  if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
-  return dim3((unsigned)gx, (unsigned)((a->n_cols + kTX - 1) / kTX));
+  return dim3((unsigned)gx, (unsigned)col_tiles);
 }
 
 extern "C" int dgn_norm_forward(const DgnNormArgs* a, void* stream) {
@@ -391,8 +459,8 @@ extern "C" int dgn_norm_backward(const DgnNormArgs* a, const DgnNormGrad* g, voi
 
 extern "C" int dgn_embedding_backward(int32_t n_rows, int32_t n_cols, int32_t vocab, const int64_t* idx,
                                       const float* g, int32_t ld_g, float* d_weight, int32_t ld_w,
-                                      const int32_t* n_rows_dev, void* stream) {
-  if (n_rows < 0 || n_cols <= 0 || vocab <= 0 || !idx || !g || !d_weight) return DGN_ERR_INVALID;
+                                      const int32_t* n_rows_dev, float* ws, void* stream) {
+  if (n_rows < 0 || n_cols <= 0 || vocab <= 0 || !idx || !g || !d_weight || !ws) return DGN_ERR_INVALID;
   const size_t smem = (size_t)kTY * vocab * kTX * sizeof(float);
   if (smem > 200 * 1024) return DGN_ERR_UNSUPPORTED;
   if (n_rows == 0) return DGN_OK;
@@ -401,8 +469,9 @@ extern "C" int dgn_embedding_backward(int32_t n_rows, int32_t n_cols, int32_t vo
     cudaFuncSetAttribute(embedding_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_set = true;
   }
-  embedding_bwd_kernel<<<(n_cols + kTX - 1) / kTX, dim3(kTX, kTY), smem, (cudaStream_t)stream>>>(
-      n_rows, n_cols, vocab, reinterpret_cast<const long long*>(idx), g, ld_g, d_weight, ld_w, n_rows_dev);
+  unsigned* counters = reinterpret_cast<unsigned*>(ws + (size_t)kEmbSlabs * vocab * n_cols);
+  embedding_bwd_kernel<<<dim3((n_cols + kTX - 1) / kTX, kEmbSlabs), dim3(kTX, kTY), smem, (cudaStream_t)stream>>>(
+      n_rows, n_cols, vocab, reinterpret_cast<const long long*>(idx), g, ld_g, d_weight, ld_w, n_rows_dev, ws, counters);
   return check_launch();
 }
 
@@ -425,5 +494,18 @@ extern "C" int dgn_readout_backward(int32_t n_graphs, const int32_t* graph_ptr, 
   const int block = 64;
   readout_bwd_kernel<<<dim3((n_cols + block - 1) / block, n_graphs + 1), block, 0, (cudaStream_t)stream>>>(
       n_graphs, graph_ptr, n_cols, h, ld_h, out, ld_o, op, g_out, ld_go, d_h, ld_dh, n_rows_total);
+  return check_launch();
+}
+
+extern "C" int dgn_adam_step(int64_t n, float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float lr,
+                             float beta1, float beta2, float eps, float weight_decay, int32_t* state, void* stream) {
+  if (n < 0 || !param || !grad || !exp_avg || !exp_avg_sq || !state) return DGN_ERR_INVALID;
+  if ((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(exp_avg) |
+       reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15u)
+    return DGN_ERR_ALIGNMENT;
+  if (n == 0) return DGN_OK;
+  const long long threads = (n + 3) / 4;
+  adam_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, param, grad, exp_avg, exp_avg_sq, lr,
+                                                                                  beta1, beta2, eps, weight_decay, state);
   return check_launch();
 }

@@ -19,8 +19,30 @@ from __future__ import annotations
 
 import torch
 
-from . import ops
+import ctypes as C
+
+from . import _lib, ops
 from .parallel import allreduce_mean_, flatten_parameters
+
+
+class FlatAdam:
+    """Adam over the flat parameter buffer: one ``dgn_adam_step`` launch per step, replayable from a CUDA graph
+    (the step counter lives on the device).  Same update rule as ``torch.optim.Adam(lr, betas, eps, weight_decay)``
+    (rb/main_molecules.py:82)."""
+
+    def __init__(self, flat_p, flat_g, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        self.p, self.g = flat_p, flat_g
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.exp_avg = torch.zeros_like(flat_g)
+        self.exp_avg_sq = torch.zeros_like(flat_g)
+        self.state = torch.zeros(2, dtype=torch.int32, device=flat_g.device)
+
+    def step(self):
+        _lib.check(_lib.lib.dgn_adam_step(self.p.numel(), self.p.data_ptr(), self.g.data_ptr(), self.exp_avg.data_ptr(),
+                                          self.exp_avg_sq.data_ptr(), self.lr, self.betas[0], self.betas[1], self.eps,
+                                          self.weight_decay, self.state.data_ptr(),
+                                          torch.cuda.current_stream(self.p.device).cuda_stream), "dgn_adam_step")
+        ops._count(1)
 
 
 class TrainStep:
@@ -32,8 +54,7 @@ class TrainStep:
         self.graphed = graphed
         self.node_key, self.edge_key = node_key, edge_key
         self.flat_p, self.flat_g = flatten_parameters(net)
-        self.opt = torch.optim.Adam([self.flat_p], lr=lr, weight_decay=weight_decay, fused=True,
-                                    capturable=graphed)
+        self.opt = FlatAdam(self.flat_p, self.flat_g, lr=lr, weight_decay=weight_decay)
         if graphed and not template_graph.padded:
             raise ValueError("graphed=True needs batches padded to a fixed capacity (BatchedGraph(capacity=...))")
         # static device-side batch: the graph object is re-bound onto this buffer once

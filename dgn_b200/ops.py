@@ -302,6 +302,19 @@ def readout(graph, h, op: str):
     return _Readout.apply(h, graph, code)
 
 
+_EMB_WS = {}
+
+
+def _emb_workspace(vocab, cols, device):
+    """Zero-initialised, reused workspace of dgn_embedding_backward (its counters return to zero)."""
+    key = (vocab, cols, str(device))
+    ws = _EMB_WS.get(key)
+    if ws is None:
+        ws = torch.zeros(32 * vocab * cols + 64, device=device, dtype=torch.float32)
+        _EMB_WS[key] = ws
+    return ws
+
+
 class _Embedding(torch.autograd.Function):
     """nn.Embedding lookup whose weight gradient is the deterministic dgn_embedding_backward kernel."""
 
@@ -319,9 +332,10 @@ class _Embedding(torch.autograd.Function):
         direct = ctx.direct and w.grad is not None and w.grad.is_contiguous()
         dw = w.grad if direct else torch.zeros_like(w)
         nd = ctx.n_rows_dev
+        ws = _emb_workspace(w.shape[0], g.shape[1], g.device)
         check(lib.dgn_embedding_backward(g.shape[0], g.shape[1], w.shape[0], idx.data_ptr(), g.data_ptr(),
                                          g.stride(0), dw.data_ptr(), dw.stride(0),
-                                         nd.data_ptr() if nd is not None else None, _stream(g)),
+                                         nd.data_ptr() if nd is not None else None, ws.data_ptr(), _stream(g)),
               "dgn_embedding_backward")
         _count(1)
         return (None if direct else dw), None, None, None

@@ -43,7 +43,7 @@ typedef enum {
   DGN_OK = 0,
   DGN_ERR_INVALID = -1,     /* bad argument (null pointer, negative size, unknown enum)     */
   DGN_ERR_UNSUPPORTED = -2, /* valid request the kernels cannot serve (too many slots ...)  */
-  DGN_ERR_ALIGNMENT = -3,   /* reserved                                                     */
+  DGN_ERR_ALIGNMENT = -3,   /* an operand that must be 16 B aligned is not                  */
   DGN_ERR_CUDA = -4         /* a CUDA runtime call failed; see dgn_last_cuda_error          */
 } DgnStatus;
 
@@ -209,10 +209,20 @@ int dgn_norm_backward(const DgnNormArgs* a, const DgnNormGrad* g, void* stream);
 /* Per-graph readout over contiguous node segments: op 0 = sum, 1 = mean, 2 = max.
  * graph_ptr [n_graphs+1] device.  Replaces dgl.sum_nodes / mean_nodes / max_nodes. */
 /* d_weight[idx[r], :] += g[r, :] for r < n_rows: gradient of an embedding lookup
- * (nn.Embedding at rb/nets/molecules_graph_regression/dgn_net.py:36,58).  Deterministic (no atomics);
- * vocab * 1 KiB of shared memory must fit (vocab <= 200).  idx is int64 (torch.long). */
+ * (nn.Embedding at rb/nets/molecules_graph_regression/dgn_net.py:36,58).  Deterministic (fixed summation
+ * order); vocab * 1 KiB of shared memory must fit (vocab <= 200).  idx is int64 (torch.long).
+ * ws: DGN_EMB_WS_FLOATS(vocab, n_cols) floats of device workspace that must be ZERO before the first call
+ * (the kernel leaves its counters zeroed again) and may be reused by later calls on the same stream. */
+#define DGN_EMB_WS_FLOATS(V, C) (32 * (V) * (C) + 64)
 int dgn_embedding_backward(int32_t n_rows, int32_t n_cols, int32_t vocab, const int64_t* idx, const float* g,
-                           int32_t ld_g, float* d_weight, int32_t ld_w, const int32_t* n_rows_dev, void* stream);
+                           int32_t ld_g, float* d_weight, int32_t ld_w, const int32_t* n_rows_dev, float* ws,
+                           void* stream);
+
+/* One Adam update of a flat fp32 parameter buffer (torch.optim.Adam as used at rb/main_molecules.py:82:
+ * weight decay added to the gradient, bias-corrected moments).  state: 2 device int32, zero-initialised:
+ * state[0] = steps taken so far (incremented by the kernel), state[1] = internal.  All pointers 16 B aligned. */
+int dgn_adam_step(int64_t n, float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, int32_t* state, void* stream);
 
 int dgn_readout_forward(int32_t n_graphs, const int32_t* graph_ptr, int32_t n_cols, const float* h, int32_t ld_h,
                         int32_t op, float* out, int32_t ld_o, void* stream);

