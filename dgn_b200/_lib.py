@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libdgn_b200.so")
 
 MAX_AGG, MAX_SCALERS, MAX_SLOTS = 32, 4, 8
 ABI_VERSION = 2
-NORM_WS_PER_COL = 320
+NORM_WS_PER_COL = 640
 
 # DgnAggKind / DgnScalerKind / DgnMsgMode
 AGG_MEAN, AGG_SUM, AGG_MAX, AGG_MIN, AGG_STD, AGG_VAR = 0, 1, 2, 3, 4, 5

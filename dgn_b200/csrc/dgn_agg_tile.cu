@@ -1,0 +1,746 @@
+// Fused DGN aggregation, tile kernels (sm_100a) - the fast path of dgn_agg_forward / dgn_agg_backward.
+//
+// A CTA owns a tile of TN consecutive destination nodes; thread = (local node, VEC-column chunk).
+// Everything that does not depend on the feature column is computed ONCE per node / per edge and staged
+// in shared memory instead of once per (node, chunk) thread:
+//   * the tile's slice of the CSR (in_ptr, in_src),
+//   * the k eigenvector components of the destination nodes and the per-edge eigen-weights w_s(delta_uv),
+//   * the per-node normalisers (sum |delta|, sum delta ...) and the factors derived from them
+//     (1/Z, W = sum(w)/Z), the degree-scaler coefficients.
+// The column threads then only do vector work: gather the message row, FMA it into the accumulators
+// with weights read from shared memory (broadcast), write S*A slabs with streaming 128-bit stores.
+//
+// Batched graphs are block diagonal: all sources of a tile lie in a narrow window of node ids.  When
+// that window is small and re-used enough (in-degree >> 1: CIFAR kNN, SBM PATTERN) the source rows of
+// the window are brought into shared memory with one TMA bulk copy (cp.async.bulk + mbarrier) and the
+// per-edge gathers become shared-memory reads instead of L2 round trips.
+//
+// Edges of a tile are processed in batches of EB slots so shared memory stays bounded for any degree.
+// The softmax aggregators (W_EXP) and F > 1024 fall back to the generic kernels in dgn_agg_fwd/bwd.cu.
+#include <limits.h>
+
+#include "dgn_plan.cuh"
+
+namespace dgn {
+
+constexpr int kTileThreads = 256;
+constexpr int kEB = 512;             // edge slots per batch
+
+struct TileCfg {
+  int TN;                            // destination nodes per tile
+  int win_rows;                      // capacity of the staged source window in rows (0 = never stage)
+  int off_ev, off_zw, off_zabs, off_f0, off_f1, off_coef, off_src, off_w, off_bar, off_red, off_win, off_g;
+  int total;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+
+// Shared-memory view of one tile + the state every thread needs.
+template <int VEC, int NS>
+struct Tile {
+  int* s_ptr; float* s_ev; float* s_zw; float* s_zabs; float* s_f0; float* s_f1; float* s_coef;
+  int* s_src; float* s_w; uint64_t* s_bar; int* s_red; float* s_win;
+  int v0, nv, E0, E1, ln, c, v, ne0, ne1, umin;
+  bool active, staged;
+};
+
+template <int MODE, int VEC, int NS>
+__device__ __forceinline__ void tile_prologue(const KernelArgs& k, const TileCfg& tc, unsigned char* smem, Tile<VEC, NS>& T) {
+  const AggPlan& P = k.plan;
+  const int tid = threadIdx.x, TN = tc.TN;
+  T.s_ptr = reinterpret_cast<int*>(smem);
+  T.s_ev = reinterpret_cast<float*>(smem + tc.off_ev);
+  T.s_zw = reinterpret_cast<float*>(smem + tc.off_zw);
+  T.s_zabs = reinterpret_cast<float*>(smem + tc.off_zabs);
+  T.s_f0 = reinterpret_cast<float*>(smem + tc.off_f0);
+  T.s_f1 = reinterpret_cast<float*>(smem + tc.off_f1);
+  T.s_coef = reinterpret_cast<float*>(smem + tc.off_coef);
+  T.s_src = reinterpret_cast<int*>(smem + tc.off_src);
+  T.s_w = reinterpret_cast<float*>(smem + tc.off_w);
+  T.s_bar = reinterpret_cast<uint64_t*>(smem + tc.off_bar);
+  T.s_red = reinterpret_cast<int*>(smem + tc.off_red);
+  T.s_win = reinterpret_cast<float*>(smem + tc.off_win);
+  T.v0 = blockIdx.x * TN;
+  T.nv = min(TN, k.N - T.v0);
+  T.ln = tid / P.chunks;
+  T.c = (tid - T.ln * P.chunks) * VEC;
+  T.active = T.ln < T.nv;
+  T.v = T.v0 + T.ln;
+  for (int i = tid; i <= T.nv; i += kTileThreads) T.s_ptr[i] = __ldg(k.in_ptr + T.v0 + i);
+  for (int i = tid; i < NS * TN; i += kTileThreads) {
+    const int s = i / TN, l = i - s * TN;
+    T.s_ev[i] = (s < P.n_slots && l < T.nv) ? __ldg(k.eig + (size_t)(T.v0 + l) * k.ld_eig + P.slot_eig[s]) : 0.f;
+    T.s_zw[i] = 0.f;
+    T.s_zabs[i] = 0.f;
+  }
+  __syncthreads();
+  T.E0 = T.s_ptr[0];
+  T.E1 = T.s_ptr[T.nv];
+  T.ne0 = T.active ? T.s_ptr[T.ln] : 0;
+  T.ne1 = T.active ? T.s_ptr[T.ln + 1] : 0;
+  T.staged = false;
+  T.umin = 0;
+  if constexpr (MODE != DGN_MSG_DENSE && VEC == 4) {
+    if (tc.win_rows > 0 && T.E1 > T.E0) {
+      // source window of the tile: block-wide min / max of in_src over the tile's slots
+      int lo = INT_MAX, hi = -1;
+      for (int e = T.E0 + tid; e < T.E1; e += kTileThreads) {
+        const int u = __ldg(k.in_src + e);
+        lo = min(lo, u);
+        hi = max(hi, u);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+      }
+      if ((tid & 31) == 0) { T.s_red[tid >> 5] = lo; T.s_red[8 + (tid >> 5)] = hi; }
+      __syncthreads();
+      lo = T.s_red[0]; hi = T.s_red[8];
+#pragma unroll
+      for (int w = 1; w < kTileThreads / 32; ++w) { lo = min(lo, T.s_red[w]); hi = max(hi, T.s_red[8 + w]); }
+      const int rows = hi - lo + 1;
+      // stage only when the window fits and every staged row is re-used on average at least twice
+      T.staged = rows <= tc.win_rows && (T.E1 - T.E0) >= 2 * rows;
+      if (T.staged) {
+        T.umin = lo;
+        const uint32_t row_bytes = (uint32_t)P.F * 4u;
+        if (tid == 0) {
+          mbar_init(T.s_bar, 1);
+          mbar_expect_tx(T.s_bar, row_bytes * (uint32_t)rows);
+        }
+        __syncthreads();
+        if (k.ld_x == P.F) {                      // rows are contiguous: one bulk copy
+          if (tid == 0) bulk_g2s(T.s_win, k.x + (size_t)lo * k.ld_x, row_bytes * (uint32_t)rows, T.s_bar);
+        } else {
+          for (int r = tid; r < rows; r += kTileThreads)
+            bulk_g2s(T.s_win + (size_t)r * P.F, k.x + (size_t)(lo + r) * k.ld_x, row_bytes, T.s_bar);
+        }
+      }
+    }
+  }
+}
+
+// phase A: eigen-weights of one batch of edge slots [b0, b0+nb) -> s_src / s_w; then the per-node sums
+template <int VEC, int NS>
+__device__ __forceinline__ void tile_weights(const KernelArgs& k, const TileCfg& tc, Tile<VEC, NS>& T, int b0, int nb,
+                                             bool accumulate_z) {
+  const AggPlan& P = k.plan;
+  const int tid = threadIdx.x, TN = tc.TN;
+  for (int i = tid; i < nb; i += kTileThreads) {
+    const int e = b0 + i;
+    const int u = __ldg(k.in_src + e);
+    T.s_src[i] = u;
+    if constexpr (NS > 0) {
+      int lo = 0, hi = T.nv;                    // local destination: largest l with s_ptr[l] <= e
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (T.s_ptr[mid] <= e) lo = mid; else hi = mid;
+      }
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        if (s < P.n_slots) {
+          const float d = __ldg(k.eig + (size_t)u * k.ld_eig + P.slot_eig[s]) - T.s_ev[s * TN + lo];
+          T.s_w[s * kEB + i] = edge_weight(P.slot_w[s], d, 0.f, 0.f);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if constexpr (NS > 0) {
+    if (accumulate_z) {                         // one thread per (node, slot): sequential, edge-id order
+      for (int j = tid; j < T.nv * NS; j += kTileThreads) {
+        const int l = j / NS, s = j - l * NS;
+        if (s < P.n_slots) {
+          const int a0 = max(T.s_ptr[l], b0) - b0, a1 = min(T.s_ptr[l + 1], b0 + nb) - b0;
+          float zw = T.s_zw[s * TN + l], za = T.s_zabs[s * TN + l];
+          for (int i = a0; i < a1; ++i) {
+            const float w = T.s_w[s * kEB + i];
+            zw += w;
+            za += fabsf(w);
+          }
+          T.s_zw[s * TN + l] = zw;
+          T.s_zabs[s * TN + l] = za;
+        }
+      }
+    }
+  }
+}
+
+// message of batch slot i (global slot e, source u) for this thread's columns
+template <int MODE, int VEC, int NS>
+__device__ __forceinline__ Vec<VEC> tile_message(const KernelArgs& k, const Tile<VEC, NS>& T, int u, int e, const Vec<VEC>& qv) {
+  if constexpr (MODE != DGN_MSG_DENSE && VEC == 4) {
+    if (T.staged) {
+      const float4 t = *reinterpret_cast<const float4*>(T.s_win + (size_t)(u - T.umin) * k.plan.F + T.c);
+      Vec<VEC> m;
+      m.a[0] = t.x; m.a[1] = t.y; m.a[2] = t.z; m.a[3] = t.w;
+      if constexpr (MODE == DGN_MSG_AFFINE) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) m.a[i] += qv.a[i];
+        if (k.r) {
+          const int id = k.in_eid ? __ldg(k.in_eid + e) : e;
+          const Vec<VEC> rv = vload<VEC>(k.r + (size_t)id * k.ld_r + T.c);
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) m.a[i] += rv.a[i];
+        }
+      }
+      return m;
+    }
+  }
+  return load_message<MODE, VEC>(k, u, e, T.c, qv);
+}
+
+// phase C: per-(node, slot) factors and per-node scaler coefficients
+template <int VEC, int NS>
+__device__ __forceinline__ void tile_factors(const KernelArgs& k, const TileCfg& tc, Tile<VEC, NS>& T) {
+  const AggPlan& P = k.plan;
+  const int tid = threadIdx.x, TN = tc.TN;
+  for (int j = tid; j < T.nv * NS; j += kTileThreads) {
+    const int l = j / NS, s = j - l * NS;
+    if (s < P.n_slots) {
+      const int kind = P.slot_w[s];
+      const float zw = T.s_zw[s * TN + l], za = T.s_zabs[s * TN + l];
+      float f0, f1;
+      if (kind == W_POS || kind == W_NEG) {     // balanced: 0.5 / (sum relu(+-delta) + eps)
+        f0 = 0.5f * __frcp_rn(zw + DGN_EPS);
+        f1 = zw * f0;
+      } else {                                  // av / dx: 1 / (sum |delta| + eps), W = sum(w) / Z
+        f0 = __frcp_rn(za + DGN_EPS);
+        f1 = zw * f0;
+      }
+      T.s_f0[s * TN + l] = f0;
+      T.s_f1[s * TN + l] = f1;
+    }
+  }
+  for (int j = tid; j < T.nv * DGN_MAX_SCALERS; j += kTileThreads) {
+    const int l = j / DGN_MAX_SCALERS, s = j - l * DGN_MAX_SCALERS;
+    float cf = 1.f;
+    if (P.S > 1 && s < P.S) {
+      const float ld = __ldg(k.log_deg + T.v0 + l);
+      const int kind = P.scaler_kind[s];
+      cf = (kind == DGN_SCALE_AMPLIFICATION) ? __fdiv_rn(ld, P.avg_log)
+           : (kind == DGN_SCALE_ATTENUATION) ? __fdiv_rn(P.avg_log, ld) : 1.f;
+    }
+    T.s_coef[s * TN + l] = cf;
+  }
+}
+
+template <int VEC, int NS, bool ISO>
+__device__ __forceinline__ void acc_init(RowAcc<VEC, NS, ISO>& R) {
+  R.sum = vfill<VEC>(0.f);
+  if constexpr (ISO) {
+    R.sq = vfill<VEC>(0.f);
+    R.mx = vfill<VEC>(-INFINITY);
+    R.mn = vfill<VEC>(INFINITY);
+  }
+#pragma unroll
+  for (int s = 0; s < NS; ++s) R.acc[s] = vfill<VEC>(0.f);
+}
+
+template <int VEC, int NS, bool ISO>
+__device__ __forceinline__ void acc_edge(const AggPlan& P, RowAcc<VEC, NS, ISO>& R, const Vec<VEC>& m, const float* s_w, int i) {
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    R.sum.a[j] += m.a[j];
+    if constexpr (ISO) {
+      R.sq.a[j] = __fadd_rn(R.sq.a[j], __fmul_rn(m.a[j], m.a[j]));   // square, round, then sum (as the reference)
+      R.mx.a[j] = fmaxf(R.mx.a[j], m.a[j]);
+      R.mn.a[j] = fminf(R.mn.a[j], m.a[j]);
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    if (s < P.n_slots) {
+      const float w = s_w[s * kEB + i];
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) R.acc[s].a[j] = fmaf(w, m.a[j], R.acc[s].a[j]);
+    }
+  }
+}
+
+template <int VEC, bool ISO>
+__device__ __forceinline__ void mean_var(const Vec<VEC>& sum, const Vec<VEC>& sq, float fD, Vec<VEC>& mean, Vec<VEC>& var) {
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    // IEEE division: keeps var == 0 exactly for constant mailboxes (the reference's relu / sqrt gradient jumps there)
+    mean.a[i] = __fdiv_rn(sum.a[i], fD);
+    if constexpr (ISO) {
+      const float msq = __fdiv_rn(sq.a[i], fD);
+      var.a[i] = fmaxf(__fsub_rn(msq, __fmul_rn(mean.a[i], mean.a[i])), 0.f);
+    } else {
+      var.a[i] = 0.f;
+    }
+  }
+}
+
+// ======================================================================================================
+// forward
+// ======================================================================================================
+template <int MODE, int VEC, int NS, bool ISO>
+__global__ void __launch_bounds__(kTileThreads) agg_fwd_tile_kernel(const __grid_constant__ KernelArgs k,
+                                                                    const __grid_constant__ TileCfg tc) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const AggPlan& P = k.plan;
+  const int TN = tc.TN;
+  Tile<VEC, NS> T;
+  tile_prologue<MODE, VEC, NS>(k, tc, smem, T);
+
+  Vec<VEC> hv = vfill<VEC>(0.f), qv = vfill<VEC>(0.f);
+  int tower = 0, cg = 0;
+  if (T.active) {
+    tower = T.c / P.Fg;
+    cg = T.c - tower * P.Fg;
+    hv = vload<VEC>(k.h_in + (size_t)T.v * k.ld_h + T.c);
+    if (k.h_copy) vstore<VEC>(k.h_copy + (size_t)T.v * k.ld_hc + (size_t)tower * k.hc_gs + cg, hv);
+    if constexpr (MODE == DGN_MSG_AFFINE) {
+      qv = vload<VEC>(k.q + (size_t)T.v * k.ld_q + T.c);
+      if (k.q_bias) {
+        const Vec<VEC> bv = vload<VEC>(k.q_bias + T.c);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) qv.a[i] += bv.a[i];
+      }
+    }
+  }
+
+  RowAcc<VEC, NS, ISO> R;
+  acc_init(R);
+  bool waited = false;
+  for (int b0 = T.E0; b0 < T.E1; b0 += kEB) {
+    const int nb = min(kEB, T.E1 - b0);
+    tile_weights<VEC, NS>(k, tc, T, b0, nb, true);
+    if (T.staged && !waited) { mbar_wait(T.s_bar, 0); waited = true; }
+    if (T.active) {
+      const int i0 = max(T.ne0, b0) - b0, i1 = min(T.ne1, b0 + nb) - b0;
+#pragma unroll 4
+      for (int i = i0; i < i1; ++i) {
+        const Vec<VEC> m = tile_message<MODE, VEC, NS>(k, T, T.s_src[i], b0 + i, qv);
+        acc_edge<VEC, NS, ISO>(P, R, m, T.s_w, i);
+      }
+    }
+    __syncthreads();
+  }
+  tile_factors<VEC, NS>(k, tc, T);
+  __syncthreads();
+  if (!T.active) return;
+
+  float* orow = k.out + (size_t)T.v * k.ld_out + (size_t)tower * k.out_gs + cg;
+  const int D = T.ne1 - T.ne0;
+  if (D == 0) {                                        // DGL: zero rows for isolated nodes
+    const Vec<VEC> z = vfill<VEC>(0.f);
+    for (int j = 0; j < P.S * P.A; ++j) vstore_stream<VEC>(orow + (size_t)j * P.Fg, z);
+    return;
+  }
+  float coef[DGN_MAX_SCALERS];
+#pragma unroll
+  for (int s = 0; s < DGN_MAX_SCALERS; ++s) coef[s] = T.s_coef[s * TN + T.ln];
+  Vec<VEC> mean, var;
+  mean_var<VEC, ISO>(R.sum, R.sq, (float)D, mean, var);
+
+  const int scaler_stride = P.A * P.Fg;
+  auto store_scaled = [&](int a, const Vec<VEC>& y) {
+    float* dst = orow + a * P.Fg;
+#pragma unroll
+    for (int s = 0; s < DGN_MAX_SCALERS; ++s) {
+      if (s < P.S) {
+        Vec<VEC> o;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) o.a[i] = y.a[i] * coef[s];
+        vstore_stream<VEC>(dst + s * scaler_stride, o);
+      }
+    }
+  };
+  for (int a = 0; a < P.A; ++a) {                      // isotropic aggregators
+    const int kind = P.agg_kind[a];
+    if (kind >= DGN_AGG_DIR_AV) continue;
+    Vec<VEC> y;
+    switch (kind) {
+      case DGN_AGG_MEAN: y = mean; break;
+      case DGN_AGG_SUM: y = R.sum; break;
+      case DGN_AGG_MAX: if constexpr (ISO) y = R.mx; else y = mean; break;
+      case DGN_AGG_MIN: if constexpr (ISO) y = R.mn; else y = mean; break;
+      case DGN_AGG_VAR: y = var; break;
+      default:
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) y.a[i] = sqrtf(var.a[i] + DGN_EPS);
+    }
+    store_scaled(a, y);
+  }
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {                       // directional aggregators, static slot index
+    if (s >= P.n_slots) break;
+    const float f0 = T.s_f0[s * TN + T.ln], f1 = T.s_f1[s * TN + T.ln];
+    unsigned todo = P.slot_aggs[s];
+    while (todo) {
+      const int a = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int kind = P.agg_kind[a];
+      const Vec<VEC>& A1 = R.acc[s];
+      Vec<VEC> y;
+      if (kind == DGN_AGG_DIR_AV) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) y.a[i] = A1.a[i] * f0;
+      } else if (kind == DGN_AGG_DIR_DX_BALANCED) {
+        if constexpr (NS >= 2) {                       // the W_NEG half always sits in slot s+1
+          constexpr int LAST = NS - 1;
+          const int s2 = (s + 1 <= LAST) ? s + 1 : LAST;
+          const float g0 = T.s_f0[s2 * TN + T.ln], wsum = f1 + T.s_f1[s2 * TN + T.ln];
+          const Vec<VEC>& A2 = R.acc[s2];
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) y.a[i] = fabsf(A1.a[i] * f0 + A2.a[i] * g0 - wsum * hv.a[i]);
+        } else {
+          y = vfill<VEC>(0.f);
+        }
+      } else {                                         // dx / dx-no-abs
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+          const float sv = A1.a[i] * f0 - f1 * hv.a[i];
+          y.a[i] = (kind == DGN_AGG_DIR_DX) ? fabsf(sv) : sv;
+        }
+      }
+      store_scaled(a, y);
+    }
+  }
+}
+
+// ======================================================================================================
+// backward, destination side (the source-side gather is agg_bwd_src_kernel in dgn_agg_bwd.cu)
+// ======================================================================================================
+template <int MODE, int VEC, int NS, bool ISO>
+__global__ void __launch_bounds__(kTileThreads) agg_bwd_tile_kernel(const __grid_constant__ KernelArgs k,
+                                                                    const __grid_constant__ TileCfg tc) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const AggPlan& P = k.plan;
+  const int TN = tc.TN, tid = threadIdx.x;
+  Tile<VEC, NS> T;
+  tile_prologue<MODE, VEC, NS>(k, tc, smem, T);
+  Vec<VEC>* sG = reinterpret_cast<Vec<VEC>*>(smem + tc.off_g);
+
+  int tower = 0, cg = 0;
+  Vec<VEC> hv = vfill<VEC>(0.f), qv = vfill<VEC>(0.f), dh = vfill<VEC>(0.f);
+  const int D = T.ne1 - T.ne0;
+  // scaler coefficients are needed before the gradient slabs can be folded: compute them up front
+  for (int j = tid; j < T.nv * DGN_MAX_SCALERS; j += kTileThreads) {
+    const int l = j / DGN_MAX_SCALERS, s = j - l * DGN_MAX_SCALERS;
+    float cf = 1.f;
+    if (P.S > 1 && s < P.S) {
+      const float ld = __ldg(k.log_deg + T.v0 + l);
+      const int kind = P.scaler_kind[s];
+      cf = (kind == DGN_SCALE_AMPLIFICATION) ? __fdiv_rn(ld, P.avg_log)
+           : (kind == DGN_SCALE_ATTENUATION) ? __fdiv_rn(P.avg_log, ld) : 1.f;
+    }
+    T.s_coef[s * TN + l] = cf;
+  }
+  __syncthreads();
+  if (T.active) {
+    tower = T.c / P.Fg;
+    cg = T.c - tower * P.Fg;
+    if (k.g_hcopy) dh = vload_stream<VEC>(k.g_hcopy + (size_t)T.v * k.ld_hc + (size_t)tower * k.hc_gs + cg);
+    if (k.d_h_add) {
+      const Vec<VEC> t = vload_stream<VEC>(k.d_h_add + (size_t)T.v * k.ld_dha + T.c);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) dh.a[i] += t.a[i];
+    }
+    if (D > 0) {
+      // phase 1: G_a = sum_s coef_s * g_out[v, s, a, :] for every aggregator, staged in shared memory; the S*A
+      // slab loads dominate this kernel's traffic and are issued back to back (unroll 4 => 4*S in flight)
+      float coef[DGN_MAX_SCALERS];
+#pragma unroll
+      for (int s = 0; s < DGN_MAX_SCALERS; ++s) coef[s] = T.s_coef[s * TN + T.ln];
+      const float* grow = k.g_out + (size_t)T.v * k.ld_out + (size_t)tower * k.out_gs + cg;
+      const int scaler_stride = P.A * P.Fg;
+#pragma unroll 4
+      for (int a = 0; a < P.A; ++a) {
+        Vec<VEC> G = vfill<VEC>(0.f);
+        const float* src = grow + a * P.Fg;
+#pragma unroll
+        for (int s = 0; s < DGN_MAX_SCALERS; ++s) {
+          if (s < P.S) {
+            const Vec<VEC> gs = vload_stream<VEC>(src + s * scaler_stride);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) G.a[i] = fmaf(coef[s], gs.a[i], G.a[i]);
+          }
+        }
+        sG[a * kTileThreads + tid] = G;
+      }
+      hv = vload<VEC>(k.h_in + (size_t)T.v * k.ld_h + T.c);
+      if constexpr (MODE == DGN_MSG_AFFINE) {
+        qv = vload<VEC>(k.q + (size_t)T.v * k.ld_q + T.c);
+        if (k.q_bias) {
+          const Vec<VEC> bv = vload<VEC>(k.q_bias + T.c);
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) qv.a[i] += bv.a[i];
+        }
+      }
+    }
+  }
+
+  // ---- pass 1: recompute the row statistics ------------------------------------------------------------
+  RowAcc<VEC, NS, ISO> R;
+  acc_init(R);
+  bool waited = false;
+  const bool single_batch = (T.E1 - T.E0) <= kEB;
+  for (int b0 = T.E0; b0 < T.E1; b0 += kEB) {
+    const int nb = min(kEB, T.E1 - b0);
+    tile_weights<VEC, NS>(k, tc, T, b0, nb, true);
+    if (T.staged && !waited) { mbar_wait(T.s_bar, 0); waited = true; }
+    if (T.active) {
+      const int i0 = max(T.ne0, b0) - b0, i1 = min(T.ne1, b0 + nb) - b0;
+#pragma unroll 4
+      for (int i = i0; i < i1; ++i) {
+        const Vec<VEC> m = tile_message<MODE, VEC, NS>(k, T, T.s_src[i], b0 + i, qv);
+        acc_edge<VEC, NS, ISO>(P, R, m, T.s_w, i);
+      }
+    }
+    if (!single_batch) __syncthreads();                // the next batch overwrites s_src / s_w
+  }
+  if (single_batch) __syncthreads();                   // s_zw / s_zabs complete before the factors are derived
+  tile_factors<VEC, NS>(k, tc, T);
+  __syncthreads();
+
+  // ---- fold the S*A gradient slabs into per-column coefficients ---------------------------------------
+  Vec<VEC> c0 = vfill<VEC>(0.f), c1 = vfill<VEC>(0.f), gmx = vfill<VEC>(0.f), gmn = vfill<VEC>(0.f);
+  Vec<VEC> cs[NS > 0 ? NS : 1];
+#pragma unroll
+  for (int s = 0; s < NS; ++s) cs[s] = vfill<VEC>(0.f);
+  if (T.active && D > 0) {
+    const float fD = (float)D, rD = __frcp_rn(fD);
+    Vec<VEC> mean, var;
+    mean_var<VEC, ISO>(R.sum, R.sq, fD, mean, var);
+    for (int a = 0; a < P.A; ++a) {                    // isotropic aggregators
+      const int kind = P.agg_kind[a];
+      if (kind >= DGN_AGG_DIR_AV) continue;
+      const Vec<VEC> G = sG[a * kTileThreads + tid];
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        if (kind == DGN_AGG_MEAN) c0.a[i] += G.a[i] * rD;
+        else if (kind == DGN_AGG_SUM) c0.a[i] += G.a[i];
+        else if (kind == DGN_AGG_MAX) gmx.a[i] += G.a[i];
+        else if (kind == DGN_AGG_MIN) gmn.a[i] += G.a[i];
+        else {
+          // var = relu(t), t = E[m^2] - E[m]^2 ; dt/dm_u = 2 (m_u - mean) / D ; relu'(0) = 0
+          float gv = (var.a[i] > 0.f) ? G.a[i] : 0.f;
+          if (kind == DGN_AGG_STD) gv *= 0.5f * rsqrtf(var.a[i] + DGN_EPS);
+          const float two_over_d = 2.f * gv * rD;
+          c1.a[i] += two_over_d;
+          c0.a[i] -= two_over_d * mean.a[i];
+        }
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {                     // directional aggregators, static slot index
+      if (s >= P.n_slots) break;
+      const float f0 = T.s_f0[s * TN + T.ln], f1 = T.s_f1[s * TN + T.ln];
+      unsigned todo = P.slot_aggs[s];
+      while (todo) {
+        const int a = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int kind = P.agg_kind[a];
+        const Vec<VEC> G = sG[a * kTileThreads + tid];
+        const Vec<VEC>& A1 = R.acc[s];
+        if (kind == DGN_AGG_DIR_AV) {
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) cs[s].a[i] = fmaf(G.a[i], f0, cs[s].a[i]);
+        } else if (kind == DGN_AGG_DIR_DX_BALANCED) {
+          if constexpr (NS >= 2) {
+            constexpr int LAST = NS - 1;
+            const int s2 = (s + 1 <= LAST) ? s + 1 : LAST;
+            const float g0 = T.s_f0[s2 * TN + T.ln], wsum = f1 + T.s_f1[s2 * TN + T.ln];
+            const Vec<VEC>& A2 = R.acc[s2];
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+              const float sv = A1.a[i] * f0 + A2.a[i] * g0 - wsum * hv.a[i];
+              const float g = G.a[i] * sign0(sv);
+              cs[s].a[i] = fmaf(g, f0, cs[s].a[i]);
+              cs[s2].a[i] = fmaf(g, g0, cs[s2].a[i]);
+              dh.a[i] -= wsum * g;
+            }
+          }
+        } else {                                       // dx / dx-no-abs
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) {
+            float g = G.a[i];
+            if (kind == DGN_AGG_DIR_DX) g *= sign0(A1.a[i] * f0 - f1 * hv.a[i]);   // same expression as the forward
+            cs[s].a[i] = fmaf(g, f0, cs[s].a[i]);
+            dh.a[i] -= f1 * g;
+          }
+        }
+      }
+    }
+  }
+
+  // ---- pass 2: per-edge message gradients ----------------------------------------------------------------
+  Vec<VEC> dq = vfill<VEC>(0.f);
+  unsigned given = 0u;          // bit i: max gradient of column i already routed; bit 4+i: min
+  for (int b0 = T.E0; b0 < T.E1; b0 += kEB) {
+    const int nb = min(kEB, T.E1 - b0);
+    if (!single_batch) tile_weights<VEC, NS>(k, tc, T, b0, nb, false);   // weights of this batch again
+    if (T.active) {
+      const int i0 = max(T.ne0, b0) - b0, i1 = min(T.ne1, b0 + nb) - b0;
+#pragma unroll 2
+      for (int i = i0; i < i1; ++i) {
+        const int e = b0 + i;
+        const Vec<VEC> m = tile_message<MODE, VEC, NS>(k, T, T.s_src[i], e, qv);
+        Vec<VEC> dm;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          float g = fmaf(c1.a[j], m.a[j], c0.a[j]);
+          if constexpr (ISO) {
+            // torch.max / torch.min send the whole gradient to the FIRST extremal mailbox entry
+            if (m.a[j] == R.mx.a[j] && !(given & (1u << j))) { g += gmx.a[j]; given |= 1u << j; }
+            if (m.a[j] == R.mn.a[j] && !(given & (16u << j))) { g += gmn.a[j]; given |= 16u << j; }
+          }
+          dm.a[j] = g;
+        }
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+          if (s < P.n_slots) {
+            const float w = T.s_w[s * kEB + i];
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) dm.a[j] = fmaf(w, cs[s].a[j], dm.a[j]);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) dq.a[j] += dm.a[j];
+        if (k.edge_ws) vstore<VEC>(k.edge_ws + (size_t)e * P.F + T.c, dm);
+        if (k.d_r) {
+          const int id = k.in_eid ? __ldg(k.in_eid + e) : e;
+          vstore<VEC>(k.d_r + (size_t)id * k.ld_dr + T.c, dm);
+        }
+      }
+    }
+    if (!single_batch) __syncthreads();
+  }
+  if (T.active) {
+    if (k.d_q) vstore<VEC>(k.d_q + (size_t)T.v * k.ld_dq + T.c, dq);
+    if (k.d_h) vstore<VEC>(k.d_h + (size_t)T.v * k.ld_dh + T.c, dh);
+  }
+}
+
+// ======================================================================================================
+// host side
+// ======================================================================================================
+static inline int align_up(int x, int a) { return (x + a - 1) / a * a; }
+
+static bool make_tile_cfg(const KernelArgs& k, int vec, int NS, bool backward, TileCfg& tc) {
+  const AggPlan& P = k.plan;
+  if (P.has_exp || P.chunks > kTileThreads || P.chunks <= 0) return false;
+  tc.TN = kTileThreads / P.chunks;
+  if (tc.TN > 64) tc.TN = 64;
+  const int TN = tc.TN, ns = NS > 0 ? NS : 1;
+  int off = align_up((TN + 1) * 4, 16);
+  tc.off_ev = off;   off += align_up(ns * TN * 4, 16);
+  tc.off_zw = off;   off += align_up(ns * TN * 4, 16);
+  tc.off_zabs = off; off += align_up(ns * TN * 4, 16);
+  tc.off_f0 = off;   off += align_up(ns * TN * 4, 16);
+  tc.off_f1 = off;   off += align_up(ns * TN * 4, 16);
+  tc.off_coef = off; off += align_up(DGN_MAX_SCALERS * TN * 4, 16);
+  tc.off_src = off;  off += kEB * 4;
+  tc.off_w = off;    off += ns * kEB * 4;
+  tc.off_bar = off;  off += 16;
+  tc.off_red = off;  off += 64;
+  tc.off_g = off;
+  if (backward) off += P.A * kTileThreads * vec * 4;
+  off = align_up(off, 128);
+  tc.off_win = off;
+  // source-window staging: only the 128-bit path, gathers from x (not DENSE); budget keeps >= 2 CTAs per SM
+  tc.win_rows = 0;
+  if (vec == 4 && k.mode != DGN_MSG_DENSE) {
+    const int budget = 100 * 1024 - off;
+    const int rows = budget > 0 ? budget / (P.F * 4) : 0;
+    if (rows >= 32) tc.win_rows = rows;
+  }
+  off += tc.win_rows * P.F * 4;
+  tc.total = off;
+  return tc.total <= 200 * 1024;
+}
+
+template <typename Kern>
+static int launch_tile(Kern kern, const KernelArgs& k, const TileCfg& tc, cudaStream_t st) {
+  if (k.N == 0) return DGN_OK;
+  if (tc.total > 48 * 1024) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return DGN_ERR_CUDA;
+  }
+  const unsigned grid = (unsigned)((k.N + tc.TN - 1) / tc.TN);
+  kern<<<grid, kTileThreads, tc.total, st>>>(k, tc);
+  return cudaGetLastError() == cudaSuccess ? DGN_OK : DGN_ERR_CUDA;
+}
+
+static bool plan_needs_iso(const AggPlan& P) {
+  for (int a = 0; a < P.A; ++a) {
+    const int kd = P.agg_kind[a];
+    if (kd == DGN_AGG_MAX || kd == DGN_AGG_MIN || kd == DGN_AGG_STD || kd == DGN_AGG_VAR) return true;
+  }
+  return false;
+}
+
+template <bool BWD, int MODE, int VEC, int NS>
+static int launch_iso(const KernelArgs& k, cudaStream_t st) {
+  TileCfg tc;
+  if (!make_tile_cfg(k, VEC, NS, BWD, tc)) return DGN_ERR_UNSUPPORTED;
+  const bool iso = plan_needs_iso(k.plan);
+  if constexpr (BWD) {
+    return iso ? launch_tile(agg_bwd_tile_kernel<MODE, VEC, NS, true>, k, tc, st)
+               : launch_tile(agg_bwd_tile_kernel<MODE, VEC, NS, false>, k, tc, st);
+  } else {
+    return iso ? launch_tile(agg_fwd_tile_kernel<MODE, VEC, NS, true>, k, tc, st)
+               : launch_tile(agg_fwd_tile_kernel<MODE, VEC, NS, false>, k, tc, st);
+  }
+}
+
+template <bool BWD, int MODE, int VEC>
+static int launch_slots(const KernelArgs& k, cudaStream_t st) {
+  const int ns = k.plan.n_slots;
+  if (ns == 0) return launch_iso<BWD, MODE, VEC, 0>(k, st);
+  if (ns <= 2) return launch_iso<BWD, MODE, VEC, 2>(k, st);
+  if (ns <= 4) return launch_iso<BWD, MODE, VEC, 4>(k, st);
+  return launch_iso<BWD, MODE, VEC, 8>(k, st);
+}
+
+template <bool BWD, int VEC>
+static int launch_mode(const KernelArgs& k, cudaStream_t st) {
+  if (k.mode == DGN_MSG_SOURCE) return launch_slots<BWD, DGN_MSG_SOURCE, VEC>(k, st);
+  if (k.mode == DGN_MSG_AFFINE) return launch_slots<BWD, DGN_MSG_AFFINE, VEC>(k, st);
+  return launch_slots<BWD, DGN_MSG_DENSE, VEC>(k, st);
+}
+
+// Returns DGN_ERR_UNSUPPORTED when the tile kernels do not cover the request (caller falls back).
+int launch_forward_tile(const KernelArgs& k, int vec, cudaStream_t st) {
+  if (k.plan.has_exp) return DGN_ERR_UNSUPPORTED;
+  if (vec == 4) return launch_mode<false, 4>(k, st);
+  if (vec == 2) return launch_mode<false, 2>(k, st);
+  return launch_mode<false, 1>(k, st);
+}
+
+int launch_backward_tile_dst(const KernelArgs& k, int vec, cudaStream_t st) {
+  if (k.plan.has_exp) return DGN_ERR_UNSUPPORTED;
+  if (vec == 4) return launch_mode<true, 4>(k, st);
+  if (vec == 2) return launch_mode<true, 2>(k, st);
+  return launch_mode<true, 1>(k, st);
+}
+
+}  // namespace dgn

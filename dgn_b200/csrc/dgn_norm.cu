@@ -163,12 +163,14 @@ __device__ __forceinline__ float masked_grad(const DgnNormArgs& a, const DgnNorm
 
 constexpr int kBwdSums = 5;   // sum g1, sum g1*xhat, sum s*g1, sum s, sum s*xhat   (s = snorm_n)
 
+// The five column sums are accumulated and merged in fp64: d_bias (and to a lesser degree d_gamma / d_beta)
+// are small differences of large sums, and fp32 partial sums would leave ~1e-5 relative noise in them.
 __global__ void __launch_bounds__(kTX * kTY) norm_bwd_reduce_kernel(const DgnNormArgs a, const DgnNormGrad g) {
   const int n = rows_of(a);
   const int col = blockIdx.y * kTX + threadIdx.x;
   int r0, r1;
   slab(n, blockIdx.x, r0, r1);
-  float acc[kBwdSums] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  double acc[kBwdSums] = {0.0, 0.0, 0.0, 0.0, 0.0};
   if (col < a.n_cols) {
     const float mean = a.gamma ? a.stats[col] : 0.f, rstd = a.gamma ? a.stats[a.n_cols + col] : 1.f;
     const float ga = a.gamma ? a.gamma[col] : 1.f, be = a.gamma ? a.beta[col] : 0.f;
@@ -177,22 +179,22 @@ __global__ void __launch_bounds__(kTX * kTY) norm_bwd_reduce_kernel(const DgnNor
       float xhat;
       const float g1 = masked_grad(a, g, r, col, mean, rstd, ga, be, yb, xhat);
       const float sn = a.snorm ? a.snorm[r] : 1.f;
-      acc[0] += g1;
-      acc[1] = fmaf(g1, xhat, acc[1]);
-      acc[2] = fmaf(sn, g1, acc[2]);
-      acc[3] += sn;
-      acc[4] = fmaf(sn, xhat, acc[4]);
+      acc[0] += (double)g1;
+      acc[1] += (double)g1 * (double)xhat;
+      acc[2] += (double)sn * (double)g1;
+      acc[3] += (double)sn;
+      acc[4] += (double)sn * (double)xhat;
     }
   }
-  __shared__ float sh[kBwdSums][kTY][kTX];
+  __shared__ double sh[kBwdSums][kTY][kTX];
 #pragma unroll
   for (int q = 0; q < kBwdSums; ++q) sh[q][threadIdx.y][threadIdx.x] = acc[q];
   __syncthreads();
   if (threadIdx.y == 0 && col < a.n_cols) {
-    float* part = g.scratch + (size_t)blockIdx.x * kBwdSums * a.n_cols;
+    double* part = reinterpret_cast<double*>(g.scratch) + (size_t)blockIdx.x * kBwdSums * a.n_cols;
 #pragma unroll
     for (int q = 0; q < kBwdSums; ++q) {
-      float t = acc[q];
+      double t = acc[q];
       for (int j = 1; j < kTY; ++j) t += sh[q][j][threadIdx.x];
       part[q * a.n_cols + col] = t;
     }
@@ -203,15 +205,16 @@ __global__ void __launch_bounds__(kTX * kTY) norm_bwd_apply_kernel(const DgnNorm
   const int n = rows_of(a);
   const int col = blockIdx.y * kTX + threadIdx.x;
   __shared__ float s_b[kTX], s_g[kTX];
-  __shared__ float sh[kBwdSums][kTY][kTX];
+  __shared__ double sh[kBwdSums][kTY][kTX];
   {
     constexpr int PER = kParts / kTY;
-    float acc[kBwdSums] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    double acc[kBwdSums] = {0.0, 0.0, 0.0, 0.0, 0.0};
     if (col < a.n_cols) {
-      float v[PER][kBwdSums];
+      double v[PER][kBwdSums];
 #pragma unroll
       for (int j = 0; j < PER; ++j) {                  // independent loads, fixed summation order
-        const float* part = g.scratch + (size_t)(threadIdx.y + j * kTY) * kBwdSums * a.n_cols;
+        const double* part = reinterpret_cast<const double*>(g.scratch) +
+                             (size_t)(threadIdx.y + j * kTY) * kBwdSums * a.n_cols;
 #pragma unroll
         for (int q = 0; q < kBwdSums; ++q) v[j][q] = part[q * a.n_cols + col];
       }
@@ -227,24 +230,23 @@ __global__ void __launch_bounds__(kTX * kTY) norm_bwd_apply_kernel(const DgnNorm
 #pragma unroll
       for (int q = 0; q < kBwdSums; ++q)
         for (int j = 1; j < kTY; ++j) acc[q] += sh[q][j][threadIdx.x];
-      s_b[threadIdx.x] = acc[0];
-      s_g[threadIdx.x] = acc[1];
+      const double inv_n = (n > 0) ? 1.0 / (double)n : 0.0;
+      s_b[threadIdx.x] = (float)(acc[0] * inv_n);      // mean of g1
+      s_g[threadIdx.x] = (float)(acc[1] * inv_n);      // mean of g1 * xhat
       if (blockIdx.x == 0) {
         const float keep = g.accumulate ? 1.f : 0.f;
         if (a.gamma) {
-          if (g.d_beta) g.d_beta[col] = keep * g.d_beta[col] + acc[0];
-          if (g.d_gamma) g.d_gamma[col] = keep * g.d_gamma[col] + acc[1];
+          if (g.d_beta) g.d_beta[col] = keep * g.d_beta[col] + (float)acc[0];
+          if (g.d_gamma) g.d_gamma[col] = keep * g.d_gamma[col] + (float)acc[1];
         }
         if (g.d_bias) {
           // d_bias = sum_r d_y[r] with d_y = s * ga*rstd*(g1 - mb - xhat*mg) (training BN), s*ga*rstd*g1 (eval), s*g1 (no BN)
-          float db = acc[2];
+          double db = acc[2];
           if (a.gamma) {
-            const float ga = a.gamma[col], rstd = a.stats[a.n_cols + col];
-            const float inv_n = (n > 0) ? 1.f / (float)n : 0.f;
             if (a.training) db = acc[2] - (acc[0] * inv_n) * acc[3] - (acc[1] * inv_n) * acc[4];
-            db *= ga * rstd;
+            db *= (double)a.gamma[col] * (double)a.stats[a.n_cols + col];
           }
-          g.d_bias[col] = keep * g.d_bias[col] + db;
+          g.d_bias[col] = keep * g.d_bias[col] + (float)db;
         }
       }
     }
@@ -254,9 +256,8 @@ __global__ void __launch_bounds__(kTX * kTY) norm_bwd_apply_kernel(const DgnNorm
   const float mean = a.gamma ? a.stats[col] : 0.f, rstd = a.gamma ? a.stats[a.n_cols + col] : 1.f;
   const float ga = a.gamma ? a.gamma[col] : 1.f, be = a.gamma ? a.beta[col] : 0.f;
   const float yb = a.y_bias ? a.y_bias[col] : 0.f;
-  const float inv_n = (n > 0) ? 1.f / (float)n : 0.f;
-  const float mb = (a.gamma && a.training) ? s_b[threadIdx.x] * inv_n : 0.f;
-  const float mg = (a.gamma && a.training) ? s_g[threadIdx.x] * inv_n : 0.f;
+  const float mb = (a.gamma && a.training) ? s_b[threadIdx.x] : 0.f;
+  const float mg = (a.gamma && a.training) ? s_g[threadIdx.x] : 0.f;
   for (int r = blockIdx.x * kTY + threadIdx.y; r < a.n_rows; r += gridDim.x * kTY) {
     float dy = 0.f, dres = 0.f;
     if (r < n) {

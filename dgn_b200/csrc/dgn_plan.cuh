@@ -255,6 +255,12 @@ int launch_forward(const KernelArgs& k, int vec, cudaStream_t st);
 int launch_backward(const KernelArgs& k, int vec, float* d_x, int ld_dx, const float* addend, int ld_add,
                     cudaStream_t st);
 
+// Tile kernels (dgn_agg_tile.cu): the fast path.  Return DGN_ERR_UNSUPPORTED when they do not cover the request
+// (softmax aggregators, F/VEC > 256) - the generic kernels above then take over.  DGN_NO_TILE=1 disables them.
+int launch_forward_tile(const KernelArgs& k, int vec, cudaStream_t st);
+int launch_backward_tile_dst(const KernelArgs& k, int vec, cudaStream_t st);
+bool tile_kernels_enabled();
+
 // Picks the vector width: the widest the operands' alignment allows; `narrow_small` lets small launches
 // (that would not fill the 148 SMs) use 8 B lanes for more, shorter threads.  DGN_FORCE_VEC overrides.
 int choose_vec(int max_vec, long long n_nodes, int n_feat, bool narrow_small);

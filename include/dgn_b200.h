@@ -37,7 +37,7 @@ extern "C" {
 #define DGN_MAX_SCALERS 4   /* scalers per layer (the reference registry has 3)             */
 #define DGN_MAX_SLOTS 8     /* distinct eigen-weighted feature sums one launch can carry    */
 #define DGN_EPS 1e-8f       /* rb/nets/aggregators.py:5                                     */
-#define DGN_NORM_WS_FLOATS(C) (320 * (C)) /* fp32 workspace of dgn_norm_* for C columns         */
+#define DGN_NORM_WS_FLOATS(C) (640 * (C)) /* fp32 workspace of dgn_norm_* for C columns         */
 
 typedef enum {
   DGN_OK = 0,

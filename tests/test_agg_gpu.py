@@ -266,3 +266,17 @@ def test_too_many_slots_is_reported():
     x = torch.randn(g.number_of_nodes(), 8, device=DEV)
     with pytest.raises(_lib.DgnError, match="unsupported"):
         aggregate(g, spec, _lib.MSG_SOURCE, x, g.ndata["eig"], x=x)
+
+
+def test_generic_kernels_still_match_oracle_when_tile_kernels_are_disabled():
+    """The tile kernels are the default path; DGN_NO_TILE=1 forces the generic per-(node,chunk) kernels,
+    which remain the fallback for softmax aggregators / very wide rows.  Re-run the oracle comparison on them."""
+    import os
+    import subprocess
+    import sys
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, DGN_NO_TILE="1")
+    out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(repo, "tests", "test_agg_gpu.py"), "-q", "-x",
+                          "-m", "gpu", "-k", "aggregate_matches_oracle or cat_input or towers_group or registry_callable"],
+                         env=env, capture_output=True, text=True, cwd=repo)
+    assert out.returncode == 0, out.stdout[-3000:]
