@@ -1,35 +1,42 @@
 // Fused DGN aggregation, tile kernels (sm_100a) - the fast path of dgn_agg_forward / dgn_agg_backward.
 //
 // A CTA owns a tile of TN consecutive destination nodes; thread = (local node, VEC-column chunk).
-// Everything that does not depend on the feature column is computed ONCE per node / per edge and staged
-// in shared memory instead of once per (node, chunk) thread:
-//   * the tile's slice of the CSR (in_ptr, in_src),
-//   * the k eigenvector components of the destination nodes and the per-edge eigen-weights w_s(delta_uv),
-//   * the per-node normalisers (sum |delta|, sum delta ...) and the factors derived from them
-//     (1/Z, W = sum(w)/Z), the degree-scaler coefficients.
-// The column threads then only do vector work: gather the message row, FMA it into the accumulators
-// with weights read from shared memory (broadcast), write S*A slabs with streaming 128-bit stores.
 //
-// Batched graphs are block diagonal: all sources of a tile lie in a narrow window of node ids.  When
-// that window is small and re-used enough (in-degree >> 1: CIFAR kNN, SBM PATTERN) the source rows of
-// the window are brought into shared memory with one TMA bulk copy (cp.async.bulk + mbarrier) and the
-// per-edge gathers become shared-memory reads instead of L2 round trips.
+// (1) Everything that does not depend on the feature column is computed ONCE per node / per edge and
+//     staged in shared memory instead of once per (node, chunk) thread: the tile's slice of the CSR, the k
+//     eigenvector components of the destination nodes, the per-edge eigen-weights w_s(delta_uv), the
+//     per-node normalisers (sum |delta|, sum delta ...) with the factors derived from them (1/Z, W) and the
+//     degree-scaler coefficients.  The column threads only do vector work.
+//
+// (2) The gather is latency bound (dependent in_ptr -> in_src -> row chain), so what buys bandwidth is
+//     memory-level parallelism.  All bulky operands reach shared memory through the TMA engine
+//     (cp.async.bulk + mbarrier complete_tx), i.e. without holding registers or issue slots:
+//       * the gathered message rows of a batch of edge slots: one row-sized bulk copy per edge, all rows of
+//         the batch in flight at once while the threads compute the eigen-weights;
+//       * when the tile's sources fall into a narrow node window that is re-used enough (block-diagonal
+//         batches with in-degree >> 1: CIFAR kNN, SBM PATTERN), the whole window once per tile instead, so
+//         the per-edge gathers become shared-memory reads;
+//       * backward: the tile's S*A gradient slabs (the dominant traffic), one bulk copy per node row.
 //
 // Edges of a tile are processed in batches of EB slots so shared memory stays bounded for any degree.
-// The softmax aggregators (W_EXP) and F > 1024 fall back to the generic kernels in dgn_agg_fwd/bwd.cu.
+// The softmax aggregators (W_EXP) and F/VEC > 256 fall back to the generic kernels in dgn_agg_fwd/bwd.cu.
 #include <limits.h>
 
 #include "dgn_plan.cuh"
 
 namespace dgn {
 
-constexpr int kTileThreads = 256;
-constexpr int kEB = 512;             // edge slots per batch
+constexpr int kMaxTileThreads = 256;
 
 struct TileCfg {
+  int threads;                       // block size (128 or 256)
   int TN;                            // destination nodes per tile
+  int EB;                            // edge slots per batch
   int win_rows;                      // capacity of the staged source window in rows (0 = never stage)
-  int off_ev, off_zw, off_zabs, off_f0, off_f1, off_coef, off_src, off_w, off_bar, off_red, off_win, off_g;
+  int use_msg;                       // gathered message rows are bulk-copied into shared memory per batch
+  int use_gt;                        // backward: the tile's gradient slabs are bulk-copied into shared memory
+  int gt_row;                        // floats per node in the gradient tile (S*A*F)
+  int off_ev, off_zw, off_zabs, off_f0, off_f1, off_coef, off_src, off_w, off_bar, off_red, off_win, off_msg, off_gt;
   int total;
 };
 
@@ -37,11 +44,12 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// TMA bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                    smem_u32(dst)),
@@ -60,18 +68,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // Shared-memory view of one tile + the state every thread needs.
-template <int VEC, int NS>
 struct Tile {
   int* s_ptr; float* s_ev; float* s_zw; float* s_zabs; float* s_f0; float* s_f1; float* s_coef;
-  int* s_src; float* s_w; uint64_t* s_bar; int* s_red; float* s_win;
-  int v0, nv, E0, E1, ln, c, v, ne0, ne1, umin;
-  bool active, staged;
+  int* s_src; float* s_w; uint64_t* s_bar; int* s_red; float* s_win; float* s_msg; float* s_gt;
+  int v0, nv, E0, E1, ln, c, v, ne0, ne1, umin, TN, EB;
+  uint32_t msg_parity;
+  bool active, staged, use_msg;
 };
+// s_bar[0]: source window, s_bar[1]: message rows of the current batch, s_bar[2]: gradient tile
 
 template <int MODE, int VEC, int NS>
-__device__ __forceinline__ void tile_prologue(const KernelArgs& k, const TileCfg& tc, unsigned char* smem, Tile<VEC, NS>& T) {
+__device__ __forceinline__ void tile_prologue(const KernelArgs& k, const TileCfg& tc, unsigned char* smem, Tile& T) {
   const AggPlan& P = k.plan;
-  const int tid = threadIdx.x, TN = tc.TN;
+  const int tid = threadIdx.x, TN = tc.TN, nthr = blockDim.x;
   T.s_ptr = reinterpret_cast<int*>(smem);
   T.s_ev = reinterpret_cast<float*>(smem + tc.off_ev);
   T.s_zw = reinterpret_cast<float*>(smem + tc.off_zw);
@@ -84,14 +93,25 @@ __device__ __forceinline__ void tile_prologue(const KernelArgs& k, const TileCfg
   T.s_bar = reinterpret_cast<uint64_t*>(smem + tc.off_bar);
   T.s_red = reinterpret_cast<int*>(smem + tc.off_red);
   T.s_win = reinterpret_cast<float*>(smem + tc.off_win);
+  T.s_msg = reinterpret_cast<float*>(smem + tc.off_msg);
+  T.s_gt = reinterpret_cast<float*>(smem + tc.off_gt);
+  T.TN = TN;
+  T.EB = tc.EB;
   T.v0 = blockIdx.x * TN;
   T.nv = min(TN, k.N - T.v0);
   T.ln = tid / P.chunks;
   T.c = (tid - T.ln * P.chunks) * VEC;
   T.active = T.ln < T.nv;
   T.v = T.v0 + T.ln;
-  for (int i = tid; i <= T.nv; i += kTileThreads) T.s_ptr[i] = __ldg(k.in_ptr + T.v0 + i);
-  for (int i = tid; i < NS * TN; i += kTileThreads) {
+  T.msg_parity = 0;
+  if (tid == 0) {
+    mbar_init(&T.s_bar[0], 1);
+    mbar_init(&T.s_bar[1], 1);
+    mbar_init(&T.s_bar[2], 1);
+    mbar_fence_init();
+  }
+  for (int i = tid; i <= T.nv; i += nthr) T.s_ptr[i] = __ldg(k.in_ptr + T.v0 + i);
+  for (int i = tid; i < NS * TN; i += nthr) {
     const int s = i / TN, l = i - s * TN;
     T.s_ev[i] = (s < P.n_slots && l < T.nv) ? __ldg(k.eig + (size_t)(T.v0 + l) * k.ld_eig + P.slot_eig[s]) : 0.f;
     T.s_zw[i] = 0.f;
@@ -104,11 +124,12 @@ __device__ __forceinline__ void tile_prologue(const KernelArgs& k, const TileCfg
   T.ne1 = T.active ? T.s_ptr[T.ln + 1] : 0;
   T.staged = false;
   T.umin = 0;
+  T.use_msg = tc.use_msg != 0;
   if constexpr (MODE != DGN_MSG_DENSE && VEC == 4) {
     if (tc.win_rows > 0 && T.E1 > T.E0) {
       // source window of the tile: block-wide min / max of in_src over the tile's slots
       int lo = INT_MAX, hi = -1;
-      for (int e = T.E0 + tid; e < T.E1; e += kTileThreads) {
+      for (int e = T.E0 + tid; e < T.E1; e += nthr) {
         const int u = __ldg(k.in_src + e);
         lo = min(lo, u);
         hi = max(hi, u);
@@ -121,40 +142,43 @@ __device__ __forceinline__ void tile_prologue(const KernelArgs& k, const TileCfg
       if ((tid & 31) == 0) { T.s_red[tid >> 5] = lo; T.s_red[8 + (tid >> 5)] = hi; }
       __syncthreads();
       lo = T.s_red[0]; hi = T.s_red[8];
-#pragma unroll
-      for (int w = 1; w < kTileThreads / 32; ++w) { lo = min(lo, T.s_red[w]); hi = max(hi, T.s_red[8 + w]); }
+      for (int w = 1; w < nthr / 32; ++w) { lo = min(lo, T.s_red[w]); hi = max(hi, T.s_red[8 + w]); }
       const int rows = hi - lo + 1;
       // stage only when the window fits and every staged row is re-used on average at least twice
       T.staged = rows <= tc.win_rows && (T.E1 - T.E0) >= 2 * rows;
       if (T.staged) {
         T.umin = lo;
+        T.use_msg = false;
         const uint32_t row_bytes = (uint32_t)P.F * 4u;
-        if (tid == 0) {
-          mbar_init(T.s_bar, 1);
-          mbar_expect_tx(T.s_bar, row_bytes * (uint32_t)rows);
-        }
-        __syncthreads();
+        if (tid == 0) mbar_expect_tx(&T.s_bar[0], row_bytes * (uint32_t)rows);
         if (k.ld_x == P.F) {                      // rows are contiguous: one bulk copy
-          if (tid == 0) bulk_g2s(T.s_win, k.x + (size_t)lo * k.ld_x, row_bytes * (uint32_t)rows, T.s_bar);
+          if (tid == 0) bulk_g2s(T.s_win, k.x + (size_t)lo * k.ld_x, row_bytes * (uint32_t)rows, &T.s_bar[0]);
         } else {
-          for (int r = tid; r < rows; r += kTileThreads)
-            bulk_g2s(T.s_win + (size_t)r * P.F, k.x + (size_t)(lo + r) * k.ld_x, row_bytes, T.s_bar);
+          for (int r = tid; r < rows; r += nthr)
+            bulk_g2s(T.s_win + (size_t)r * P.F, k.x + (size_t)(lo + r) * k.ld_x, row_bytes, &T.s_bar[0]);
         }
       }
     }
   }
 }
 
-// phase A: eigen-weights of one batch of edge slots [b0, b0+nb) -> s_src / s_w; then the per-node sums
-template <int VEC, int NS>
-__device__ __forceinline__ void tile_weights(const KernelArgs& k, const TileCfg& tc, Tile<VEC, NS>& T, int b0, int nb,
-                                             bool accumulate_z) {
+// Phase A of one batch of edge slots [b0, b0+nb): kick off the message-row copies, compute the eigen-weights
+// into s_src / s_w, then (optionally) add this batch to the per-(node, slot) sums.
+template <int MODE, int VEC, int NS>
+__device__ __forceinline__ void tile_batch_begin(const KernelArgs& k, Tile& T, int b0, int nb, bool accumulate_z) {
   const AggPlan& P = k.plan;
-  const int tid = threadIdx.x, TN = tc.TN;
-  for (int i = tid; i < nb; i += kTileThreads) {
+  const int tid = threadIdx.x, TN = T.TN, nthr = blockDim.x;
+  if (T.use_msg && tid == 0) mbar_expect_tx(&T.s_bar[1], (uint32_t)nb * (uint32_t)P.F * 4u);
+  for (int i = tid; i < nb; i += nthr) {
     const int e = b0 + i;
     const int u = __ldg(k.in_src + e);
     T.s_src[i] = u;
+    if (T.use_msg) {                            // whole message row -> shared memory, asynchronously
+      const float* row;
+      if constexpr (MODE == DGN_MSG_DENSE) row = k.r + (size_t)(k.in_eid ? __ldg(k.in_eid + e) : e) * k.ld_r;
+      else row = k.x + (size_t)u * k.ld_x;
+      bulk_g2s(T.s_msg + (size_t)i * P.F, row, (uint32_t)P.F * 4u, &T.s_bar[1]);
+    }
     if constexpr (NS > 0) {
       int lo = 0, hi = T.nv;                    // local destination: largest l with s_ptr[l] <= e
       while (hi - lo > 1) {
@@ -165,7 +189,7 @@ __device__ __forceinline__ void tile_weights(const KernelArgs& k, const TileCfg&
       for (int s = 0; s < NS; ++s) {
         if (s < P.n_slots) {
           const float d = __ldg(k.eig + (size_t)u * k.ld_eig + P.slot_eig[s]) - T.s_ev[s * TN + lo];
-          T.s_w[s * kEB + i] = edge_weight(P.slot_w[s], d, 0.f, 0.f);
+          T.s_w[s * T.EB + i] = edge_weight(P.slot_w[s], d, 0.f, 0.f);
         }
       }
     }
@@ -173,13 +197,13 @@ __device__ __forceinline__ void tile_weights(const KernelArgs& k, const TileCfg&
   __syncthreads();
   if constexpr (NS > 0) {
     if (accumulate_z) {                         // one thread per (node, slot): sequential, edge-id order
-      for (int j = tid; j < T.nv * NS; j += kTileThreads) {
+      for (int j = tid; j < T.nv * NS; j += nthr) {
         const int l = j / NS, s = j - l * NS;
         if (s < P.n_slots) {
           const int a0 = max(T.s_ptr[l], b0) - b0, a1 = min(T.s_ptr[l + 1], b0 + nb) - b0;
           float zw = T.s_zw[s * TN + l], za = T.s_zabs[s * TN + l];
           for (int i = a0; i < a1; ++i) {
-            const float w = T.s_w[s * kEB + i];
+            const float w = T.s_w[s * T.EB + i];
             zw += w;
             za += fabsf(w);
           }
@@ -189,24 +213,31 @@ __device__ __forceinline__ void tile_weights(const KernelArgs& k, const TileCfg&
       }
     }
   }
+  if (T.use_msg) {                              // every thread observes the completed copies of this batch
+    mbar_wait(&T.s_bar[1], T.msg_parity);
+    T.msg_parity ^= 1u;
+  }
 }
 
 // message of batch slot i (global slot e, source u) for this thread's columns
-template <int MODE, int VEC, int NS>
-__device__ __forceinline__ Vec<VEC> tile_message(const KernelArgs& k, const Tile<VEC, NS>& T, int u, int e, const Vec<VEC>& qv) {
-  if constexpr (MODE != DGN_MSG_DENSE && VEC == 4) {
-    if (T.staged) {
-      const float4 t = *reinterpret_cast<const float4*>(T.s_win + (size_t)(u - T.umin) * k.plan.F + T.c);
+template <int MODE, int VEC>
+__device__ __forceinline__ Vec<VEC> tile_message(const KernelArgs& k, const Tile& T, int i, int e, const Vec<VEC>& qv) {
+  const int u = T.s_src[i];
+  if constexpr (VEC == 4) {
+    const bool from_win = (MODE != DGN_MSG_DENSE) && T.staged;
+    if (from_win || T.use_msg) {
+      const float* row = from_win ? T.s_win + (size_t)(u - T.umin) * k.plan.F : T.s_msg + (size_t)i * k.plan.F;
+      const float4 t = *reinterpret_cast<const float4*>(row + T.c);
       Vec<VEC> m;
       m.a[0] = t.x; m.a[1] = t.y; m.a[2] = t.z; m.a[3] = t.w;
       if constexpr (MODE == DGN_MSG_AFFINE) {
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) m.a[i] += qv.a[i];
+        for (int j = 0; j < VEC; ++j) m.a[j] += qv.a[j];
         if (k.r) {
           const int id = k.in_eid ? __ldg(k.in_eid + e) : e;
           const Vec<VEC> rv = vload<VEC>(k.r + (size_t)id * k.ld_r + T.c);
 #pragma unroll
-          for (int i = 0; i < VEC; ++i) m.a[i] += rv.a[i];
+          for (int j = 0; j < VEC; ++j) m.a[j] += rv.a[j];
         }
       }
       return m;
@@ -215,29 +246,10 @@ __device__ __forceinline__ Vec<VEC> tile_message(const KernelArgs& k, const Tile
   return load_message<MODE, VEC>(k, u, e, T.c, qv);
 }
 
-// phase C: per-(node, slot) factors and per-node scaler coefficients
-template <int VEC, int NS>
-__device__ __forceinline__ void tile_factors(const KernelArgs& k, const TileCfg& tc, Tile<VEC, NS>& T) {
+// per-node scaler coefficients (rb/nets/scalers.py): 1, log(D+1)/avg, avg/log(D+1)
+__device__ __forceinline__ void tile_scaler_coefs(const KernelArgs& k, Tile& T) {
   const AggPlan& P = k.plan;
-  const int tid = threadIdx.x, TN = tc.TN;
-  for (int j = tid; j < T.nv * NS; j += kTileThreads) {
-    const int l = j / NS, s = j - l * NS;
-    if (s < P.n_slots) {
-      const int kind = P.slot_w[s];
-      const float zw = T.s_zw[s * TN + l], za = T.s_zabs[s * TN + l];
-      float f0, f1;
-      if (kind == W_POS || kind == W_NEG) {     // balanced: 0.5 / (sum relu(+-delta) + eps)
-        f0 = 0.5f * __frcp_rn(zw + DGN_EPS);
-        f1 = zw * f0;
-      } else {                                  // av / dx: 1 / (sum |delta| + eps), W = sum(w) / Z
-        f0 = __frcp_rn(za + DGN_EPS);
-        f1 = zw * f0;
-      }
-      T.s_f0[s * TN + l] = f0;
-      T.s_f1[s * TN + l] = f1;
-    }
-  }
-  for (int j = tid; j < T.nv * DGN_MAX_SCALERS; j += kTileThreads) {
+  for (int j = threadIdx.x; j < T.nv * DGN_MAX_SCALERS; j += blockDim.x) {
     const int l = j / DGN_MAX_SCALERS, s = j - l * DGN_MAX_SCALERS;
     float cf = 1.f;
     if (P.S > 1 && s < P.S) {
@@ -246,7 +258,26 @@ __device__ __forceinline__ void tile_factors(const KernelArgs& k, const TileCfg&
       cf = (kind == DGN_SCALE_AMPLIFICATION) ? __fdiv_rn(ld, P.avg_log)
            : (kind == DGN_SCALE_ATTENUATION) ? __fdiv_rn(P.avg_log, ld) : 1.f;
     }
-    T.s_coef[s * TN + l] = cf;
+    T.s_coef[s * T.TN + l] = cf;
+  }
+}
+
+// per-(node, slot) factors derived from the completed sums
+template <int NS>
+__device__ __forceinline__ void tile_factors(const KernelArgs& k, Tile& T) {
+  const AggPlan& P = k.plan;
+  const int TN = T.TN;
+  for (int j = threadIdx.x; j < T.nv * NS; j += blockDim.x) {
+    const int l = j / NS, s = j - l * NS;
+    if (s < P.n_slots) {
+      const int kind = P.slot_w[s];
+      const float zw = T.s_zw[s * TN + l], za = T.s_zabs[s * TN + l];
+      float f0;
+      if (kind == W_POS || kind == W_NEG) f0 = 0.5f * __frcp_rn(zw + DGN_EPS);   // balanced halves
+      else f0 = __frcp_rn(za + DGN_EPS);                                          // av / dx: 1 / (sum |delta| + eps)
+      T.s_f0[s * TN + l] = f0;
+      T.s_f1[s * TN + l] = zw * f0;                                               // W = sum(w) / Z
+    }
   }
 }
 
@@ -263,7 +294,8 @@ __device__ __forceinline__ void acc_init(RowAcc<VEC, NS, ISO>& R) {
 }
 
 template <int VEC, int NS, bool ISO>
-__device__ __forceinline__ void acc_edge(const AggPlan& P, RowAcc<VEC, NS, ISO>& R, const Vec<VEC>& m, const float* s_w, int i) {
+__device__ __forceinline__ void acc_edge(const AggPlan& P, RowAcc<VEC, NS, ISO>& R, const Vec<VEC>& m, const float* s_w,
+                                         int EB, int i) {
 #pragma unroll
   for (int j = 0; j < VEC; ++j) {
     R.sum.a[j] += m.a[j];
@@ -276,7 +308,7 @@ __device__ __forceinline__ void acc_edge(const AggPlan& P, RowAcc<VEC, NS, ISO>&
 #pragma unroll
   for (int s = 0; s < NS; ++s) {
     if (s < P.n_slots) {
-      const float w = s_w[s * kEB + i];
+      const float w = s_w[s * EB + i];
 #pragma unroll
       for (int j = 0; j < VEC; ++j) R.acc[s].a[j] = fmaf(w, m.a[j], R.acc[s].a[j]);
     }
@@ -302,13 +334,13 @@ __device__ __forceinline__ void mean_var(const Vec<VEC>& sum, const Vec<VEC>& sq
 // forward
 // ======================================================================================================
 template <int MODE, int VEC, int NS, bool ISO>
-__global__ void __launch_bounds__(kTileThreads) agg_fwd_tile_kernel(const __grid_constant__ KernelArgs k,
-                                                                    const __grid_constant__ TileCfg tc) {
+__global__ void __launch_bounds__(kMaxTileThreads) agg_fwd_tile_kernel(const __grid_constant__ KernelArgs k,
+                                                                       const __grid_constant__ TileCfg tc) {
   extern __shared__ __align__(128) unsigned char smem[];
   const AggPlan& P = k.plan;
-  const int TN = tc.TN;
-  Tile<VEC, NS> T;
+  Tile T;
   tile_prologue<MODE, VEC, NS>(k, tc, smem, T);
+  const int TN = T.TN;
 
   Vec<VEC> hv = vfill<VEC>(0.f), qv = vfill<VEC>(0.f);
   int tower = 0, cg = 0;
@@ -329,22 +361,23 @@ __global__ void __launch_bounds__(kTileThreads) agg_fwd_tile_kernel(const __grid
 
   RowAcc<VEC, NS, ISO> R;
   acc_init(R);
-  bool waited = false;
-  for (int b0 = T.E0; b0 < T.E1; b0 += kEB) {
-    const int nb = min(kEB, T.E1 - b0);
-    tile_weights<VEC, NS>(k, tc, T, b0, nb, true);
-    if (T.staged && !waited) { mbar_wait(T.s_bar, 0); waited = true; }
+  bool win_waited = false;
+  for (int b0 = T.E0; b0 < T.E1; b0 += T.EB) {
+    const int nb = min(T.EB, T.E1 - b0);
+    tile_batch_begin<MODE, VEC, NS>(k, T, b0, nb, true);
+    if (T.staged && !win_waited) { mbar_wait(&T.s_bar[0], 0); win_waited = true; }
     if (T.active) {
       const int i0 = max(T.ne0, b0) - b0, i1 = min(T.ne1, b0 + nb) - b0;
 #pragma unroll 4
       for (int i = i0; i < i1; ++i) {
-        const Vec<VEC> m = tile_message<MODE, VEC, NS>(k, T, T.s_src[i], b0 + i, qv);
-        acc_edge<VEC, NS, ISO>(P, R, m, T.s_w, i);
+        const Vec<VEC> m = tile_message<MODE, VEC>(k, T, i, b0 + i, qv);
+        acc_edge<VEC, NS, ISO>(P, R, m, T.s_w, T.EB, i);
       }
     }
     __syncthreads();
   }
-  tile_factors<VEC, NS>(k, tc, T);
+  tile_factors<NS>(k, T);
+  tile_scaler_coefs(k, T);
   __syncthreads();
   if (!T.active) return;
 
@@ -431,31 +464,29 @@ __global__ void __launch_bounds__(kTileThreads) agg_fwd_tile_kernel(const __grid
 // backward, destination side (the source-side gather is agg_bwd_src_kernel in dgn_agg_bwd.cu)
 // ======================================================================================================
 template <int MODE, int VEC, int NS, bool ISO>
-__global__ void __launch_bounds__(kTileThreads) agg_bwd_tile_kernel(const __grid_constant__ KernelArgs k,
-                                                                    const __grid_constant__ TileCfg tc) {
+__global__ void __launch_bounds__(kMaxTileThreads) agg_bwd_tile_kernel(const __grid_constant__ KernelArgs k,
+                                                                       const __grid_constant__ TileCfg tc) {
   extern __shared__ __align__(128) unsigned char smem[];
   const AggPlan& P = k.plan;
-  const int TN = tc.TN, tid = threadIdx.x;
-  Tile<VEC, NS> T;
+  const int tid = threadIdx.x;
+  Tile T;
   tile_prologue<MODE, VEC, NS>(k, tc, smem, T);
-  Vec<VEC>* sG = reinterpret_cast<Vec<VEC>*>(smem + tc.off_g);
+  const int TN = T.TN;
+
+  // the tile's gradient slabs: one bulk copy per node row (S*A*F contiguous floats), issued first so they are
+  // in flight during everything that follows
+  const bool use_gt = tc.use_gt != 0;
+  if (use_gt) {
+    if (tid == 0) mbar_expect_tx(&T.s_bar[2], (uint32_t)T.nv * (uint32_t)tc.gt_row * 4u);
+    for (int l = tid; l < T.nv; l += blockDim.x)
+      bulk_g2s(T.s_gt + (size_t)l * tc.gt_row, k.g_out + (size_t)(T.v0 + l) * k.ld_out, (uint32_t)tc.gt_row * 4u,
+               &T.s_bar[2]);
+  }
+  tile_scaler_coefs(k, T);
 
   int tower = 0, cg = 0;
   Vec<VEC> hv = vfill<VEC>(0.f), qv = vfill<VEC>(0.f), dh = vfill<VEC>(0.f);
   const int D = T.ne1 - T.ne0;
-  // scaler coefficients are needed before the gradient slabs can be folded: compute them up front
-  for (int j = tid; j < T.nv * DGN_MAX_SCALERS; j += kTileThreads) {
-    const int l = j / DGN_MAX_SCALERS, s = j - l * DGN_MAX_SCALERS;
-    float cf = 1.f;
-    if (P.S > 1 && s < P.S) {
-      const float ld = __ldg(k.log_deg + T.v0 + l);
-      const int kind = P.scaler_kind[s];
-      cf = (kind == DGN_SCALE_AMPLIFICATION) ? __fdiv_rn(ld, P.avg_log)
-           : (kind == DGN_SCALE_ATTENUATION) ? __fdiv_rn(P.avg_log, ld) : 1.f;
-    }
-    T.s_coef[s * TN + l] = cf;
-  }
-  __syncthreads();
   if (T.active) {
     tower = T.c / P.Fg;
     cg = T.c - tower * P.Fg;
@@ -466,27 +497,6 @@ __global__ void __launch_bounds__(kTileThreads) agg_bwd_tile_kernel(const __grid
       for (int i = 0; i < VEC; ++i) dh.a[i] += t.a[i];
     }
     if (D > 0) {
-      // phase 1: G_a = sum_s coef_s * g_out[v, s, a, :] for every aggregator, staged in shared memory; the S*A
-      // slab loads dominate this kernel's traffic and are issued back to back (unroll 4 => 4*S in flight)
-      float coef[DGN_MAX_SCALERS];
-#pragma unroll
-      for (int s = 0; s < DGN_MAX_SCALERS; ++s) coef[s] = T.s_coef[s * TN + T.ln];
-      const float* grow = k.g_out + (size_t)T.v * k.ld_out + (size_t)tower * k.out_gs + cg;
-      const int scaler_stride = P.A * P.Fg;
-#pragma unroll 4
-      for (int a = 0; a < P.A; ++a) {
-        Vec<VEC> G = vfill<VEC>(0.f);
-        const float* src = grow + a * P.Fg;
-#pragma unroll
-        for (int s = 0; s < DGN_MAX_SCALERS; ++s) {
-          if (s < P.S) {
-            const Vec<VEC> gs = vload_stream<VEC>(src + s * scaler_stride);
-#pragma unroll
-            for (int i = 0; i < VEC; ++i) G.a[i] = fmaf(coef[s], gs.a[i], G.a[i]);
-          }
-        }
-        sG[a * kTileThreads + tid] = G;
-      }
       hv = vload<VEC>(k.h_in + (size_t)T.v * k.ld_h + T.c);
       if constexpr (MODE == DGN_MSG_AFFINE) {
         qv = vload<VEC>(k.q + (size_t)T.v * k.ld_q + T.c);
@@ -502,25 +512,26 @@ __global__ void __launch_bounds__(kTileThreads) agg_bwd_tile_kernel(const __grid
   // ---- pass 1: recompute the row statistics ------------------------------------------------------------
   RowAcc<VEC, NS, ISO> R;
   acc_init(R);
-  bool waited = false;
-  const bool single_batch = (T.E1 - T.E0) <= kEB;
-  for (int b0 = T.E0; b0 < T.E1; b0 += kEB) {
-    const int nb = min(kEB, T.E1 - b0);
-    tile_weights<VEC, NS>(k, tc, T, b0, nb, true);
-    if (T.staged && !waited) { mbar_wait(T.s_bar, 0); waited = true; }
+  bool win_waited = false;
+  const bool single_batch = (T.E1 - T.E0) <= T.EB;
+  for (int b0 = T.E0; b0 < T.E1; b0 += T.EB) {
+    const int nb = min(T.EB, T.E1 - b0);
+    tile_batch_begin<MODE, VEC, NS>(k, T, b0, nb, true);
+    if (T.staged && !win_waited) { mbar_wait(&T.s_bar[0], 0); win_waited = true; }
     if (T.active) {
       const int i0 = max(T.ne0, b0) - b0, i1 = min(T.ne1, b0 + nb) - b0;
 #pragma unroll 4
       for (int i = i0; i < i1; ++i) {
-        const Vec<VEC> m = tile_message<MODE, VEC, NS>(k, T, T.s_src[i], b0 + i, qv);
-        acc_edge<VEC, NS, ISO>(P, R, m, T.s_w, i);
+        const Vec<VEC> m = tile_message<MODE, VEC>(k, T, i, b0 + i, qv);
+        acc_edge<VEC, NS, ISO>(P, R, m, T.s_w, T.EB, i);
       }
     }
-    if (!single_batch) __syncthreads();                // the next batch overwrites s_src / s_w
+    if (!single_batch) __syncthreads();                // the next batch overwrites s_src / s_w / s_msg
   }
-  if (single_batch) __syncthreads();                   // s_zw / s_zabs complete before the factors are derived
-  tile_factors<VEC, NS>(k, tc, T);
+  __syncthreads();                                     // sums complete (and s_coef visible) before the factors
+  tile_factors<NS>(k, T);
   __syncthreads();
+  if (use_gt) mbar_wait(&T.s_bar[2], 0);
 
   // ---- fold the S*A gradient slabs into per-column coefficients ---------------------------------------
   Vec<VEC> c0 = vfill<VEC>(0.f), c1 = vfill<VEC>(0.f), gmx = vfill<VEC>(0.f), gmn = vfill<VEC>(0.f);
@@ -528,13 +539,42 @@ __global__ void __launch_bounds__(kTileThreads) agg_bwd_tile_kernel(const __grid
 #pragma unroll
   for (int s = 0; s < NS; ++s) cs[s] = vfill<VEC>(0.f);
   if (T.active && D > 0) {
+    float coef[DGN_MAX_SCALERS];
+#pragma unroll
+    for (int s = 0; s < DGN_MAX_SCALERS; ++s) coef[s] = T.s_coef[s * TN + T.ln];
+    const int scaler_stride = P.A * P.Fg;
+    const float* grow_g = k.g_out + (size_t)T.v * k.ld_out + (size_t)tower * k.out_gs + cg;
+    const float* grow_s = T.s_gt + (size_t)T.ln * tc.gt_row + cg;          // single tower when use_gt
+    auto slab_grad = [&](int a) {               // G_a = sum_s coef_s * g_out[v, s, a, :]
+      Vec<VEC> G = vfill<VEC>(0.f);
+#pragma unroll
+      for (int s = 0; s < DGN_MAX_SCALERS; ++s) {
+        if (s < P.S) {
+          Vec<VEC> gs;
+          if (use_gt) {
+            if constexpr (VEC == 4) {
+              const float4 t = *reinterpret_cast<const float4*>(grow_s + a * P.Fg + s * scaler_stride);
+              gs.a[0] = t.x; gs.a[1] = t.y; gs.a[2] = t.z; gs.a[3] = t.w;
+            } else {
+#pragma unroll
+              for (int i = 0; i < VEC; ++i) gs.a[i] = grow_s[a * P.Fg + s * scaler_stride + i];
+            }
+          } else {
+            gs = vload_stream<VEC>(grow_g + a * P.Fg + s * scaler_stride);
+          }
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) G.a[i] = fmaf(coef[s], gs.a[i], G.a[i]);
+        }
+      }
+      return G;
+    };
     const float fD = (float)D, rD = __frcp_rn(fD);
     Vec<VEC> mean, var;
     mean_var<VEC, ISO>(R.sum, R.sq, fD, mean, var);
     for (int a = 0; a < P.A; ++a) {                    // isotropic aggregators
       const int kind = P.agg_kind[a];
       if (kind >= DGN_AGG_DIR_AV) continue;
-      const Vec<VEC> G = sG[a * kTileThreads + tid];
+      const Vec<VEC> G = slab_grad(a);
 #pragma unroll
       for (int i = 0; i < VEC; ++i) {
         if (kind == DGN_AGG_MEAN) c0.a[i] += G.a[i] * rD;
@@ -560,7 +600,7 @@ __global__ void __launch_bounds__(kTileThreads) agg_bwd_tile_kernel(const __grid
         const int a = __ffs(todo) - 1;
         todo &= todo - 1;
         const int kind = P.agg_kind[a];
-        const Vec<VEC> G = sG[a * kTileThreads + tid];
+        const Vec<VEC> G = slab_grad(a);
         const Vec<VEC>& A1 = R.acc[s];
         if (kind == DGN_AGG_DIR_AV) {
 #pragma unroll
@@ -596,15 +636,15 @@ __global__ void __launch_bounds__(kTileThreads) agg_bwd_tile_kernel(const __grid
   // ---- pass 2: per-edge message gradients ----------------------------------------------------------------
   Vec<VEC> dq = vfill<VEC>(0.f);
   unsigned given = 0u;          // bit i: max gradient of column i already routed; bit 4+i: min
-  for (int b0 = T.E0; b0 < T.E1; b0 += kEB) {
-    const int nb = min(kEB, T.E1 - b0);
-    if (!single_batch) tile_weights<VEC, NS>(k, tc, T, b0, nb, false);   // weights of this batch again
+  for (int b0 = T.E0; b0 < T.E1; b0 += T.EB) {
+    const int nb = min(T.EB, T.E1 - b0);
+    if (!single_batch) tile_batch_begin<MODE, VEC, NS>(k, T, b0, nb, false);   // this batch's rows / weights again
     if (T.active) {
       const int i0 = max(T.ne0, b0) - b0, i1 = min(T.ne1, b0 + nb) - b0;
 #pragma unroll 2
       for (int i = i0; i < i1; ++i) {
         const int e = b0 + i;
-        const Vec<VEC> m = tile_message<MODE, VEC, NS>(k, T, T.s_src[i], e, qv);
+        const Vec<VEC> m = tile_message<MODE, VEC>(k, T, i, e, qv);
         Vec<VEC> dm;
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
@@ -619,7 +659,7 @@ __global__ void __launch_bounds__(kTileThreads) agg_bwd_tile_kernel(const __grid
 #pragma unroll
         for (int s = 0; s < NS; ++s) {
           if (s < P.n_slots) {
-            const float w = T.s_w[s * kEB + i];
+            const float w = T.s_w[s * T.EB + i];
 #pragma unroll
             for (int j = 0; j < VEC; ++j) dm.a[j] = fmaf(w, cs[s].a[j], dm.a[j]);
           }
@@ -648,10 +688,33 @@ static inline int align_up(int x, int a) { return (x + a - 1) / a * a; }
 
 static bool make_tile_cfg(const KernelArgs& k, int vec, int NS, bool backward, TileCfg& tc) {
   const AggPlan& P = k.plan;
-  if (P.has_exp || P.chunks > kTileThreads || P.chunks <= 0) return false;
-  tc.TN = kTileThreads / P.chunks;
+  if (P.has_exp || P.chunks > kMaxTileThreads || P.chunks <= 0) return false;
+  const int T_towers = P.F / P.Fg;
+  const int row_bytes = P.F * 4;
+  const bool rows_bulk_ok = vec == 4 && (row_bytes % 16 == 0);
+  // backward: gradient tile through TMA when a node's slabs are one contiguous, 16 B aligned run
+  tc.gt_row = P.S * P.A * P.F;
+  tc.use_gt = backward && vec == 4 && T_towers == 1 && (k.ld_out % 4 == 0) &&
+              ((reinterpret_cast<uintptr_t>(k.g_out) & 15u) == 0);
+  // block size: 256 threads unless that makes the gradient tile too large for >= 2 CTAs per SM
+  tc.threads = kMaxTileThreads;
+  if (tc.use_gt && (kMaxTileThreads / P.chunks) * tc.gt_row * 4 > 72 * 1024 && P.chunks <= 128) tc.threads = 128;
+  tc.TN = tc.threads / P.chunks;
   if (tc.TN > 64) tc.TN = 64;
+  if (tc.use_gt && tc.TN * tc.gt_row * 4 > 96 * 1024) tc.use_gt = 0;
   const int TN = tc.TN, ns = NS > 0 ? NS : 1;
+  // messages of a batch in shared memory (row-sized bulk copies): SOURCE / AFFINE rows of x, DENSE rows of r
+  tc.use_msg = rows_bulk_ok && ((k.mode == DGN_MSG_DENSE) ? (k.ld_r % 4 == 0) : (k.ld_x % 4 == 0));
+  // batch size: enough slots for a typical tile (2x the average), at most 32 KB of message rows
+  const double avg_deg = k.N > 0 ? (double)k.E / (double)k.N : 0.0;
+  int eb_max = tc.use_msg ? (32 * 1024) / row_bytes : 512;
+  eb_max = eb_max / 32 * 32;
+  if (eb_max < 32) eb_max = 32;
+  if (eb_max > 512) eb_max = 512;
+  int eb = ((int)(2.0 * TN * avg_deg) + 31) / 32 * 32;
+  if (eb < 32) eb = 32;
+  if (eb > eb_max) eb = eb_max;
+  tc.EB = eb;
   int off = align_up((TN + 1) * 4, 16);
   tc.off_ev = off;   off += align_up(ns * TN * 4, 16);
   tc.off_zw = off;   off += align_up(ns * TN * 4, 16);
@@ -659,22 +722,27 @@ static bool make_tile_cfg(const KernelArgs& k, int vec, int NS, bool backward, T
   tc.off_f0 = off;   off += align_up(ns * TN * 4, 16);
   tc.off_f1 = off;   off += align_up(ns * TN * 4, 16);
   tc.off_coef = off; off += align_up(DGN_MAX_SCALERS * TN * 4, 16);
-  tc.off_src = off;  off += kEB * 4;
-  tc.off_w = off;    off += ns * kEB * 4;
-  tc.off_bar = off;  off += 16;
+  tc.off_src = off;  off += tc.EB * 4;
+  tc.off_w = off;    off += ns * tc.EB * 4;
+  tc.off_bar = off;  off += 32;
   tc.off_red = off;  off += 64;
-  tc.off_g = off;
-  if (backward) off += P.A * kTileThreads * vec * 4;
+  off = align_up(off, 128);
+  tc.off_gt = off;
+  if (tc.use_gt) off += TN * tc.gt_row * 4;
+  off = align_up(off, 128);
+  tc.off_msg = off;
+  if (tc.use_msg) off += tc.EB * row_bytes;
   off = align_up(off, 128);
   tc.off_win = off;
-  // source-window staging: only the 128-bit path, gathers from x (not DENSE); budget keeps >= 2 CTAs per SM
+  // Source-window staging pays when rows are re-used (average in-degree well above 1).  Its shared-memory
+  // reservation costs occupancy, so it is only offered when the graph is dense enough to use it.
   tc.win_rows = 0;
-  if (vec == 4 && k.mode != DGN_MSG_DENSE) {
+  if (rows_bulk_ok && k.mode != DGN_MSG_DENSE && avg_deg >= 16.0) {
     const int budget = 100 * 1024 - off;
-    const int rows = budget > 0 ? budget / (P.F * 4) : 0;
+    const int rows = budget > 0 ? budget / row_bytes : 0;
     if (rows >= 32) tc.win_rows = rows;
   }
-  off += tc.win_rows * P.F * 4;
+  off += tc.win_rows * row_bytes;
   tc.total = off;
   return tc.total <= 200 * 1024;
 }
@@ -686,7 +754,7 @@ static int launch_tile(Kern kern, const KernelArgs& k, const TileCfg& tc, cudaSt
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return DGN_ERR_CUDA;
   }
   const unsigned grid = (unsigned)((k.N + tc.TN - 1) / tc.TN);
-  kern<<<grid, kTileThreads, tc.total, st>>>(k, tc);
+  kern<<<grid, tc.threads, tc.total, st>>>(k, tc);
   return cudaGetLastError() == cudaSuccess ? DGN_OK : DGN_ERR_CUDA;
 }
 
