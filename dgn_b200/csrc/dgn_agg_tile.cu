@@ -36,7 +36,7 @@ struct TileCfg {
   int use_msg;                       // gathered message rows are bulk-copied into shared memory per batch
   int use_gt;                        // backward: the tile's gradient slabs are bulk-copied into shared memory
   int gt_row;                        // floats per node in the gradient tile (S*A*F)
-  int off_ev, off_zw, off_zabs, off_f0, off_f1, off_coef, off_src, off_w, off_bar, off_red, off_win, off_msg, off_gt;
+  int off_ev, off_zw, off_zabs, off_f0, off_f1, off_coef, off_src, off_w, off_bar, off_red, off_win, off_msg, off_gt, off_g;
   int total;
 };
 
@@ -508,6 +508,33 @@ __global__ void __launch_bounds__(kMaxTileThreads) agg_bwd_tile_kernel(const __g
       }
     }
   }
+  Vec<VEC>* sG = reinterpret_cast<Vec<VEC>*>(smem + tc.off_g);
+  if (!use_gt) {
+    __syncthreads();                                   // s_coef visible
+    if (T.active && D > 0) {
+      // G_a = sum_s coef_s * g_out[v, s, a, :] for every aggregator, staged per thread in shared memory: the S*A
+      // slab loads dominate this kernel's traffic and are issued back to back (unroll 4 => 4*S loads in flight)
+      float coef[DGN_MAX_SCALERS];
+#pragma unroll
+      for (int s = 0; s < DGN_MAX_SCALERS; ++s) coef[s] = T.s_coef[s * TN + T.ln];
+      const float* grow = k.g_out + (size_t)T.v * k.ld_out + (size_t)tower * k.out_gs + cg;
+      const int scaler_stride = P.A * P.Fg;
+#pragma unroll 4
+      for (int a = 0; a < P.A; ++a) {
+        Vec<VEC> G = vfill<VEC>(0.f);
+        const float* src = grow + a * P.Fg;
+#pragma unroll
+        for (int s = 0; s < DGN_MAX_SCALERS; ++s) {
+          if (s < P.S) {
+            const Vec<VEC> gs = vload_stream<VEC>(src + s * scaler_stride);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) G.a[i] = fmaf(coef[s], gs.a[i], G.a[i]);
+          }
+        }
+        sG[a * (int)blockDim.x + tid] = G;
+      }
+    }
+  }
 
   // ---- pass 1: recompute the row statistics ------------------------------------------------------------
   RowAcc<VEC, NS, ISO> R;
@@ -543,24 +570,20 @@ __global__ void __launch_bounds__(kMaxTileThreads) agg_bwd_tile_kernel(const __g
 #pragma unroll
     for (int s = 0; s < DGN_MAX_SCALERS; ++s) coef[s] = T.s_coef[s * TN + T.ln];
     const int scaler_stride = P.A * P.Fg;
-    const float* grow_g = k.g_out + (size_t)T.v * k.ld_out + (size_t)tower * k.out_gs + cg;
     const float* grow_s = T.s_gt + (size_t)T.ln * tc.gt_row + cg;          // single tower when use_gt
     auto slab_grad = [&](int a) {               // G_a = sum_s coef_s * g_out[v, s, a, :]
+      if (!use_gt) return sG[a * (int)blockDim.x + tid];
       Vec<VEC> G = vfill<VEC>(0.f);
 #pragma unroll
       for (int s = 0; s < DGN_MAX_SCALERS; ++s) {
         if (s < P.S) {
           Vec<VEC> gs;
-          if (use_gt) {
-            if constexpr (VEC == 4) {
-              const float4 t = *reinterpret_cast<const float4*>(grow_s + a * P.Fg + s * scaler_stride);
-              gs.a[0] = t.x; gs.a[1] = t.y; gs.a[2] = t.z; gs.a[3] = t.w;
-            } else {
-#pragma unroll
-              for (int i = 0; i < VEC; ++i) gs.a[i] = grow_s[a * P.Fg + s * scaler_stride + i];
-            }
+          if constexpr (VEC == 4) {
+            const float4 t = *reinterpret_cast<const float4*>(grow_s + a * P.Fg + s * scaler_stride);
+            gs.a[0] = t.x; gs.a[1] = t.y; gs.a[2] = t.z; gs.a[3] = t.w;
           } else {
-            gs = vload_stream<VEC>(grow_g + a * P.Fg + s * scaler_stride);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) gs.a[i] = grow_s[a * P.Fg + s * scaler_stride + i];
           }
 #pragma unroll
           for (int i = 0; i < VEC; ++i) G.a[i] = fmaf(coef[s], gs.a[i], G.a[i]);
@@ -694,8 +717,11 @@ static bool make_tile_cfg(const KernelArgs& k, int vec, int NS, bool backward, T
   const bool rows_bulk_ok = vec == 4 && (row_bytes % 16 == 0);
   // backward: gradient tile through TMA when a node's slabs are one contiguous, 16 B aligned run
   tc.gt_row = P.S * P.A * P.F;
+  // (measured on B200: the smaller CTAs it forces cost more than the async copy gains for the 7.7 KB rows of
+  //  cfg2, so it is only taken when a 256-thread tile of gradient rows fits in 48 KB)
   tc.use_gt = backward && vec == 4 && T_towers == 1 && (k.ld_out % 4 == 0) &&
-              ((reinterpret_cast<uintptr_t>(k.g_out) & 15u) == 0);
+              ((reinterpret_cast<uintptr_t>(k.g_out) & 15u) == 0) &&
+              (kMaxTileThreads / P.chunks) * tc.gt_row * 4 <= 48 * 1024;
   // block size: 256 threads unless that makes the gradient tile too large for >= 2 CTAs per SM
   tc.threads = kMaxTileThreads;
   if (tc.use_gt && (kMaxTileThreads / P.chunks) * tc.gt_row * 4 > 72 * 1024 && P.chunks <= 128) tc.threads = 128;
@@ -704,9 +730,11 @@ static bool make_tile_cfg(const KernelArgs& k, int vec, int NS, bool backward, T
   if (tc.use_gt && tc.TN * tc.gt_row * 4 > 96 * 1024) tc.use_gt = 0;
   const int TN = tc.TN, ns = NS > 0 ? NS : 1;
   // messages of a batch in shared memory (row-sized bulk copies): SOURCE / AFFINE rows of x, DENSE rows of r
-  tc.use_msg = rows_bulk_ok && ((k.mode == DGN_MSG_DENSE) ? (k.ld_r % 4 == 0) : (k.ld_x % 4 == 0));
-  // batch size: enough slots for a typical tile (2x the average), at most 32 KB of message rows
+  // High-degree graphs (SBM PATTERN) take the source-window path instead: no per-edge copies, large batches.
   const double avg_deg = k.N > 0 ? (double)k.E / (double)k.N : 0.0;
+  const bool dense_graph = avg_deg >= 16.0 && k.mode != DGN_MSG_DENSE;
+  tc.use_msg = rows_bulk_ok && !dense_graph && ((k.mode == DGN_MSG_DENSE) ? (k.ld_r % 4 == 0) : (k.ld_x % 4 == 0));
+  // batch size: enough slots for a typical tile (2x the average), at most 32 KB of message rows
   int eb_max = tc.use_msg ? (32 * 1024) / row_bytes : 512;
   eb_max = eb_max / 32 * 32;
   if (eb_max < 32) eb_max = 32;
@@ -730,6 +758,9 @@ static bool make_tile_cfg(const KernelArgs& k, int vec, int NS, bool backward, T
   tc.off_gt = off;
   if (tc.use_gt) off += TN * tc.gt_row * 4;
   off = align_up(off, 128);
+  tc.off_g = off;                                      // per-thread staged slab sums G_a (backward without gradient tile)
+  if (backward && !tc.use_gt) off += P.A * tc.threads * vec * 4;
+  off = align_up(off, 128);
   tc.off_msg = off;
   if (tc.use_msg) off += tc.EB * row_bytes;
   off = align_up(off, 128);
@@ -737,7 +768,7 @@ static bool make_tile_cfg(const KernelArgs& k, int vec, int NS, bool backward, T
   // Source-window staging pays when rows are re-used (average in-degree well above 1).  Its shared-memory
   // reservation costs occupancy, so it is only offered when the graph is dense enough to use it.
   tc.win_rows = 0;
-  if (rows_bulk_ok && k.mode != DGN_MSG_DENSE && avg_deg >= 16.0) {
+  if (rows_bulk_ok && dense_graph) {
     const int budget = 100 * 1024 - off;
     const int rows = budget > 0 ? budget / row_bytes : 0;
     if (rows >= 32) tc.win_rows = rows;
