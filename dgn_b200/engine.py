@@ -64,20 +64,33 @@ class TrainStep:
         self.targets = torch.zeros(targets_like.shape, dtype=targets_like.dtype, device=self.dev)
         self.targets.copy_(targets_like)
         self.loss = torch.zeros((), device=self.dev)
+        # With more than one rank the gradient all-reduce and the Adam launch stay OUTSIDE the captured graph
+        # (2 extra launches per step): replaying NCCL collectives from a CUDA graph is fragile across
+        # NCCL / driver versions, and the collective is latency bound either way.
+        import torch.distributed as dist
+        self.split_update = graphed and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         self.launches_per_step = 0
         self.cuda_graph = None
         if graphed:
             self._capture(warmup_iters)
 
     # one optimisation step on whatever currently sits in the static batch buffers
-    def _step_body(self):
+    def _fwd_bwd(self):
         g = self.g
         self.flat_g.zero_()
         scores = self.net(g, g.ndata[self.node_key], g.edata[self.edge_key], g.snorm_n, None)
         loss = self.net.loss(scores, self.targets)
         loss.backward()
-        allreduce_mean_(self.flat_g)
+        return loss
+
+    def _reduce_and_update(self):
+        allreduce_mean_(self.flat_g)          # one NCCL all-reduce of the flat gradient (no-op on a single rank)
         self.opt.step()
+
+    def _step_body(self):
+        loss = self._fwd_bwd()
+        if not self.split_update:
+            self._reduce_and_update()
         return loss
 
     def _capture(self, warmup_iters):
@@ -86,6 +99,8 @@ class TrainStep:
         with torch.cuda.stream(side):                 # lazy initialisation (cuBLAS, autograd) outside capture
             for _ in range(max(1, warmup_iters)):   # >= 1: lazy library initialisation must not be captured
                 self._step_body()
+                if self.split_update:
+                    self._reduce_and_update()
         torch.cuda.current_stream(self.dev).wait_stream(side)
         torch.cuda.synchronize(self.dev)
         self.cuda_graph = torch.cuda.CUDAGraph()
@@ -93,7 +108,7 @@ class TrainStep:
         with torch.cuda.graph(self.cuda_graph):
             loss = self._step_body()
             self.loss.copy_(loss.detach())
-        self.launches_per_step = ops.LAUNCHES - before
+        self.launches_per_step = ops.LAUNCHES - before + (1 if self.split_update else 0)
 
     # ------------------------------------------------------------------------------------------------
     def load(self, host_graph, host_targets):
@@ -112,6 +127,8 @@ class TrainStep:
         """One training step on the staged batch; returns the loss as a device scalar."""
         if self.cuda_graph is not None:
             self.cuda_graph.replay()
+            if self.split_update:
+                self._reduce_and_update()
             return self.loss
         before = ops.LAUNCHES
         loss = self._step_body()
