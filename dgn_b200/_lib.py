@@ -82,6 +82,10 @@ SIGNATURES = {
                                          C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dgn_adam_step": (C.c_int, [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
                                 C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
+    "dgn_gemm_ws_floats": (C.c_int64, []),
+    "dgn_gemm_tf32x3": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
+                                  C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                  C.c_void_p]),
     "dgn_readout_forward": (C.c_int, [C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
                                       C.c_void_p, C.c_int32, C.c_void_p]),
     "dgn_readout_backward": (C.c_int, [C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,

@@ -3,9 +3,9 @@
 ``pretrans_layers == posttrans_layers == 1`` (all five reference configs, rb/configs/*.json) makes a DGN
 layer a fixed chain
 
-    P = h W_src^T, Q = h W_dst^T                         2 library GEMMs (node level)
+    P = h W_src^T, Q = h W_dst^T                         2 GEMMs (node level), dgn_gemm_tf32x3 on tcgen05
     cat = [h | scalers(aggregators(P[u] + Q[v] + b))]    dgn_agg_forward      (b fused as q_bias)
-    y = cat W_post^T                                     1 library GEMM
+    y = cat W_post^T                                     1 GEMM (dgn_gemm_tf32x3)
     out = relu(BN((y + b_post) * snorm_n)) + h           dgn_norm_forward     (b_post fused as y_bias)
 
 Running that chain through generic autograd costs ~50 kernels per layer and direction in glue: slice
@@ -22,7 +22,7 @@ from __future__ import annotations
 import torch
 
 from . import _lib
-from .ops import (agg_backward_raw, agg_forward_raw, norm_backward_raw, norm_forward_raw, _f32c, _need_cuda)
+from .ops import (agg_backward_raw, agg_forward_raw, gemm, norm_backward_raw, norm_forward_raw, _f32c, _need_cuda)
 
 _ONES = {}
 
@@ -56,14 +56,14 @@ class _FusedLayer(torch.autograd.Function):
         N, dev = h.shape[0], h.device
         P = Q = None
         if cfg.has_pretrans:
-            P = torch.mm(h, W_pre[:, :Fi].t())
-            Q = torch.mm(h, W_pre[:, Fi:2 * Fi].t())
+            P = gemm(h, W_pre[:, :Fi])                   # h @ W_src^T  (tcgen05 3xTF32, fp32-accurate)
+            Q = gemm(h, W_pre[:, Fi:2 * Fi])             # h @ W_dst^T
             cat = torch.empty((N, Fi + spec.out_width), device=dev, dtype=torch.float32)
             agg_forward_raw(g, spec, _lib.MSG_AFFINE, P, Q, R, h, cfg.eig, cat, True, q_bias=b_pre)
         else:                                            # simple layer: message = h[src], no h block
             cat = torch.empty((N, spec.out_width), device=dev, dtype=torch.float32)
             agg_forward_raw(g, spec, _lib.MSG_SOURCE, h, None, None, h, cfg.eig, cat, False)
-        y = torch.mm(cat, W_post.t())
+        y = gemm(cat, W_post)                            # cat @ W_post^T
         Co = y.shape[1]
         out = torch.empty((N, Co), device=dev, dtype=torch.float32)
         stats = torch.empty(_lib.NORM_WS_PER_COL * Co, device=dev, dtype=torch.float32)
@@ -109,12 +109,13 @@ class _FusedLayer(torch.autograd.Function):
         norm_backward_raw(ctx.nargs, g_out, d_y, scratch, d_gamma, d_beta, d_bpost, accumulate=direct)
 
         # ---- posttrans GEMM --------------------------------------------------------------------------------------------
-        d_cat = torch.mm(d_y, W_post)
+        d_cat = gemm(d_y, W_post, b_kmajor=False)        # d_y @ W_post
+        # dW_post = d_y^T @ cat, computed as (cat^T @ d_y)^T so the 128-row tile dimension is the wide one
         if direct:
-            pW_post.grad.addmm_(d_y.t(), cat)
+            gemm(cat, d_y, a_kmajor=False, b_kmajor=False, out=pW_post.grad, accumulate=True, c_transposed=True)
             d_Wpost = None
         else:
-            d_Wpost = torch.mm(d_y.t(), cat)
+            d_Wpost = gemm(cat, d_y, a_kmajor=False, b_kmajor=False, c_transposed=True)
 
         # ---- aggregation -----------------------------------------------------------------------------------------------
         d_h = torch.empty((N, Fi), device=dev, dtype=torch.float32)
@@ -128,17 +129,17 @@ class _FusedLayer(torch.autograd.Function):
                 d_R = torch.empty((max(E, 1), Fi), device=dev, dtype=torch.float32)[:E]
             agg_backward_raw(g, spec, _lib.MSG_AFFINE, P, Q, R, h, cfg.eig, d_cat, True, d_x=d_P, d_q=d_Q, d_r=d_R,
                              d_h=d_h, edge_ws=ws, q_bias=b_pre, d_h_addend=resid)
-            d_h.addmm_(d_P, W_pre[:, :Fi])
-            d_h.addmm_(d_Q, W_pre[:, Fi:2 * Fi])
+            gemm(d_P, W_pre[:, :Fi], b_kmajor=False, out=d_h, accumulate=True)            # += d_P @ W_src
+            gemm(d_Q, W_pre[:, Fi:2 * Fi], b_kmajor=False, out=d_h, accumulate=True)      # += d_Q @ W_dst
             if direct:
                 gW = pW_pre.grad
-                gW[:, :Fi].addmm_(d_P.t(), h)
-                gW[:, Fi:2 * Fi].addmm_(d_Q.t(), h)
+                gemm(d_P, h, a_kmajor=False, b_kmajor=False, out=gW[:, :Fi], accumulate=True)          # += d_P^T @ h
+                gemm(d_Q, h, a_kmajor=False, b_kmajor=False, out=gW[:, Fi:2 * Fi], accumulate=True)    # += d_Q^T @ h
                 pb_pre.grad.addmv_(d_Q.t(), _ones(N, dev))
             else:
                 d_Wpre = torch.zeros_like(W_pre)          # columns past 2F (edge features) get theirs via R
-                d_Wpre[:, :Fi] = torch.mm(d_P.t(), h)
-                d_Wpre[:, Fi:2 * Fi] = torch.mm(d_Q.t(), h)
+                gemm(d_P, h, a_kmajor=False, b_kmajor=False, out=d_Wpre[:, :Fi])
+                gemm(d_Q, h, a_kmajor=False, b_kmajor=False, out=d_Wpre[:, Fi:2 * Fi])
                 d_bpre = torch.mv(d_Q.t(), _ones(N, dev))
         else:
             # x and h_in are the same tensor: the kernel folds d_h_in (+ residual) into the scattered gradient

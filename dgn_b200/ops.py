@@ -351,3 +351,53 @@ def embedding(weight, idx, n_rows_dev=None, direct_grad=False):
     if weight.shape[0] > 200:            # tile would not fit in shared memory: library op (still on the GPU)
         return torch.nn.functional.embedding(idx, weight)
     return _Embedding.apply(weight, idx, n_rows_dev, direct_grad)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# fp32-accurate tensor-core GEMM (tcgen05, 3xTF32)
+# ---------------------------------------------------------------------------------------------------------
+_GEMM_WS = {}
+GEMM_ENABLED = True          # set False to route every GEMM through the library (A/B comparisons)
+
+
+def _gemm_workspace(device):
+    ws = _GEMM_WS.get(str(device))
+    if ws is None:
+        ws = torch.zeros(int(lib.dgn_gemm_ws_floats()), device=device, dtype=torch.float32)
+        _GEMM_WS[str(device)] = ws
+    return ws
+
+
+def gemm(a, b, a_kmajor=True, b_kmajor=True, out=None, accumulate=False, c_transposed=False):
+    """``C (+)= op(A) @ op(B)`` in fp32 accuracy on the tcgen05 tensor cores (``dgn_gemm_tf32x3``).
+
+    ``a`` is ``[M, K]`` (``a_kmajor``) or ``[K, M]``; ``b`` is ``[N, K]`` (``b_kmajor``, i.e. ``A @ B.T``) or ``[K, N]``.
+    ``out`` is ``[M, N]`` (or ``[N, M]`` with ``c_transposed``), row stride free, unit column stride.  Shapes the kernel
+    does not take (rows not 16 B aligned) go through the library GEMM on the same device."""
+    _need_cuda(a, b)
+    M, K = (a.shape[0], a.shape[1]) if a_kmajor else (a.shape[1], a.shape[0])
+    N = b.shape[0] if b_kmajor else b.shape[1]
+    if out is None:
+        out = torch.empty((N, M) if c_transposed else (M, N), device=a.device, dtype=torch.float32)
+        accumulate = False
+    ok = (GEMM_ENABLED and a.dtype == torch.float32 and b.dtype == torch.float32 and a.stride(1) == 1 and
+          b.stride(1) == 1 and out.stride(1) == 1 and K > 0)
+    if ok:
+        rc = lib.dgn_gemm_tf32x3(M, N, K, a.data_ptr(), a.stride(0), int(a_kmajor), b.data_ptr(), b.stride(0),
+                                 int(b_kmajor), out.data_ptr(), out.stride(0), int(accumulate), int(c_transposed),
+                                 _gemm_workspace(a.device).data_ptr(), _stream(a))
+        if rc == 0:
+            _count(1)
+            return out
+        if rc != -2:                      # anything but "unsupported shape / alignment" is an error
+            check(rc, "dgn_gemm_tf32x3")
+    A = a if a_kmajor else a.t()
+    Bm = b.t() if b_kmajor else b
+    res = torch.mm(A, Bm)
+    if c_transposed:
+        res = res.t()
+    if accumulate:
+        out.add_(res)
+    else:
+        out.copy_(res)
+    return out

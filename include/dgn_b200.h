@@ -224,6 +224,19 @@ int dgn_embedding_backward(int32_t n_rows, int32_t n_cols, int32_t vocab, const 
 int dgn_adam_step(int64_t n, float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float lr, float beta1,
                   float beta2, float eps, float weight_decay, int32_t* state, void* stream);
 
+/* C (+)= op(A) * op(B) in fp32 accuracy on the tcgen05 tensor cores (3xTF32 split, fp32 accumulation in tensor
+ * memory).  Replaces the library GEMMs of the pre/post-transform MLPs (FCLayer, rb/nets/layers.py:76-100).
+ *   a_kmajor = 1: A is [M][K] with row stride lda;  0: A is [K][M]
+ *   b_kmajor = 1: B is [N][K] with row stride ldb;  0: B is [K][N]
+ *   c_transposed = 1: the result is written as C[N][M] (row stride ldc);  accumulate = 1: C += result
+ * All operand rows must be 16 B aligned with contiguous extents that are multiples of 4 floats, otherwise
+ * DGN_ERR_UNSUPPORTED is returned (callers then use the library GEMM).  ws: dgn_gemm_ws_floats() floats of
+ * device memory, zero before the first call; deterministic (split-K partials are added in a fixed order). */
+int64_t dgn_gemm_ws_floats(void);
+int dgn_gemm_tf32x3(int32_t M, int32_t N, int32_t K, const float* A, int32_t lda, int32_t a_kmajor, const float* B,
+                    int32_t ldb, int32_t b_kmajor, float* C, int32_t ldc, int32_t accumulate, int32_t c_transposed,
+                    float* ws, void* stream);
+
 int dgn_readout_forward(int32_t n_graphs, const int32_t* graph_ptr, int32_t n_cols, const float* h, int32_t ld_h,
                         int32_t op, float* out, int32_t ld_o, void* stream);
 /* d_h has n_rows_total rows: rows past graph_ptr[n_graphs] (padding of a fixed-capacity batch) are zeroed. */
