@@ -15,8 +15,8 @@
 //              epilogue: tcgen05.ld the accumulator (one row per thread), store / accumulate / split-K reduce;
 //   warp 4     MMA issuer: one elected lane waits on `full`, issues 4 k-steps x 3 tcgen05.mma per stage and
 //              hands the stage back with tcgen05.commit -> `empty` mbarrier; the last commit signals the epilogue.
-// Split-K partial tiles go to a workspace; the last CTA of each output tile (device counter) adds them in split
-// order, so the result does not depend on scheduling.
+// Split-K partial tiles go to a workspace and a small second kernel adds them in split order, so the result does
+// not depend on scheduling.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -25,7 +25,7 @@
 namespace dgn {
 
 constexpr int BM = 128, BN = 64, BK = 32;          // tile (BK floats = one 128 B swizzle row)
-constexpr int kStages = 3;
+constexpr int kStages = 2;                         // 96 KB per CTA -> two CTAs per SM hide each other's load latency
 constexpr int kLoaderThreads = 128;
 constexpr int kGemmThreads = 160;                   // 4 loader/epilogue warps + 1 MMA warp
 constexpr int A_TILE = BM * BK * 4, B_TILE = BN * BK * 4;                 // bytes
@@ -90,11 +90,9 @@ __device__ __forceinline__ uint32_t sw128(uint32_t row_in_atom, uint32_t ch) { r
 
 // round-to-nearest TF32 (the tensor core itself just ignores the low 13 mantissa bits, so pre-rounded values are
 // consumed exactly): |a - hi| <= 2^-12 |a|, and the residual is rounded once more, leaving ~2^-23 |a| unaccounted
-__device__ __forceinline__ float rn_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
+// (integer add + mask = round-half-away in magnitude; the cvt.rna.tf32.f32 instruction does the same but runs on a
+//  low-throughput conversion pipe and made the loader warps the bottleneck of the whole kernel)
+__device__ __forceinline__ float rn_tf32(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
 
 __device__ __forceinline__ void split_store(unsigned char* hi_tile, unsigned char* lo_tile, uint32_t off, float4 v) {
   float4 h, l;
@@ -106,26 +104,45 @@ __device__ __forceinline__ void split_store(unsigned char* hi_tile, unsigned cha
   *reinterpret_cast<float4*>(lo_tile + off) = l;
 }
 
-// One operand tile: ROWS (M or N extent) x BK, K-major source [ROWS][K] or MN-major source [K][ROWS]
+// One operand tile: ROWS (M or N extent) x BK, K-major source [ROWS][K] or MN-major source [K][ROWS].
+// fetch_tile issues the global loads into registers (the next k-block is fetched before the current one is
+// converted and stored, so its latency overlaps that work); store_tile does the split + swizzled stores.
 template <int ROWS, bool KMAJOR>
-__device__ __forceinline__ void load_tile(const float* __restrict__ src, int ld, int r0, int k0, int r_max, int k_max,
-                                          unsigned char* hi_tile, unsigned char* lo_tile, int t) {
+__device__ __forceinline__ void fetch_tile(const float* __restrict__ src, int ld, int r0, int k0, int r_max, int k_max,
+                                           float4 (&v)[ROWS * BK / 4 / kLoaderThreads], int t) {
   constexpr int CHUNKS = ROWS * BK / 4;
 #pragma unroll
   for (int i = 0; i < CHUNKS / kLoaderThreads; ++i) {
     const int id = t + i * kLoaderThreads;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if constexpr (KMAJOR) {
+      const int row = id >> 3, ch = id & 7;
+      const int gr = r0 + row, gk = k0 + ch * 4;
+      if (gr < r_max && gk < k_max) v[i] = __ldg(reinterpret_cast<const float4*>(src + (size_t)gr * ld + gk));
+    } else {
+      constexpr int CPR = ROWS / 4;
+      const int krow = id / CPR, ch = id % CPR;
+      const int gk = k0 + krow, gr = r0 + ch * 4;
+      if (gk < k_max && gr < r_max) v[i] = __ldg(reinterpret_cast<const float4*>(src + (size_t)gk * ld + gr));
+    }
+  }
+}
+
+template <int ROWS, bool KMAJOR>
+__device__ __forceinline__ void store_tile(const float4 (&vv)[ROWS * BK / 4 / kLoaderThreads], unsigned char* hi_tile,
+                                           unsigned char* lo_tile, int t) {
+  constexpr int CHUNKS = ROWS * BK / 4;
+#pragma unroll
+  for (int i = 0; i < CHUNKS / kLoaderThreads; ++i) {
+    const int id = t + i * kLoaderThreads;
+    const float4 v = vv[i];
     uint32_t off;
     if constexpr (KMAJOR) {
       const int row = id >> 3, ch = id & 7;                      // 8 chunks (32 floats of K) per row
-      const int gr = r0 + row, gk = k0 + ch * 4;
-      if (gr < r_max && gk < k_max) v = __ldg(reinterpret_cast<const float4*>(src + (size_t)gr * ld + gk));
       off = (uint32_t)(row >> 3) * 1024u + sw128(row & 7, ch);
     } else {
       constexpr int CPR = ROWS / 4;                              // 16 B chunks per K-row
       const int krow = id / CPR, ch = id % CPR;
-      const int gk = k0 + krow, gr = r0 + ch * 4;
-      if (gk < k_max && gr < r_max) v = __ldg(reinterpret_cast<const float4*>(src + (size_t)gk * ld + gr));
       // SW128_32B atoms: 4 K-rows x 32 MN-floats (512 B); atoms contiguous along MN, then along K
       const uint32_t kl = krow & 3, c16 = ch & 7;
       off = (uint32_t)(krow >> 2) * (uint32_t)(ROWS / 32) * 512u + (uint32_t)(ch >> 3) * 512u + kl * 128u +
@@ -136,14 +153,13 @@ __device__ __forceinline__ void load_tile(const float* __restrict__ src, int ld,
 }
 
 template <bool A_K, bool B_K>
-__global__ void __launch_bounds__(kGemmThreads, 1) gemm_tf32x3_kernel(const GemmArgs g) {
+__global__ void __launch_bounds__(kGemmThreads, 2) gemm_tf32x3_kernel(const GemmArgs g) {
   extern __shared__ unsigned char raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * STAGE_BYTES);
   uint64_t* empty = full + kStages;
   uint64_t* accum_full = empty + kStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
-  __shared__ int s_is_last;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN, split = blockIdx.z;
@@ -168,15 +184,28 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tf32x3_kernel(const Gemm
 
   if (warp < 4) {
     // ------------------------------ loaders ------------------------------
+    float4 va[BM * BK / 4 / kLoaderThreads], vb[BN * BK / 4 / kLoaderThreads];
+    fetch_tile<BM, A_K>(g.A, g.lda, m0, kb0 * BK, g.M, g.K, va, tid);
+    fetch_tile<BN, B_K>(g.B, g.ldb, n0, kb0 * BK, g.N, g.K, vb, tid);
     for (int i = 0; i < nkb; ++i) {
       const int s = i % kStages;
+      float4 na[BM * BK / 4 / kLoaderThreads], nb_[BN * BK / 4 / kLoaderThreads];
+      if (i + 1 < nkb) {                                             // next k-block in flight during this one's stores
+        fetch_tile<BM, A_K>(g.A, g.lda, m0, (kb0 + i + 1) * BK, g.M, g.K, na, tid);
+        fetch_tile<BN, B_K>(g.B, g.ldb, n0, (kb0 + i + 1) * BK, g.N, g.K, nb_, tid);
+      }
       if (i >= kStages) mb_wait(&empty[s], ((i / kStages) - 1) & 1);
       unsigned char* st = smem + s * STAGE_BYTES;
-      const int k0 = (kb0 + i) * BK;
-      load_tile<BM, A_K>(g.A, g.lda, m0, k0, g.M, g.K, st, st + A_TILE, tid);
-      load_tile<BN, B_K>(g.B, g.ldb, n0, k0, g.N, g.K, st + 2 * A_TILE, st + 2 * A_TILE + B_TILE, tid);
+      store_tile<BM, A_K>(va, st, st + A_TILE, tid);
+      store_tile<BN, B_K>(vb, st + 2 * A_TILE, st + 2 * A_TILE + B_TILE, tid);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
       mb_arrive(&full[s]);
+      if (i + 1 < nkb) {
+#pragma unroll
+        for (int q = 0; q < BM * BK / 4 / kLoaderThreads; ++q) va[q] = na[q];
+#pragma unroll
+        for (int q = 0; q < BN * BK / 4 / kLoaderThreads; ++q) vb[q] = nb_[q];
+      }
     }
   } else if (lane == 0) {
     // ------------------------------ MMA issuer ------------------------------
@@ -241,38 +270,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tf32x3_kernel(const Gemm
 
     const int row = warp * 32 + lane, gm = m0 + row;
     const int tile_id = blockIdx.y * gridDim.x + blockIdx.x;
-    if (g.splits > 1) {
+    if (g.splits > 1) {                                              // partial tile -> workspace; reduced by splitk_reduce_kernel
       float* part = g.ws + ((size_t)split * gridDim.x * gridDim.y + tile_id) * (BM * BN) + (size_t)row * BN;
 #pragma unroll
       for (int j = 0; j < BN; j += 4)
         *reinterpret_cast<float4*>(part + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
                                                            __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-      __threadfence();
-      asm volatile("bar.sync 1, 128;" ::: "memory");                 // the 4 epilogue warps only
-      if (tid == 0) {
-        const unsigned done = atomicAdd(&g.counters[tile_id], 1u);
-        s_is_last = (done == (unsigned)g.splits - 1);
-        if (s_is_last) g.counters[tile_id] = 0u;
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (s_is_last) {
-        __threadfence();
-#pragma unroll
-        for (int j = 0; j < BN; ++j) r[j] = 0u;
-        for (int sp = 0; sp < g.splits; ++sp) {                      // fixed order: deterministic
-          const float* p = g.ws + ((size_t)sp * gridDim.x * gridDim.y + tile_id) * (BM * BN) + (size_t)row * BN;
-#pragma unroll
-          for (int j = 0; j < BN; j += 4) {
-            const float4 v = __ldcg(reinterpret_cast<const float4*>(p + j));
-            r[j] = __float_as_uint(__uint_as_float(r[j]) + v.x);
-            r[j + 1] = __float_as_uint(__uint_as_float(r[j + 1]) + v.y);
-            r[j + 2] = __float_as_uint(__uint_as_float(r[j + 2]) + v.z);
-            r[j + 3] = __float_as_uint(__uint_as_float(r[j + 3]) + v.w);
-          }
-        }
-      }
     }
-    if (g.splits == 1 || s_is_last) {
+    if (g.splits == 1) {
       if (gm < g.M) {
         if (!g.c_transposed) {
           // handled below (staged through shared memory so that the stores are coalesced)
@@ -289,7 +294,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tf32x3_kernel(const Gemm
       }
     }
   }
-  if (warp < 4 && !g.c_transposed && (g.splits == 1 || s_is_last)) {
+  if (warp < 4 && !g.c_transposed && g.splits == 1) {
     // every warp transposes its 32 x 64 block through its own shared-memory patch (the pipeline stages are
     // idle by now): thread-per-row registers -> lane-per-column stores, 128 B per instruction
     float* patch = reinterpret_cast<float*>(smem) + warp * (32 * (BN + 1));
@@ -317,6 +322,33 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tf32x3_kernel(const Gemm
   }
 }
 
+// Sums the split-K partial tiles in split order (deterministic) and writes / accumulates C.
+// One thread per (row, 4-column chunk) of the M x N result.
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const GemmArgs g, int m_tiles, int n_tiles) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int n4 = (g.N + 3) / 4;
+  if (idx >= (long long)g.M * n4) return;
+  const int m = (int)(idx / n4), n = (int)(idx - (long long)m * n4) * 4;
+  const int tm = m / BM, tn = n / BN, tile_id = tn * m_tiles + tm;
+  const size_t in_tile = (size_t)(m - tm * BM) * BN + (n - tn * BN);
+  const size_t split_stride = (size_t)m_tiles * n_tiles * (BM * BN);
+  const float* p = g.ws + (size_t)tile_id * (BM * BN) + in_tile;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+  for (int sp = 0; sp < g.splits; ++sp) {
+    const float4 v = __ldcs(reinterpret_cast<const float4*>(p + (size_t)sp * split_stride));
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  const float a[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (n + j < g.N) {
+      float* c = g.c_transposed ? g.C + (size_t)(n + j) * g.ldc + m : g.C + (size_t)m * g.ldc + n + j;
+      *c = g.accumulate ? *c + a[j] : a[j];
+    }
+  }
+}
+
 }  // namespace dgn
 
 using namespace dgn;
@@ -336,7 +368,7 @@ extern "C" int64_t dgn_gemm_ws_floats(void) { return kWsCounters + (int64_t)kWsT
 static int pick_splits(int mt, int nt, int kb) {
   const int tiles = mt * nt;
   if (tiles >= 148 || kb <= 2) return 1;
-  int s = (2 * 148 + tiles - 1) / tiles;                              // aim at ~2 CTAs' worth of tiles per SM
+  int s = (2 * 148) / tiles;                                          // one wave at 2 CTAs per SM
   if (s > 16) s = 16;
   if (s > kb / 2) s = kb / 2;                                         // at least 2 k-blocks per split
   return s < 1 ? 1 : s;
@@ -360,7 +392,7 @@ extern "C" int dgn_gemm_tf32x3(int32_t M, int32_t N, int32_t K, const float* A, 
   g.kb_per_split = (kb + splits - 1) / splits;
   splits = (kb + g.kb_per_split - 1) / g.kb_per_split;                // no empty split
   g.splits = splits;
-  if (splits > 1 && ((int64_t)splits * mt * nt > kWsTiles || mt * nt > kWsCounters)) return DGN_ERR_UNSUPPORTED;
+  if (splits > 1 && (int64_t)splits * mt * nt > kWsTiles) return DGN_ERR_UNSUPPORTED;
   g.ws = ws + kWsCounters;
   g.counters = reinterpret_cast<unsigned*>(ws);
   const dim3 grid(mt, nt, splits);
@@ -378,6 +410,11 @@ extern "C" int dgn_gemm_tf32x3(int32_t M, int32_t N, int32_t K, const float* A, 
   else LAUNCH(false, false);
 #undef LAUNCH
   if (e == cudaSuccess) e = cudaGetLastError();
+  if (e == cudaSuccess && splits > 1) {
+    const long long threads = (long long)M * ((N + 3) / 4);
+    splitk_reduce_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(g, mt, nt);
+    e = cudaGetLastError();
+  }
   if (e != cudaSuccess) { g_dgn_last_cuda = e; return DGN_ERR_CUDA; }
   return DGN_OK;
 }

@@ -380,7 +380,10 @@ def gemm(a, b, a_kmajor=True, b_kmajor=True, out=None, accumulate=False, c_trans
     if out is None:
         out = torch.empty((N, M) if c_transposed else (M, N), device=a.device, dtype=torch.float32)
         accumulate = False
-    ok = (GEMM_ENABLED and a.dtype == torch.float32 and b.dtype == torch.float32 and a.stride(1) == 1 and
+    # the tensor-core kernel wins once there is real work (long K or a large output); tiny products are
+    # launch-latency bound and stay with the library (measured: tools/gemm_bench.py, profiles/README.md)
+    worth = K >= 256 or M * N >= (1 << 20)
+    ok = (GEMM_ENABLED and worth and a.dtype == torch.float32 and b.dtype == torch.float32 and a.stride(1) == 1 and
           b.stride(1) == 1 and out.stride(1) == 1 and K > 0)
     if ok:
         rc = lib.dgn_gemm_tf32x3(M, N, K, a.data_ptr(), a.stride(0), int(a_kmajor), b.data_ptr(), b.stride(0),

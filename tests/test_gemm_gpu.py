@@ -2,8 +2,14 @@
 import pytest
 import torch
 
-from dgn_b200 import _lib
+from dgn_b200 import _lib, ops
 from dgn_b200.ops import gemm
+
+
+@pytest.fixture(autouse=True)
+def _count_tensor_core_launches():
+    ops.LAUNCHES = 0
+    yield
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -36,6 +42,8 @@ def test_gemm_matches_fp64(M, N, K, a_k, b_k):
     before = _lib.lib.dgn_abi_version()
     out = gemm(a, b, a_kmajor=a_k, b_kmajor=b_k)
     assert before and out.shape == (M, N)
+    if K >= 256 and K % 4 == 0 and (M if not a_k else K) % 4 == 0 and (N if not b_k else K) % 4 == 0:
+        assert ops.LAUNCHES == 1, "expected the tcgen05 kernel, not the library fallback"
     lib_out = (a if a_k else a.t()) @ (b.t() if b_k else b)                 # fp32 library GEMM
     scale = float(ref.abs().max())
     err = float((out.double() - ref).abs().max())
