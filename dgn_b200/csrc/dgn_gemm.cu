@@ -301,16 +301,24 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tf32x3_kernel(const Gemm
 #pragma unroll
     for (int j = 0; j < BN; ++j) patch[lane * (BN + 1) + j] = __uint_as_float(r[j]);
     __syncwarp();
+    const bool pair_ok = (g.ldc % 2 == 0) && (n0 + BN <= g.N) && ((reinterpret_cast<uintptr_t>(g.C) & 7u) == 0);
     for (int rr = 0; rr < 32; ++rr) {
       const int gmr = m0 + warp * 32 + rr;
       if (gmr >= g.M) break;
       float* crow = g.C + (size_t)gmr * g.ldc + n0;
+      if (pair_ok) {                                                   // lane writes columns 2*lane, 2*lane+1: 256 B per warp
+        float2 v = make_float2(patch[rr * (BN + 1) + 2 * lane], patch[rr * (BN + 1) + 2 * lane + 1]);
+        float2* dst = reinterpret_cast<float2*>(crow + 2 * lane);
+        if (g.accumulate) { const float2 o = *dst; v.x += o.x; v.y += o.y; }
+        *dst = v;
+      } else {
 #pragma unroll
-      for (int h = 0; h < BN / 32; ++h) {
-        const int j = lane + 32 * h;
-        if (n0 + j < g.N) {
-          const float v = patch[rr * (BN + 1) + j];
-          crow[j] = g.accumulate ? crow[j] + v : v;
+        for (int h = 0; h < BN / 32; ++h) {
+          const int j = lane + 32 * h;
+          if (n0 + j < g.N) {
+            const float v = patch[rr * (BN + 1) + j];
+            crow[j] = g.accumulate ? crow[j] + v : v;
+          }
         }
       }
     }
@@ -334,11 +342,13 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const GemmArgs g, in
   const size_t split_stride = (size_t)m_tiles * n_tiles * (BM * BN);
   const float* p = g.ws + (size_t)tile_id * (BM * BN) + in_tile;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-  for (int sp = 0; sp < g.splits; ++sp) {
-    const float4 v = __ldcs(reinterpret_cast<const float4*>(p + (size_t)sp * split_stride));
-    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-  }
+  float4 v[16];                                                      // splits <= 16: every load in flight at once
+#pragma unroll
+  for (int sp = 0; sp < 16; ++sp)
+    v[sp] = (sp < g.splits) ? __ldcs(reinterpret_cast<const float4*>(p + (size_t)sp * split_stride))
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int sp = 0; sp < 16; ++sp) { acc.x += v[sp].x; acc.y += v[sp].y; acc.z += v[sp].z; acc.w += v[sp].w; }
   const float a[4] = {acc.x, acc.y, acc.z, acc.w};
 #pragma unroll
   for (int j = 0; j < 4; ++j) {

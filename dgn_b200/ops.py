@@ -396,11 +396,10 @@ def gemm(a, b, a_kmajor=True, b_kmajor=True, out=None, accumulate=False, c_trans
             check(rc, "dgn_gemm_tf32x3")
     A = a if a_kmajor else a.t()
     Bm = b.t() if b_kmajor else b
-    res = torch.mm(A, Bm)
-    if c_transposed:
-        res = res.t()
+    if c_transposed:                              # (A @ B)^T = B^T @ A^T
+        A, Bm = Bm.t(), A.t()
     if accumulate:
-        out.add_(res)
+        out.addmm_(A, Bm)                         # one library launch, beta = 1
     else:
-        out.copy_(res)
+        torch.mm(A, Bm, out=out)
     return out
