@@ -10,8 +10,9 @@ L=4, hidden 64, 10 aggregators x 3 scalers, k=2 eigenvectors).  Prints ONE JSON 
 * value      device-resident inputs, CUDA-event time of the K steps (L2 flushed between steps), max over ranks
 * e2e        same metric with HOST inputs: per step one H2D copy of the packed batch from pinned memory
              and a D2H read of the loss, inside the timed region
-* roofline   fused aggregation kernels (forward + backward of layer 0) timed alone with CUDA events,
-             algorithmic bytes of SURVEY.md 8(d) / DESIGN.md over the measured HBM copy peak
+* roofline   fused aggregation kernels (forward + backward of one layer of the workload) timed alone with CUDA
+             events (CUDA graph of 8 launches over rotating operand sets > L2), algorithmic bytes of SURVEY.md 8(d) /
+             DESIGN.md over the measured HBM copy peak (MEASURED_PEAKS.json)
 * cpu_baseline / --impl reference   the oracle port of the reference's python path on the host cores
 """
 from __future__ import annotations
@@ -126,7 +127,7 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -228,6 +229,15 @@ def kernel_roofline(graph, avg_log, device, rot=8, replays=10):
     bf, bb = agg_bytes(n_real, e_real, F, A, S, 3, 2)
     return {"fwd_us": t_f * 1e6, "bwd_us": t_b * 1e6, "bytes_fwd": bf, "bytes_bwd": bb,
             "achieved_gbs": (bf + bb) / (t_f + t_b) / 1e9, "fwd_gbs": bf / t_f / 1e9, "bwd_gbs": bb / t_b / 1e9}
+
+
+def measured_traffic():
+    """DRAM bytes of one forward + backward launch from the committed ncu capture (profiles/), or None."""
+    try:
+        t = json.load(open(os.path.join(REPO, "profiles", "r1_agg_traffic.json")))
+        return int(t["fwd_bytes"]) + int(t["bwd_bytes"])
+    except Exception:
+        return None
 
 
 def measured_peak():
@@ -369,7 +379,9 @@ def run_gpu_arm(args):
         kr = kernel_roofline(step.g, avg_log, dev)
         peak, peak_src = measured_peak()
         roof = {"bound": "hbm", "achieved": kr["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": kr["achieved_gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                "frac": kr["achieved_gbs"] / peak, "traffic": measured_traffic(), "peak_source": peak_src,
+                "traffic_note": "dram__bytes_read+write of one fwd+bwd launch, ncu --set full (profiles/r1_agg_traffic.json); "
+                                "output writes stay in the 126 MB L2 during the kernel, algorithmic bytes are bytes_fwd+bytes_bwd",
                 "kernel": "dgn agg_fwd_kernel + agg_bwd_dst_kernel + agg_bwd_src_kernel (one DGN layer of the bench "
                           "workload, timed alone: CUDA graph of 8 launches on rotating operand sets > L2)",
                 "fwd_us": kr["fwd_us"], "bwd_us": kr["bwd_us"], "bytes_fwd": kr["bytes_fwd"],
@@ -397,7 +409,7 @@ def run_gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="dgn_b200", choices=["dgn_b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
