@@ -15,6 +15,11 @@
  *                       and dgl.batch (rb/data/molecules.py:229).
  *   dgn_norm_*        - rb/nets/dgn_layer.py:122-130 (graph norm, BatchNorm1d, ReLU, residual).
  *   dgn_readout_*     - dgl.{mean,sum,max}_nodes at rb/nets/molecules_graph_regression/dgn_net.py:71-86.
+ *   dgn_gemm_tf32x3   - the Linear layers of pretrans / posttrans (FCLayer, rb/nets/layers.py:76-100) in fp32
+ *                       accuracy on the tcgen05 tensor cores.
+ *   dgn_embedding_backward, dgn_adam_step - the two remaining per-step pieces of the training loop that sit
+ *                       between launches of the path (rb/nets/molecules_graph_regression/dgn_net.py:58,
+ *                       rb/main_molecules.py:82).
  *
  * Conventions: plain pointers and sizes only, no ownership transfer, no allocation, no
  * exceptions.  Every pointer in DgnGraph / DgnAggIO / DgnAggGrad is DEVICE memory unless the

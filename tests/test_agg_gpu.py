@@ -280,3 +280,48 @@ def test_generic_kernels_still_match_oracle_when_tile_kernels_are_disabled():
                           "-m", "gpu", "-k", "aggregate_matches_oracle or cat_input or towers_group or registry_callable"],
                          env=env, capture_output=True, text=True, cwd=repo)
     assert out.returncode == 0, out.stdout[-3000:]
+
+
+def test_empty_and_degenerate_graphs():
+    """No edges at all, a single node, a single column, and a star whose hub degree spans several edge batches."""
+    full = [AGGREGATORS[a] for a in ("mean", "max", "min", "std", "dir1-dx", "dir2-av")]
+    # (1) graph without edges: every row is zero, gradients are zero / identity through the copied columns
+    g = BatchedGraph(5, np.zeros(0, np.int32), np.zeros(0, np.int32), [5]).to(DEV)
+    eig = torch.randn(5, 3, device=DEV)
+    h = torch.randn(5, 8, device=DEV, requires_grad=True)
+    spec = AggSpec(full, [SCALERS[s] for s in S3], 1.0, 8, 3)
+    out = aggregate(g, spec, _lib.MSG_SOURCE, h, eig, x=h, cat_input=True)
+    assert torch.equal(out[:, :8], h.detach()) and torch.all(out[:, 8:] == 0)
+    out.sum().backward()
+    assert torch.equal(h.grad, torch.ones_like(h))
+    # (2) zero nodes
+    g0 = BatchedGraph(0, np.zeros(0, np.int32), np.zeros(0, np.int32), []).to(DEV)
+    out0 = aggregate(g0, spec, _lib.MSG_SOURCE, torch.zeros(0, 8, device=DEV), torch.zeros(0, 3, device=DEV),
+                     x=torch.zeros(0, 8, device=DEV))
+    assert out0.shape == (0, 3 * 6 * 8)
+    # (3) one column (scalar path), self loop on a single node
+    g1 = BatchedGraph(1, np.zeros(1, np.int32), np.zeros(1, np.int32), [1]).to(DEV)
+    x1 = torch.tensor([[2.5]], device=DEV, requires_grad=True)
+    spec1 = AggSpec([AGGREGATORS[a] for a in ("mean", "std", "dir1-dx")], [SCALERS["identity"]], 1.0, 1, 2)
+    o1 = aggregate(g1, spec1, _lib.MSG_SOURCE, x1, torch.tensor([[0.0, 0.3]], device=DEV), x=x1)
+    assert_close(o1, np.array([[2.5, 1e-4, 0.0]], np.float32), what="self loop")
+    # (4) star: hub with 1500 in-edges (several batches of the tile kernels), leaves with none
+    n = 1501
+    src = np.arange(1, n, dtype=np.int32)
+    dst = np.zeros(n - 1, np.int32)
+    gs = BatchedGraph(n, src, dst, [n])
+    rng = np.random.default_rng(0)
+    hs = torch.tensor(rng.standard_normal((n, 16)).astype(np.float32))
+    es = torch.tensor(rng.standard_normal((n, 3)).astype(np.float32))
+    names = ["mean", "max", "min", "std", "dir1-dx", "dir2-av", "sum"]
+    hl = hs.clone().requires_grad_(True)
+    ref = oracle_aggregate(n, src.astype(np.int64), dst.astype(np.int64), es, hl, hl[src.astype(np.int64)], names, S3, 1.3)
+    gy = torch.tensor(rng.standard_normal(tuple(ref.shape)).astype(np.float32))
+    ref.backward(gy)
+    gs.to(DEV)
+    hd = hs.to(DEV).requires_grad_(True)
+    specs = AggSpec([AGGREGATORS[a] for a in names], [SCALERS[s] for s in S3], 1.3, 16, 3)
+    outs = aggregate(gs, specs, _lib.MSG_SOURCE, hd, es.to(DEV), x=hd)
+    outs.backward(gy.to(DEV))
+    assert_close(outs, ref, what="star out")
+    assert_close(hd.grad, hl.grad, what="star dh")
