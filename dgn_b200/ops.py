@@ -94,6 +94,8 @@ def _agg_io(mode, x, q, r, h_in, eig, out, lead, Wt, cat_input, q_bias=None):
 def agg_forward_raw(graph, spec, mode, x, q, r, h_in, eig, out, cat_input, q_bias=None):
     """dgn_agg_forward on pre-allocated tensors (fp32, unit inner stride).  ``out`` is
     ``[N, T*((F_t if cat_input else 0) + S*A*F_t)]``."""
+    if graph.number_of_nodes() == 0:
+        return                                   # empty batch: nothing to launch (zero-size tensors have no address)
     lead = spec.Fg if cat_input else 0
     Wt = lead + spec.out_width
     io = _agg_io(mode, x, q, r, h_in, eig, out, lead, Wt, cat_input, q_bias)
@@ -105,6 +107,8 @@ def agg_forward_raw(graph, spec, mode, x, q, r, h_in, eig, out, cat_input, q_bia
 def agg_backward_raw(graph, spec, mode, x, q, r, h_in, eig, g_out, cat_input, d_x=None, d_q=None, d_r=None,
                      d_h=None, edge_ws=None, fold_h_in=False, q_bias=None, d_h_addend=None):
     """dgn_agg_backward on pre-allocated tensors; any of the d_* outputs may be None."""
+    if graph.number_of_nodes() == 0:
+        return
     lead = spec.Fg if cat_input else 0
     Wt = lead + spec.out_width
     io = _agg_io(mode, x, q, r, h_in, eig, g_out, lead, Wt, False, q_bias)     # io.out is never written here
