@@ -18,7 +18,8 @@
 //         the per-edge gathers become shared-memory reads;
 //       * backward: the tile's S*A gradient slabs (the dominant traffic), one bulk copy per node row.
 //
-// Edges of a tile are processed in batches of EB slots so shared memory stays bounded for any degree.
+// Edges are processed in rounds: in round r every node of the tile contributes its in-edge slots
+// [r*EBN, (r+1)*EBN), so all node threads stay busy whatever the degree and shared memory stays bounded.
 // The softmax aggregators (W_EXP) and F/VEC > 256 fall back to the generic kernels in dgn_agg_fwd/bwd.cu.
 #include <limits.h>
 
@@ -31,7 +32,8 @@ constexpr int kMaxTileThreads = 256;
 struct TileCfg {
   int threads;                       // block size (128 or 256)
   int TN;                            // destination nodes per tile
-  int EB;                            // edge slots per batch
+  int EBN;                           // edge slots per node and round
+  int EB;                            // edge slots per round = TN * EBN
   int win_rows;                      // capacity of the staged source window in rows (0 = never stage)
   int use_msg;                       // gathered message rows are bulk-copied into shared memory per batch
   int use_gt;                        // backward: the tile's gradient slabs are bulk-copied into shared memory
@@ -71,7 +73,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 struct Tile {
   int* s_ptr; float* s_ev; float* s_zw; float* s_zabs; float* s_f0; float* s_f1; float* s_coef;
   int* s_src; float* s_w; uint64_t* s_bar; int* s_red; float* s_win; float* s_msg; float* s_gt;
-  int v0, nv, E0, E1, ln, c, v, ne0, ne1, umin, TN, EB;
+  int v0, nv, E0, E1, ln, c, v, ne0, ne1, umin, TN, EB, EBN;
   uint32_t msg_parity;
   bool active, staged, use_msg;
 };
@@ -97,6 +99,7 @@ __device__ __forceinline__ void tile_prologue(const KernelArgs& k, const TileCfg
   T.s_gt = reinterpret_cast<float*>(smem + tc.off_gt);
   T.TN = TN;
   T.EB = tc.EB;
+  T.EBN = tc.EBN;
   T.v0 = blockIdx.x * TN;
   T.nv = min(TN, k.N - T.v0);
   T.ln = tid / P.chunks;
@@ -162,15 +165,22 @@ __device__ __forceinline__ void tile_prologue(const KernelArgs& k, const TileCfg
   }
 }
 
-// Phase A of one batch of edge slots [b0, b0+nb): kick off the message-row copies, compute the eigen-weights
-// into s_src / s_w, then (optionally) add this batch to the per-(node, slot) sums.
+// Phase A of round r: slot j of local node l is global in-edge slot s_ptr[l] + r*EBN + j (if it exists) and lives at
+// index l*EBN + j of the round buffers.  Kick off the message-row copies, compute the eigen-weights into
+// s_src / s_w, then (optionally) add this round to the per-(node, slot) sums.
 template <int MODE, int VEC, int NS>
-__device__ __forceinline__ void tile_batch_begin(const KernelArgs& k, Tile& T, int b0, int nb, bool accumulate_z) {
+__device__ __forceinline__ void tile_round_begin(const KernelArgs& k, Tile& T, int r, bool accumulate_z) {
   const AggPlan& P = k.plan;
-  const int tid = threadIdx.x, TN = T.TN, nthr = blockDim.x;
-  if (T.use_msg && tid == 0) mbar_expect_tx(&T.s_bar[1], (uint32_t)nb * (uint32_t)P.F * 4u);
-  for (int i = tid; i < nb; i += nthr) {
-    const int e = b0 + i;
+  const int tid = threadIdx.x, TN = T.TN, nthr = blockDim.x, EBN = T.EBN;
+  if (T.use_msg && tid == 0) {
+    int cnt = 0;                                // valid slots of this round
+    for (int l = 0; l < T.nv; ++l) cnt += min(EBN, max(0, T.s_ptr[l + 1] - T.s_ptr[l] - r * EBN));
+    mbar_expect_tx(&T.s_bar[1], (uint32_t)cnt * (uint32_t)P.F * 4u);
+  }
+  for (int i = tid; i < T.nv * EBN; i += nthr) {
+    const int l = i / EBN, j = i - l * EBN;
+    const int e = T.s_ptr[l] + r * EBN + j;
+    if (e >= T.s_ptr[l + 1]) continue;
     const int u = __ldg(k.in_src + e);
     T.s_src[i] = u;
     if (T.use_msg) {                            // whole message row -> shared memory, asynchronously
@@ -179,31 +189,24 @@ __device__ __forceinline__ void tile_batch_begin(const KernelArgs& k, Tile& T, i
       else row = k.x + (size_t)u * k.ld_x;
       bulk_g2s(T.s_msg + (size_t)i * P.F, row, (uint32_t)P.F * 4u, &T.s_bar[1]);
     }
-    if constexpr (NS > 0) {
-      int lo = 0, hi = T.nv;                    // local destination: largest l with s_ptr[l] <= e
-      while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (T.s_ptr[mid] <= e) lo = mid; else hi = mid;
-      }
 #pragma unroll
-      for (int s = 0; s < NS; ++s) {
-        if (s < P.n_slots) {
-          const float d = __ldg(k.eig + (size_t)u * k.ld_eig + P.slot_eig[s]) - T.s_ev[s * TN + lo];
-          T.s_w[s * T.EB + i] = edge_weight(P.slot_w[s], d, 0.f, 0.f);
-        }
+    for (int s = 0; s < NS; ++s) {
+      if (s < P.n_slots) {
+        const float d = __ldg(k.eig + (size_t)u * k.ld_eig + P.slot_eig[s]) - T.s_ev[s * TN + l];
+        T.s_w[s * T.EB + i] = edge_weight(P.slot_w[s], d, 0.f, 0.f);
       }
     }
   }
   __syncthreads();
   if constexpr (NS > 0) {
     if (accumulate_z) {                         // one thread per (node, slot): sequential, edge-id order
-      for (int j = tid; j < T.nv * NS; j += nthr) {
-        const int l = j / NS, s = j - l * NS;
+      for (int q = tid; q < T.nv * NS; q += nthr) {
+        const int l = q / NS, s = q - l * NS;
         if (s < P.n_slots) {
-          const int a0 = max(T.s_ptr[l], b0) - b0, a1 = min(T.s_ptr[l + 1], b0 + nb) - b0;
+          const int cnt = min(EBN, max(0, T.s_ptr[l + 1] - T.s_ptr[l] - r * EBN));
           float zw = T.s_zw[s * TN + l], za = T.s_zabs[s * TN + l];
-          for (int i = a0; i < a1; ++i) {
-            const float w = T.s_w[s * T.EB + i];
+          for (int j = 0; j < cnt; ++j) {
+            const float w = T.s_w[s * T.EB + l * EBN + j];
             zw += w;
             za += fabsf(w);
           }
@@ -213,7 +216,7 @@ __device__ __forceinline__ void tile_batch_begin(const KernelArgs& k, Tile& T, i
       }
     }
   }
-  if (T.use_msg) {                              // every thread observes the completed copies of this batch
+  if (T.use_msg) {                              // every thread observes the completed copies of this round
     mbar_wait(&T.s_bar[1], T.msg_parity);
     T.msg_parity ^= 1u;
   }
@@ -362,19 +365,18 @@ __global__ void __launch_bounds__(kMaxTileThreads) agg_fwd_tile_kernel(const __g
   RowAcc<VEC, NS, ISO> R;
   acc_init(R);
   bool win_waited = false;
-  for (int b0 = T.E0; b0 < T.E1; b0 += T.EB) {
-    const int nb = min(T.EB, T.E1 - b0);
-    tile_batch_begin<MODE, VEC, NS>(k, T, b0, nb, true);
+  const int Dn = T.ne1 - T.ne0;
+  for (int r = 0; __syncthreads_or(T.active && r * T.EBN < Dn); ++r) {   // barrier + "any node has slots left"
+    tile_round_begin<MODE, VEC, NS>(k, T, r, true);
     if (T.staged && !win_waited) { mbar_wait(&T.s_bar[0], 0); win_waited = true; }
     if (T.active) {
-      const int i0 = max(T.ne0, b0) - b0, i1 = min(T.ne1, b0 + nb) - b0;
+      const int cnt = min(T.EBN, max(0, Dn - r * T.EBN)), base = T.ln * T.EBN, e0 = T.ne0 + r * T.EBN;
 #pragma unroll 4
-      for (int i = i0; i < i1; ++i) {
-        const Vec<VEC> m = tile_message<MODE, VEC>(k, T, i, b0 + i, qv);
-        acc_edge<VEC, NS, ISO>(P, R, m, T.s_w, T.EB, i);
+      for (int j = 0; j < cnt; ++j) {
+        const Vec<VEC> m = tile_message<MODE, VEC>(k, T, base + j, e0 + j, qv);
+        acc_edge<VEC, NS, ISO>(P, R, m, T.s_w, T.EB, base + j);
       }
     }
-    __syncthreads();
   }
   tile_factors<NS>(k, T);
   tile_scaler_coefs(k, T);
@@ -540,21 +542,21 @@ __global__ void __launch_bounds__(kMaxTileThreads) agg_bwd_tile_kernel(const __g
   RowAcc<VEC, NS, ISO> R;
   acc_init(R);
   bool win_waited = false;
-  const bool single_batch = (T.E1 - T.E0) <= T.EB;
-  for (int b0 = T.E0; b0 < T.E1; b0 += T.EB) {
-    const int nb = min(T.EB, T.E1 - b0);
-    tile_batch_begin<MODE, VEC, NS>(k, T, b0, nb, true);
+  int rounds = 0;
+  for (int r = 0; __syncthreads_or(T.active && r * T.EBN < D); ++r) {    // barrier + "any node has slots left"
+    tile_round_begin<MODE, VEC, NS>(k, T, r, true);
     if (T.staged && !win_waited) { mbar_wait(&T.s_bar[0], 0); win_waited = true; }
     if (T.active) {
-      const int i0 = max(T.ne0, b0) - b0, i1 = min(T.ne1, b0 + nb) - b0;
+      const int cnt = min(T.EBN, max(0, D - r * T.EBN)), base = T.ln * T.EBN, e0 = T.ne0 + r * T.EBN;
 #pragma unroll 4
-      for (int i = i0; i < i1; ++i) {
-        const Vec<VEC> m = tile_message<MODE, VEC>(k, T, i, b0 + i, qv);
-        acc_edge<VEC, NS, ISO>(P, R, m, T.s_w, T.EB, i);
+      for (int j = 0; j < cnt; ++j) {
+        const Vec<VEC> m = tile_message<MODE, VEC>(k, T, base + j, e0 + j, qv);
+        acc_edge<VEC, NS, ISO>(P, R, m, T.s_w, T.EB, base + j);
       }
     }
-    if (!single_batch) __syncthreads();                // the next batch overwrites s_src / s_w / s_msg
+    ++rounds;
   }
+  const bool single_batch = rounds <= 1;               // round buffers still hold every slot of the tile
   __syncthreads();                                     // sums complete (and s_coef visible) before the factors
   tile_factors<NS>(k, T);
   __syncthreads();
@@ -659,36 +661,38 @@ __global__ void __launch_bounds__(kMaxTileThreads) agg_bwd_tile_kernel(const __g
   // ---- pass 2: per-edge message gradients ----------------------------------------------------------------
   Vec<VEC> dq = vfill<VEC>(0.f);
   unsigned given = 0u;          // bit i: max gradient of column i already routed; bit 4+i: min
-  for (int b0 = T.E0; b0 < T.E1; b0 += T.EB) {
-    const int nb = min(T.EB, T.E1 - b0);
-    if (!single_batch) tile_batch_begin<MODE, VEC, NS>(k, T, b0, nb, false);   // this batch's rows / weights again
+  for (int r = 0; r < rounds; ++r) {
+    if (!single_batch) {
+      __syncthreads();                                 // previous round's buffers are no longer read
+      tile_round_begin<MODE, VEC, NS>(k, T, r, false); // this round's rows / weights again
+    }
     if (T.active) {
-      const int i0 = max(T.ne0, b0) - b0, i1 = min(T.ne1, b0 + nb) - b0;
+      const int cnt = min(T.EBN, max(0, D - r * T.EBN)), base = T.ln * T.EBN, e0 = T.ne0 + r * T.EBN;
 #pragma unroll 2
-      for (int i = i0; i < i1; ++i) {
-        const int e = b0 + i;
+      for (int j = 0; j < cnt; ++j) {
+        const int e = e0 + j, i = base + j;
         const Vec<VEC> m = tile_message<MODE, VEC>(k, T, i, e, qv);
         Vec<VEC> dm;
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) {
-          float g = fmaf(c1.a[j], m.a[j], c0.a[j]);
+        for (int q = 0; q < VEC; ++q) {
+          float g = fmaf(c1.a[q], m.a[q], c0.a[q]);
           if constexpr (ISO) {
             // torch.max / torch.min send the whole gradient to the FIRST extremal mailbox entry
-            if (m.a[j] == R.mx.a[j] && !(given & (1u << j))) { g += gmx.a[j]; given |= 1u << j; }
-            if (m.a[j] == R.mn.a[j] && !(given & (16u << j))) { g += gmn.a[j]; given |= 16u << j; }
+            if (m.a[q] == R.mx.a[q] && !(given & (1u << q))) { g += gmx.a[q]; given |= 1u << q; }
+            if (m.a[q] == R.mn.a[q] && !(given & (16u << q))) { g += gmn.a[q]; given |= 16u << q; }
           }
-          dm.a[j] = g;
+          dm.a[q] = g;
         }
 #pragma unroll
         for (int s = 0; s < NS; ++s) {
           if (s < P.n_slots) {
             const float w = T.s_w[s * T.EB + i];
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) dm.a[j] = fmaf(w, cs[s].a[j], dm.a[j]);
+            for (int q = 0; q < VEC; ++q) dm.a[q] = fmaf(w, cs[s].a[q], dm.a[q]);
           }
         }
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) dq.a[j] += dm.a[j];
+        for (int q = 0; q < VEC; ++q) dq.a[q] += dm.a[q];
         if (k.edge_ws) vstore<VEC>(k.edge_ws + (size_t)e * P.F + T.c, dm);
         if (k.d_r) {
           const int id = k.in_eid ? __ldg(k.in_eid + e) : e;
@@ -696,7 +700,6 @@ __global__ void __launch_bounds__(kMaxTileThreads) agg_bwd_tile_kernel(const __g
         }
       }
     }
-    if (!single_batch) __syncthreads();
   }
   if (T.active) {
     if (k.d_q) vstore<VEC>(k.d_q + (size_t)T.v * k.ld_dq + T.c, dq);
@@ -734,15 +737,15 @@ static bool make_tile_cfg(const KernelArgs& k, int vec, int NS, bool backward, T
   const double avg_deg = k.N > 0 ? (double)k.E / (double)k.N : 0.0;
   const bool dense_graph = avg_deg >= 16.0 && k.mode != DGN_MSG_DENSE;
   tc.use_msg = rows_bulk_ok && !dense_graph && ((k.mode == DGN_MSG_DENSE) ? (k.ld_r % 4 == 0) : (k.ld_x % 4 == 0));
-  // batch size: enough slots for a typical tile (2x the average), at most 32 KB of message rows
-  int eb_max = tc.use_msg ? (32 * 1024) / row_bytes : 512;
-  eb_max = eb_max / 32 * 32;
-  if (eb_max < 32) eb_max = 32;
-  if (eb_max > 512) eb_max = 512;
-  int eb = ((int)(2.0 * TN * avg_deg) + 31) / 32 * 32;
-  if (eb < 32) eb = 32;
-  if (eb > eb_max) eb = eb_max;
-  tc.EB = eb;
+  // slots per node and round: ~1.5x the average in-degree (power of two, 4..64), bounded so that a round of
+  // message rows stays within 32 KB of shared memory
+  int ebn = 4;
+  while (ebn < 64 && ebn < 1.5 * avg_deg) ebn <<= 1;
+  if (tc.use_msg) {
+    while (ebn > 2 && TN * ebn * row_bytes > 32 * 1024) ebn >>= 1;
+  }
+  tc.EBN = ebn;
+  tc.EB = TN * ebn;
   int off = align_up((TN + 1) * 4, 16);
   tc.off_ev = off;   off += align_up(ns * TN * 4, 16);
   tc.off_zw = off;   off += align_up(ns * TN * 4, 16);
