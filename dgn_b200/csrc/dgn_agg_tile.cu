@@ -737,12 +737,13 @@ static bool make_tile_cfg(const KernelArgs& k, int vec, int NS, bool backward, T
   const double avg_deg = k.N > 0 ? (double)k.E / (double)k.N : 0.0;
   const bool dense_graph = avg_deg >= 16.0 && k.mode != DGN_MSG_DENSE;
   tc.use_msg = rows_bulk_ok && !dense_graph && ((k.mode == DGN_MSG_DENSE) ? (k.ld_r % 4 == 0) : (k.ld_x % 4 == 0));
-  // slots per node and round: ~1.5x the average in-degree (power of two, 4..64), bounded so that a round of
-  // message rows stays within 32 KB of shared memory
+  // slots per node and round: ~2.5x the average in-degree (power of two, 4..64) so that almost every tile is done
+  // in one round, bounded so that a round of message rows stays within 32 KB (64 KB for denser graphs) of smem
   int ebn = 4;
-  while (ebn < 64 && ebn < 1.5 * avg_deg) ebn <<= 1;
+  while (ebn < 64 && ebn < 2.5 * avg_deg) ebn <<= 1;
   if (tc.use_msg) {
-    while (ebn > 2 && TN * ebn * row_bytes > 32 * 1024) ebn >>= 1;
+    const int msg_cap = (avg_deg >= 6.0 ? 64 : 32) * 1024;
+    while (ebn > 2 && TN * ebn * row_bytes > msg_cap) ebn >>= 1;
   }
   tc.EBN = ebn;
   tc.EB = TN * ebn;
