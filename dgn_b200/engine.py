@@ -54,6 +54,7 @@ class TrainStep:
         self.graphed = graphed
         self.node_key, self.edge_key = node_key, edge_key
         self.flat_p, self.flat_g = flatten_parameters(net)
+        ops.SIDE_STREAM_ENABLED = True         # weight-gradient GEMMs become a parallel branch of the step
         self.opt = FlatAdam(self.flat_p, self.flat_g, lr=lr, weight_decay=weight_decay)
         if graphed and not template_graph.padded:
             raise ValueError("graphed=True needs batches padded to a fixed capacity (BatchedGraph(capacity=...))")
@@ -81,6 +82,7 @@ class TrainStep:
         scores = self.net(g, g.ndata[self.node_key], g.edata[self.edge_key], g.snorm_n, None)
         loss = self.net.loss(scores, self.targets)
         loss.backward()
+        ops.side_join(self.dev)               # weight-gradient GEMMs forked onto the side stream are done
         return loss
 
     def _reduce_and_update(self):

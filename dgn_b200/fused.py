@@ -22,7 +22,8 @@ from __future__ import annotations
 import torch
 
 from . import _lib
-from .ops import (agg_backward_raw, agg_forward_raw, gemm, norm_backward_raw, norm_forward_raw, _f32c, _need_cuda)
+from .ops import (agg_backward_raw, agg_forward_raw, gemm, norm_backward_raw, norm_forward_raw, side_queue, _f32c,
+                  _need_cuda)
 
 _ONES = {}
 
@@ -110,9 +111,16 @@ class _FusedLayer(torch.autograd.Function):
 
         # ---- posttrans GEMM --------------------------------------------------------------------------------------------
         d_cat = gemm(d_y, W_post, b_kmajor=False)        # d_y @ W_post
-        # dW_post = d_y^T @ cat, computed as (cat^T @ d_y)^T so the 128-row tile dimension is the wide one
+        # dW_post = d_y^T @ cat, computed as (cat^T @ d_y)^T so the 128-row tile dimension is the wide one.
+        # Weight gradients are off the critical path: with direct accumulation they run on the side stream.
+        side = side_queue(dev) if direct else None
         if direct:
-            gemm(cat, d_y, a_kmajor=False, b_kmajor=False, out=pW_post.grad, accumulate=True, c_transposed=True)
+            def _dw_post():
+                gemm(cat, d_y, a_kmajor=False, b_kmajor=False, out=pW_post.grad, accumulate=True, c_transposed=True)
+            if side is not None:
+                side.run(_dw_post, keep=(cat, d_y))
+            else:
+                _dw_post()
             d_Wpost = None
         else:
             d_Wpost = gemm(cat, d_y, a_kmajor=False, b_kmajor=False, c_transposed=True)
@@ -133,9 +141,16 @@ class _FusedLayer(torch.autograd.Function):
             gemm(d_Q, W_pre[:, Fi:2 * Fi], b_kmajor=False, out=d_h, accumulate=True)      # += d_Q @ W_dst
             if direct:
                 gW = pW_pre.grad
-                gemm(d_P, h, a_kmajor=False, b_kmajor=False, out=gW[:, :Fi], accumulate=True)          # += d_P^T @ h
-                gemm(d_Q, h, a_kmajor=False, b_kmajor=False, out=gW[:, Fi:2 * Fi], accumulate=True)    # += d_Q^T @ h
-                pb_pre.grad.addmv_(d_Q.t(), _ones(N, dev))
+                ones = _ones(N, dev)
+
+                def _dw_pre():
+                    gemm(d_P, h, a_kmajor=False, b_kmajor=False, out=gW[:, :Fi], accumulate=True)          # += d_P^T @ h
+                    gemm(d_Q, h, a_kmajor=False, b_kmajor=False, out=gW[:, Fi:2 * Fi], accumulate=True)    # += d_Q^T @ h
+                    pb_pre.grad.addmv_(d_Q.t(), ones)
+                if side is not None:
+                    side.run(_dw_pre, keep=(d_P, d_Q, h))
+                else:
+                    _dw_pre()
             else:
                 d_Wpre = torch.zeros_like(W_pre)          # columns past 2F (edge features) get theirs via R
                 gemm(d_P, h, a_kmajor=False, b_kmajor=False, out=d_Wpre[:, :Fi])

@@ -365,10 +365,12 @@ GEMM_ENABLED = True          # set False to route every GEMM through the library
 
 
 def _gemm_workspace(device):
-    ws = _GEMM_WS.get(str(device))
+    """Split-K workspace, one per (device, stream): GEMMs on the side stream run concurrently with the main one."""
+    key = (str(device), torch.cuda.current_stream(device).cuda_stream)
+    ws = _GEMM_WS.get(key)
     if ws is None:
         ws = torch.zeros(int(lib.dgn_gemm_ws_floats()), device=device, dtype=torch.float32)
-        _GEMM_WS[str(device)] = ws
+        _GEMM_WS[key] = ws
     return ws
 
 
@@ -407,3 +409,50 @@ def gemm(a, b, a_kmajor=True, b_kmajor=True, out=None, accumulate=False, c_trans
     else:
         torch.mm(A, Bm, out=out)
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# side stream for work that is off the critical path (weight-gradient GEMMs)
+# ---------------------------------------------------------------------------------------------------------
+class _SideQueue:
+    """A second CUDA stream that forks from / joins the current one.  Under CUDA-graph capture the forked work
+    becomes a parallel branch of the graph, so the small critical-path kernels and the weight-gradient GEMMs
+    (only needed by the optimizer at the very end) share the GPU instead of running back to back."""
+
+    def __init__(self, device):
+        self.stream = torch.cuda.Stream(device=device)
+        self.keep, self.dirty = [], False
+
+    def run(self, fn, keep=()):
+        main = torch.cuda.current_stream(self.stream.device)
+        self.stream.wait_stream(main)                 # inputs produced so far on the main stream are ready
+        with torch.cuda.stream(self.stream):
+            fn()
+        self.keep.extend(keep)                        # operands must outlive the forked work: hold them until join()
+        self.dirty = True
+
+    def join(self):
+        if self.dirty:
+            torch.cuda.current_stream(self.stream.device).wait_stream(self.stream)
+            self.keep.clear()
+            self.dirty = False
+
+
+_SIDE = {}
+SIDE_STREAM_ENABLED = False      # engine.TrainStep switches it on; plain autograd use stays single-stream
+
+
+def side_queue(device):
+    if not SIDE_STREAM_ENABLED:
+        return None
+    q = _SIDE.get(str(device))
+    if q is None:
+        q = _SideQueue(device)
+        _SIDE[str(device)] = q
+    return q
+
+
+def side_join(device):
+    q = _SIDE.get(str(device))
+    if q is not None:
+        q.join()
