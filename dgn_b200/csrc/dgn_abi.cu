@@ -159,7 +159,7 @@ extern "C" int dgn_agg_backward(const DgnGraph* g, const DgnAggSpec* spec, const
   if (k.d_h) vec = imin(vec, imin(vwp(k.d_h), vw(k.ld_dh)));
   if (k.d_h_add) vec = imin(vec, imin(vwp(k.d_h_add), vw(k.ld_dha)));
   if (grad->d_x) vec = imin(vec, imin(imin(vwp(grad->d_x), vw(grad->ld_dx)), vwp(grad->edge_ws)));
-  vec = choose_vec(vec, k.N, k.plan.F, false);
+  vec = choose_vec(vec, k.N, k.plan.F, true);
   k.plan.chunks = k.plan.F / vec;
   const int rc = launch_backward(k, vec, grad->d_x, grad->ld_dx, grad->fold_h_in ? grad->d_h_in : nullptr,
                                  grad->ld_dh, (cudaStream_t)stream);

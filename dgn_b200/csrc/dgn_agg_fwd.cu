@@ -215,8 +215,9 @@ int launch_forward(const KernelArgs& k, int vec, cudaStream_t st) {
 int choose_vec(int max_vec, long long n_nodes, int n_feat, bool narrow_small) {
   static const int forced = [] { const char* e = getenv("DGN_FORCE_VEC"); return e ? atoi(e) : 0; }();
   if (forced == 1 || forced == 2 || forced == 4) return forced <= max_vec ? forced : max_vec;
-  // Measured on B200 (profiles/README.md, cfg2 N*F = 190 k): the forward is fastest with 8 B lanes when
-  // 16 B lanes would leave most SMs with a single block; the backward always prefers the widest lanes.
+  // Measured on B200 (profiles/README.md, cfg2 N*F = 190 k): both directions are faster with 8 B lanes when
+  // 16 B lanes would leave most SMs with a single block (fwd 10.9 -> 9.5 us, bwd 19.4 -> 17.0 us); larger launches
+  // always prefer the widest lanes.
   int vec = max_vec;
   if (narrow_small && vec == 4 && n_nodes * n_feat / 4 < 148LL * 512) vec = 2;
   return vec;
