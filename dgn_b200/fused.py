@@ -3,7 +3,7 @@
 ``pretrans_layers == posttrans_layers == 1`` (all five reference configs, rb/configs/*.json) makes a DGN
 layer a fixed chain
 
-    P = h W_src^T, Q = h W_dst^T                         2 GEMMs (node level), dgn_gemm_tf32x3 on tcgen05
+    P = h W_src^T, Q = h W_dst^T                         1 launch (node level), dgn_pair_linear_forward
     cat = [h | scalers(aggregators(P[u] + Q[v] + b))]    dgn_agg_forward      (b fused as q_bias)
     y = cat W_post^T                                     1 GEMM (dgn_gemm_tf32x3)
     out = relu(BN((y + b_post) * snorm_n)) + h           dgn_norm_forward     (b_post fused as y_bias)
@@ -22,8 +22,8 @@ from __future__ import annotations
 import torch
 
 from . import _lib
-from .ops import (agg_backward_raw, agg_forward_raw, gemm, norm_backward_raw, norm_forward_raw, side_queue, _f32c,
-                  _need_cuda)
+from .ops import (agg_backward_raw, agg_forward_raw, gemm, norm_backward_raw, norm_forward_raw, pair_linear_backward,
+                  pair_linear_forward, side_queue, _f32c, _need_cuda)
 
 _ONES = {}
 
@@ -57,8 +57,7 @@ class _FusedLayer(torch.autograd.Function):
         N, dev = h.shape[0], h.device
         P = Q = None
         if cfg.has_pretrans:
-            P = gemm(h, W_pre[:, :Fi])                   # h @ W_src^T  (tcgen05 3xTF32, fp32-accurate)
-            Q = gemm(h, W_pre[:, Fi:2 * Fi])             # h @ W_dst^T
+            P, Q = pair_linear_forward(h, W_pre, Fi)     # h @ W_src^T, h @ W_dst^T in one launch
             cat = torch.empty((N, Fi + spec.out_width), device=dev, dtype=torch.float32)
             agg_forward_raw(g, spec, _lib.MSG_AFFINE, P, Q, R, h, cfg.eig, cat, True, q_bias=b_pre)
         else:                                            # simple layer: message = h[src], no h block
@@ -137,8 +136,7 @@ class _FusedLayer(torch.autograd.Function):
                 d_R = torch.empty((max(E, 1), Fi), device=dev, dtype=torch.float32)[:E]
             agg_backward_raw(g, spec, _lib.MSG_AFFINE, P, Q, R, h, cfg.eig, d_cat, True, d_x=d_P, d_q=d_Q, d_r=d_R,
                              d_h=d_h, edge_ws=ws, q_bias=b_pre, d_h_addend=resid)
-            gemm(d_P, W_pre[:, :Fi], b_kmajor=False, out=d_h, accumulate=True)            # += d_P @ W_src
-            gemm(d_Q, W_pre[:, Fi:2 * Fi], b_kmajor=False, out=d_h, accumulate=True)      # += d_Q @ W_dst
+            pair_linear_backward(d_P, d_Q, W_pre, Fi, d_h)                                   # += d_P W_src + d_Q W_dst
             if direct:
                 gW = pW_pre.grad
                 ones = _ones(N, dev)

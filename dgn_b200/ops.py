@@ -456,3 +456,38 @@ def side_join(device):
     q = _SIDE.get(str(device))
     if q is not None:
         q.join()
+
+
+def pair_linear_forward(h, W, Fi):
+    """``P = h @ W[:, :Fi].T``, ``Q = h @ W[:, Fi:2Fi].T`` in one launch (dgn_pair_linear_forward); library GEMMs
+    when the shape is outside the kernel's range."""
+    N, Fo = h.shape[0], W.shape[0]
+    P = torch.empty((N, Fo), device=h.device, dtype=torch.float32)
+    Q = torch.empty((N, Fo), device=h.device, dtype=torch.float32)
+    rc = -2
+    if N > 0 and h.stride(1) == 1 and W.stride(1) == 1:
+        rc = lib.dgn_pair_linear_forward(N, Fi, Fo, h.data_ptr(), h.stride(0), W.data_ptr(), W.stride(0), P.data_ptr(),
+                                         P.stride(0), Q.data_ptr(), Q.stride(0), _stream(h))
+    if rc == -2:
+        torch.mm(h, W[:, :Fi].t(), out=P)
+        torch.mm(h, W[:, Fi:2 * Fi].t(), out=Q)
+        return P, Q
+    check(rc, "dgn_pair_linear_forward")
+    _count(1)
+    return P, Q
+
+
+def pair_linear_backward(d_P, d_Q, W, Fi, d_h):
+    """``d_h += d_P @ W[:, :Fi] + d_Q @ W[:, Fi:2Fi]`` in one launch (dgn_pair_linear_backward)."""
+    N, Fo = d_P.shape
+    rc = -2
+    if N > 0 and W.stride(1) == 1:
+        rc = lib.dgn_pair_linear_backward(N, Fi, Fo, d_P.data_ptr(), d_P.stride(0), d_Q.data_ptr(), d_Q.stride(0),
+                                          W.data_ptr(), W.stride(0), d_h.data_ptr(), d_h.stride(0), _stream(d_h))
+    if rc == -2:
+        d_h.addmm_(d_P, W[:, :Fi])
+        d_h.addmm_(d_Q, W[:, Fi:2 * Fi])
+        return d_h
+    check(rc, "dgn_pair_linear_backward")
+    _count(1)
+    return d_h

@@ -242,6 +242,17 @@ int dgn_gemm_tf32x3(int32_t M, int32_t N, int32_t K, const float* A, int32_t lda
                     int32_t ldb, int32_t b_kmajor, float* C, int32_t ldc, int32_t accumulate, int32_t c_transposed,
                     float* ws, void* stream);
 
+/* Node-level halves of the 1-layer pretrans (rb/nets/dgn_layer.py:75-80) in one launch each, straight from the
+ * parameter W = [W_src | W_dst | ...] of shape [Fo, ld_w >= 2*Fi]:
+ *   forward : P = h W_src^T, Q = h W_dst^T            (h [N,Fi], P and Q [N,Fo])
+ *   backward: d_h += d_P W_src + d_Q W_dst            (accumulates into d_h [N,Fi])
+ * fp32 FMA on CUDA cores (these K <= 128 products are launch-latency bound).  Fi, Fo <= 128 and multiples of 4,
+ * outputs 16 B aligned, else DGN_ERR_UNSUPPORTED. */
+int dgn_pair_linear_forward(int32_t N, int32_t Fi, int32_t Fo, const float* h, int32_t ld_h, const float* W, int32_t ld_w,
+                            float* P, int32_t ld_p, float* Q, int32_t ld_q, void* stream);
+int dgn_pair_linear_backward(int32_t N, int32_t Fi, int32_t Fo, const float* dP, int32_t ld_p, const float* dQ,
+                             int32_t ld_q, const float* W, int32_t ld_w, float* d_h, int32_t ld_dh, void* stream);
+
 int dgn_readout_forward(int32_t n_graphs, const int32_t* graph_ptr, int32_t n_cols, const float* h, int32_t ld_h,
                         int32_t op, float* out, int32_t ld_o, void* stream);
 /* d_h has n_rows_total rows: rows past graph_ptr[n_graphs] (padding of a fixed-capacity batch) are zeroed. */

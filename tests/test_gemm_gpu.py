@@ -87,3 +87,24 @@ def test_unaligned_shapes_fall_back_to_the_library():
     a, b, ref = _case(50, 45, 1395 // 5 * 5 + 1, True, True)               # K not a multiple of 4
     out = gemm(a, b)
     assert float((out.double() - ref).abs().max()) <= 1e-4 * float(ref.abs().max())
+
+
+@pytest.mark.parametrize("N,Fi,Fo,extra", [(3000, 64, 64, 0), (257, 16, 16, 8), (33, 20, 20, 0), (1000, 128, 128, 4), (5, 48, 48, 0)])
+def test_pair_linear_matches_fp64(N, Fi, Fo, extra):
+    """P = h W_src^T, Q = h W_dst^T and d_h += d_P W_src + d_Q W_dst straight from W = [W_src | W_dst | edge cols]."""
+    from dgn_b200.ops import pair_linear_backward, pair_linear_forward
+    g = torch.Generator(device=DEV).manual_seed(N)
+    h = torch.randn(N, Fi, device=DEV, generator=g)
+    W = torch.randn(Fo, 2 * Fi + extra, device=DEV, generator=g)
+    P, Q = pair_linear_forward(h, W, Fi)
+    assert ops.LAUNCHES == 1
+    refP, refQ = h.double() @ W[:, :Fi].double().t(), h.double() @ W[:, Fi:2 * Fi].double().t()
+    assert float((P.double() - refP).abs().max()) <= 2e-6 * float(refP.abs().max())
+    assert float((Q.double() - refQ).abs().max()) <= 2e-6 * float(refQ.abs().max())
+    dP = torch.randn(N, Fo, device=DEV, generator=g)
+    dQ = torch.randn(N, Fo, device=DEV, generator=g)
+    base = torch.randn(N, Fi, device=DEV, generator=g)
+    dh = base.clone()
+    pair_linear_backward(dP, dQ, W, Fi, dh)
+    ref = base.double() + dP.double() @ W[:, :Fi].double() + dQ.double() @ W[:, Fi:2 * Fi].double()
+    assert float((dh.double() - ref).abs().max()) <= 2e-6 * float(ref.abs().max())
