@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdgn_b200.so")
 
 MAX_AGG, MAX_SCALERS, MAX_SLOTS = 32, 4, 8
-ABI_VERSION = 2
+ABI_VERSION = 3
 NORM_WS_PER_COL = 640
 
 # DgnAggKind / DgnScalerKind / DgnMsgMode
@@ -42,7 +42,12 @@ class DgnAggIO(C.Structure):
                 ("ld_q", C.c_int32), ("q_bias", C.c_void_p), ("r", C.c_void_p), ("ld_r", C.c_int32), ("h_in", C.c_void_p),
                 ("ld_h", C.c_int32), ("eig", C.c_void_p), ("ld_eig", C.c_int32), ("out", C.c_void_p),
                 ("ld_out", C.c_int32), ("out_group_stride", C.c_int32), ("h_copy", C.c_void_p),
-                ("ld_hcopy", C.c_int32), ("hcopy_group_stride", C.c_int32)]
+                ("ld_hcopy", C.c_int32), ("hcopy_group_stride", C.c_int32), ("field", C.c_void_p)]
+
+
+class DgnField(C.Structure):
+    _fields_ = [("n_groups", C.c_int32), ("n_slots", C.c_int32), ("ovf_ptr", C.c_void_p), ("groups", C.c_void_p),
+                ("wsum", C.c_void_p)]
 
 
 class DgnAggGrad(C.Structure):
@@ -76,6 +81,10 @@ SIGNATURES = {
                                    C.POINTER(DgnAggGrad), C.c_void_p]),
     "dgn_build_csr_host": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dgn_field_slots": (C.c_int, [C.POINTER(DgnAggSpec)]),
+    "dgn_build_groups_host": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p]),
+    "dgn_field_build": (C.c_int, [C.POINTER(DgnGraph), C.POINTER(DgnAggSpec), C.c_void_p, C.c_int32,
+                                  C.POINTER(DgnField), C.c_void_p]),
     "dgn_norm_forward": (C.c_int, [C.POINTER(DgnNormArgs), C.c_void_p]),
     "dgn_norm_backward": (C.c_int, [C.POINTER(DgnNormArgs), C.POINTER(DgnNormGrad), C.c_void_p]),
     "dgn_embedding_backward": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,

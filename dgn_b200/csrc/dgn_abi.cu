@@ -131,7 +131,8 @@ extern "C" int dgn_agg_forward(const DgnGraph* g, const DgnAggSpec* spec, const 
   if (int rc = fill_args(g, spec, io, k, vec)) return rc;
   vec = choose_vec(vec, k.N, k.plan.F, true);
   k.plan.chunks = k.plan.F / vec;
-  const int rc = launch_forward(k, vec, (cudaStream_t)stream);
+  const int rc = io->field ? launch_forward_row(k, spec, io->field, vec, (cudaStream_t)stream)
+                           : launch_forward(k, vec, (cudaStream_t)stream);
   if (rc == DGN_ERR_CUDA) g_dgn_last_cuda = cudaPeekAtLastError();
   return rc;
 }
@@ -161,8 +162,16 @@ extern "C" int dgn_agg_backward(const DgnGraph* g, const DgnAggSpec* spec, const
   if (grad->d_x) vec = imin(vec, imin(imin(vwp(grad->d_x), vw(grad->ld_dx)), vwp(grad->edge_ws)));
   vec = choose_vec(vec, k.N, k.plan.F, true);
   k.plan.chunks = k.plan.F / vec;
-  const int rc = launch_backward(k, vec, grad->d_x, grad->ld_dx, grad->fold_h_in ? grad->d_h_in : nullptr,
-                                 grad->ld_dh, (cudaStream_t)stream);
+  int rc;
+  if (io->field) {
+    rc = launch_backward_row_dst(k, spec, io->field, vec, (cudaStream_t)stream);
+    if (rc == DGN_OK && grad->d_x)
+      rc = launch_backward_src(k, vec, grad->d_x, grad->ld_dx, grad->fold_h_in ? grad->d_h_in : nullptr, grad->ld_dh,
+                               (cudaStream_t)stream);
+  } else {
+    rc = launch_backward(k, vec, grad->d_x, grad->ld_dx, grad->fold_h_in ? grad->d_h_in : nullptr, grad->ld_dh,
+                         (cudaStream_t)stream);
+  }
   if (rc == DGN_ERR_CUDA) g_dgn_last_cuda = cudaPeekAtLastError();
   return rc;
 }

@@ -294,6 +294,12 @@ int launch_backward(const KernelArgs& k, int vec, float* d_x, int ld_dx, const f
   if (rc == DGN_ERR_UNSUPPORTED)
     rc = vec == 4 ? dispatch_mode<4>(k, iso, st) : vec == 2 ? dispatch_mode<2>(k, iso, st) : dispatch_mode<1>(k, iso, st);
   if (rc != DGN_OK || !d_x) return rc;
+  return launch_backward_src(k, vec, d_x, ld_dx, addend, ld_add, st);
+}
+
+// d_x = (addend) + source-side gather of the per-edge message gradients in edge_ws
+int launch_backward_src(const KernelArgs& k, int vec, float* d_x, int ld_dx, const float* addend, int ld_add,
+                        cudaStream_t st) {
   const long long threads = (long long)k.N * k.plan.chunks;
   if (threads == 0) return DGN_OK;
   const int block = 256;

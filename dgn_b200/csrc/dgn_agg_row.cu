@@ -1,0 +1,731 @@
+// Fused DGN aggregation over a precomputed eigen-field (sm_100a): dgn_field_build + the "row" kernels.
+//
+// The eigenvector weights of an edge, w_s(u->v) (rb/nets/aggregators.py:35-71), depend on the graph and on
+// ndata['eig'] only - not on the layer, not on the feature column.  A DGN net calls its L layers (forward and
+// backward: 2L launches) on the SAME batch, so the weights are computed once per batch by dgn_field_build,
+// already divided by their per-node normaliser, and laid out for 128-bit loads:
+//
+//   group g = 4 consecutive in-edge slots of one destination node:  [ int32 src[4] | float w_0[4] | ... | w_{ns-1}[4] ]
+//   node v owns group v (its first 4 in-edges; src = -1 pads) - no pointer chase for molecules (degree <= 4) -
+//   and the overflow groups N + ovf_ptr[v] .. N + ovf_ptr[v+1] (degree > 4: superpixel kNN, SBM PATTERN).
+//   wsum[s][v] = sum_u w_s(u->v), the factor of h_in in the dx aggregators.
+//
+// With that, a (node, column chunk) thread's dependent chain is group -> message rows -> stores: no in_ptr ->
+// in_src -> eig[u] chain, no per-launch abs / relu / exp / division, no shared memory, no block barrier.  The
+// kernels keep everything in registers, issue the 4 row gathers of a group back to back and write / read the
+// wide [N, S*A*F] operand with streaming 128-bit accesses.  The aggregator list is compiled into a short
+// op table (isotropic first, then slot by slot) so that every accumulator keeps a static register name.
+#include <stdlib.h>
+
+#include "dgn_plan.cuh"
+
+extern thread_local cudaError_t g_dgn_last_cuda;
+
+namespace dgn {
+
+// ------------------------------------------------------------------------------------------------------
+// plans
+// ------------------------------------------------------------------------------------------------------
+enum FieldKind : int {
+  FW_ABS = 0,   // |d| / (sum |d| + eps)                         dir-av
+  FW_SGN = 1,   // d / (sum |d| + eps)                           dir-dx, dir-dx-no-abs
+  FW_BAL = 2,   // (relu(d)/(sum relu(d)+eps) + relu(-d)/(sum relu(-d)+eps)) / 2     dir-dx-balanced
+  FW_SOFT = 3   // softmax_u(alpha |d|)                          dirK-0.1 / dirK-neg-0.1
+};
+
+enum RowOp : int { OP_WSUM = 0, OP_DX = 1, OP_DX_ABS = 2 };   // directional: sum w m ; sum w m - W h ; |sum w m - W h|
+
+struct FieldPlan {
+  int n_slots;
+  int eig[DGN_MAX_SLOTS];
+  int kind[DGN_MAX_SLOTS];
+  float alpha[DGN_MAX_SLOTS];
+};
+
+struct RowPlan {
+  int F, Fg, A, S, n_slots;
+  int n_iso;                          // order[0, n_iso): isotropic aggregators
+  int slot_end[DGN_MAX_SLOTS];        // order[slot_end[s-1], slot_end[s]) read slot s
+  uint8_t order[DGN_MAX_AGG];         // aggregator index (output block) of every position
+  uint8_t op[DGN_MAX_AGG];            // by position: DgnAggKind (isotropic) or RowOp (directional)
+  uint8_t scaler_kind[DGN_MAX_SCALERS];
+  float avg_log;
+};
+
+struct RowArgs {
+  RowPlan rp;
+  int N, mode, gstride;               // gstride = 1 + n_slots (float4 per group)
+  const int32_t* in_ptr;
+  const int32_t* in_eid;
+  const int32_t* ovf_ptr;
+  const float4* groups;
+  const float* wsum;
+  const float* log_deg;
+  const float* x; int ld_x;
+  const float* q; int ld_q;
+  const float* q_bias;
+  const float* r; int ld_r;
+  const float* h_in; int ld_h;
+  float* out; int ld_out; int out_gs;
+  float* h_copy; int ld_hc; int hc_gs;
+  const float* g_out;
+  const float* g_hcopy;
+  float* d_q; int ld_dq;
+  float* d_r; int ld_dr;
+  float* d_h; int ld_dh;
+  const float* d_h_add; int ld_dha;
+  float* edge_ws;
+};
+
+static int field_slot(FieldPlan& f, int eig, int kind, float alpha) {
+  for (int s = 0; s < f.n_slots; ++s)
+    if (f.eig[s] == eig && f.kind[s] == kind && (kind != FW_SOFT || f.alpha[s] == alpha)) return s;
+  if (f.n_slots >= DGN_MAX_SLOTS) return -1;
+  const int s = f.n_slots++;
+  f.eig[s] = eig; f.kind[s] = kind; f.alpha[s] = alpha;
+  return s;
+}
+
+// spec -> slots (FieldPlan) and op table (RowPlan).  Both the field builder and the kernels derive the slot
+// numbering from here, so a field built for one spec serves every spec with the same directional aggregators.
+int make_row_plan(const DgnAggSpec* spec, FieldPlan& fp, RowPlan* rp) {
+  memset(&fp, 0, sizeof(fp));
+  if (spec->n_feat <= 0 || spec->n_agg <= 0 || spec->n_agg > DGN_MAX_AGG || spec->n_scalers <= 0 ||
+      spec->n_scalers > DGN_MAX_SCALERS || spec->n_eig < 0)
+    return DGN_ERR_INVALID;
+  int slot_of[DGN_MAX_AGG], op_of[DGN_MAX_AGG];
+  for (int a = 0; a < spec->n_agg; ++a) {
+    const int kind = spec->agg_kind[a], eig = spec->agg_eig[a];
+    slot_of[a] = -1; op_of[a] = kind;
+    if (kind > DGN_AGG_DIR_SOFTMAX) return DGN_ERR_INVALID;
+    if (kind < DGN_AGG_DIR_AV) continue;
+    if (eig >= spec->n_eig) return DGN_ERR_INVALID;
+    switch (kind) {
+      case DGN_AGG_DIR_AV: slot_of[a] = field_slot(fp, eig, FW_ABS, 0.f); op_of[a] = OP_WSUM; break;
+      case DGN_AGG_DIR_DX: slot_of[a] = field_slot(fp, eig, FW_SGN, 0.f); op_of[a] = OP_DX_ABS; break;
+      case DGN_AGG_DIR_DX_NO_ABS: slot_of[a] = field_slot(fp, eig, FW_SGN, 0.f); op_of[a] = OP_DX; break;
+      case DGN_AGG_DIR_DX_BALANCED: slot_of[a] = field_slot(fp, eig, FW_BAL, 0.f); op_of[a] = OP_DX_ABS; break;
+      default: slot_of[a] = field_slot(fp, eig, FW_SOFT, spec->agg_alpha[a]); op_of[a] = OP_WSUM; break;
+    }
+    if (slot_of[a] < 0) return DGN_ERR_UNSUPPORTED;
+  }
+  if (!rp) return DGN_OK;
+  memset(rp, 0, sizeof(*rp));
+  rp->F = spec->n_feat;
+  rp->Fg = spec->group_feat > 0 ? spec->group_feat : spec->n_feat;
+  if (rp->F % rp->Fg != 0) return DGN_ERR_INVALID;
+  rp->A = spec->n_agg;
+  rp->S = spec->n_scalers > 1 ? spec->n_scalers : 1;     // rb/nets/dgn_layer.py:95
+  rp->avg_log = spec->avg_log;
+  rp->n_slots = fp.n_slots;
+  for (int s = 0; s < spec->n_scalers; ++s) {
+    if (spec->scaler_kind[s] > DGN_SCALE_ATTENUATION) return DGN_ERR_INVALID;
+    rp->scaler_kind[s] = spec->scaler_kind[s];
+  }
+  int n = 0;
+  for (int a = 0; a < rp->A; ++a)
+    if (slot_of[a] < 0) { rp->order[n] = (uint8_t)a; rp->op[n] = (uint8_t)op_of[a]; ++n; }
+  rp->n_iso = n;
+  for (int s = 0; s < DGN_MAX_SLOTS; ++s) {
+    for (int a = 0; a < rp->A; ++a)
+      if (slot_of[a] == s) { rp->order[n] = (uint8_t)a; rp->op[n] = (uint8_t)op_of[a]; ++n; }
+    rp->slot_end[s] = n;
+  }
+  return DGN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// dgn_field_build: thread = (node, slot)
+// ------------------------------------------------------------------------------------------------------
+struct FieldArgs {
+  FieldPlan fp;
+  int N;
+  const int32_t* in_ptr;
+  const int32_t* in_src;
+  const int32_t* ovf_ptr;
+  const float* eig; int ld_eig;
+  float* groups;                       // viewed as floats: group g, row r (0 = sources), lane l -> (g*gstride + r)*4 + l
+  float* wsum;
+};
+
+__global__ void __launch_bounds__(256) field_build_kernel(const __grid_constant__ FieldArgs k) {
+  const int ns = k.fp.n_slots, lanes = ns > 0 ? ns : 1, gstride = 1 + ns;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int v = (int)(t / lanes), s = (int)(t - (long long)v * lanes);
+  if (v >= k.N) return;
+  const int e0 = __ldg(k.in_ptr + v), e1 = __ldg(k.in_ptr + v + 1), D = e1 - e0;
+  const int ovf0 = __ldg(k.ovf_ptr + v);
+  auto group_of = [&](int j) { return j < 4 ? v : k.N + ovf0 + ((j - 4) >> 2); };
+  const int n_groups_v = D <= 4 ? 1 : 1 + ((D - 4 + 3) >> 2);
+  if (s == 0) {                                   // padded source lists
+    for (int j = 0; j < 4 * n_groups_v; ++j) {
+      const int u = j < D ? __ldg(k.in_src + e0 + j) : -1;
+      reinterpret_cast<int*>(k.groups)[((size_t)group_of(j) * gstride) * 4 + (j & 3)] = u;
+    }
+  }
+  if (ns == 0) return;
+  const int col = k.fp.eig[s], kind = k.fp.kind[s];
+  const float alpha = k.fp.alpha[s];
+  const float ev = __ldg(k.eig + (size_t)v * k.ld_eig + col);
+  // pass 1: the per-node normalisers, summed in mailbox (edge-id) order
+  float z0 = 0.f, z1 = 0.f, mx = -INFINITY;
+  for (int e = e0; e < e1; ++e) {
+    const float d = __ldg(k.eig + (size_t)__ldg(k.in_src + e) * k.ld_eig + col) - ev;
+    if (kind == FW_BAL) { z0 += fmaxf(d, 0.f); z1 += fmaxf(-d, 0.f); }
+    else if (kind == FW_SOFT) mx = fmaxf(mx, alpha * fabsf(d));
+    else z0 += fabsf(d);
+  }
+  if (kind == FW_SOFT) {
+    for (int e = e0; e < e1; ++e) {
+      const float d = __ldg(k.eig + (size_t)__ldg(k.in_src + e) * k.ld_eig + col) - ev;
+      z0 += expf(alpha * fabsf(d) - mx);
+    }
+  } else {
+    z0 += DGN_EPS; z1 += DGN_EPS;
+  }
+  // pass 2: normalised weights into the group lanes (IEEE division, like the reference's tensor division)
+  float ws = 0.f;
+  for (int j = 0; j < 4 * n_groups_v; ++j) {
+    float w = 0.f;
+    if (j < D) {
+      const float d = __ldg(k.eig + (size_t)__ldg(k.in_src + e0 + j) * k.ld_eig + col) - ev;
+      switch (kind) {
+        case FW_ABS: w = __fdiv_rn(fabsf(d), z0); break;
+        case FW_SGN: w = __fdiv_rn(d, z0); break;
+        case FW_BAL: w = __fdiv_rn(__fadd_rn(__fdiv_rn(fmaxf(d, 0.f), z0), __fdiv_rn(fmaxf(-d, 0.f), z1)), 2.f); break;
+        default: w = __fdiv_rn(expf(alpha * fabsf(d) - mx), z0); break;
+      }
+      ws += w;
+    }
+    k.groups[((size_t)group_of(j) * gstride + 1 + s) * 4 + (j & 3)] = w;
+  }
+  k.wsum[(size_t)s * k.N + v] = ws;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------------------
+template <int VEC, int NS, bool ISO>
+struct Acc {
+  Vec<VEC> sum;
+  Vec<VEC> sq, mx, mn;                 // only maintained when ISO
+  Vec<VEC> w[NS > 0 ? NS : 1];
+};
+
+template <int VEC, int NS, bool ISO>
+__device__ __forceinline__ void acc_clear(Acc<VEC, NS, ISO>& R) {
+  R.sum = vfill<VEC>(0.f);
+  R.sq = vfill<VEC>(0.f);
+  R.mx = vfill<VEC>(-INFINITY);
+  R.mn = vfill<VEC>(INFINITY);
+#pragma unroll
+  for (int s = 0; s < (NS > 0 ? NS : 1); ++s) R.w[s] = vfill<VEC>(0.f);
+}
+
+__device__ __forceinline__ float lane_of(const float4& f, int j) { return j == 0 ? f.x : j == 1 ? f.y : j == 2 ? f.z : f.w; }
+__device__ __forceinline__ int lane_of(const int4& f, int j) { return j == 0 ? f.x : j == 1 ? f.y : j == 2 ? f.z : f.w; }
+
+// x / D for a small positive integer D given rD = RN(1/D): one Newton step on the residual gives the correctly
+// rounded quotient (Markstein), i.e. the value of the reference's true division, in 3 instructions.
+__device__ __forceinline__ float div_by(float x, float fD, float rD) {
+  const float q = x * rD;
+  return fmaf(fmaf(-q, fD, x), rD, q);
+}
+
+// Walks the in-edge groups of node v: the node-aligned first group, then its overflow groups.  fn(jg, m, wts) is
+// called for every real in-edge in mailbox order with its message (this thread's columns) and slot weights.
+template <int MODE, int VEC, int NS, typename Fn>
+__device__ __forceinline__ void walk_groups(const RowArgs& k, int v, int c, const Vec<VEC>& qv, int e0, int ovf0, int ovf1,
+                                            Fn&& fn) {
+  constexpr int NSA = NS > 0 ? NS : 1;
+  const bool need_eid = (MODE == DGN_MSG_DENSE) || (MODE == DGN_MSG_AFFINE && k.r != nullptr);
+  int g = v, o = ovf0, jbase = 0;
+  while (true) {
+    const float4* gp = k.groups + (size_t)g * k.gstride;
+    const int4 su = __ldg(reinterpret_cast<const int4*>(gp));
+    float4 wv[NSA];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) wv[s] = (s < k.rp.n_slots) ? __ldg(gp + 1 + s) : make_float4(0.f, 0.f, 0.f, 0.f);
+    Vec<VEC> m[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {                 // the 4 gathers of the group are issued back to back
+      const int u = lane_of(su, j);
+      if constexpr (MODE == DGN_MSG_DENSE) {
+        int id = e0 + jbase + j;
+        if (k.in_eid && u >= 0) id = __ldg(k.in_eid + id);
+        m[j] = vload<VEC>(k.r + (size_t)(u >= 0 ? id : 0) * k.ld_r + c);
+      } else {
+        m[j] = vload<VEC>(k.x + (size_t)max(u, 0) * k.ld_x + c);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (lane_of(su, j) >= 0) {
+        Vec<VEC> mm = m[j];
+        if constexpr (MODE == DGN_MSG_AFFINE) {
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) mm.a[i] += qv.a[i];
+          if (need_eid) {
+            const int e = e0 + jbase + j;
+            const int id = k.in_eid ? __ldg(k.in_eid + e) : e;
+            const Vec<VEC> rv = vload<VEC>(k.r + (size_t)id * k.ld_r + c);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) mm.a[i] += rv.a[i];
+          }
+        }
+        float wj[NSA];
+#pragma unroll
+        for (int s = 0; s < NSA; ++s) wj[s] = lane_of(wv[s], j);
+        fn(jbase + j, mm, wj);
+      }
+    }
+    if (o >= ovf1) break;
+    g = k.N + o;
+    ++o;
+    jbase += 4;
+  }
+}
+
+template <int VEC, int NS, bool ISO>
+__device__ __forceinline__ void acc_add(Acc<VEC, NS, ISO>& R, const Vec<VEC>& m, const float* wj) {
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    R.sum.a[i] += m.a[i];
+    if constexpr (ISO) {
+      R.sq.a[i] = __fadd_rn(R.sq.a[i], __fmul_rn(m.a[i], m.a[i]));     // square, round, then sum (as the reference)
+      R.mx.a[i] = fmaxf(R.mx.a[i], m.a[i]);
+      R.mn.a[i] = fminf(R.mn.a[i], m.a[i]);
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) R.w[s].a[i] = fmaf(wj[s], m.a[i], R.w[s].a[i]);
+  }
+}
+
+__device__ __forceinline__ void row_scaler_coefs(const RowPlan& P, float ld, float (&coef)[DGN_MAX_SCALERS]) {
+#pragma unroll
+  for (int s = 0; s < DGN_MAX_SCALERS; ++s) {
+    float cf = 1.f;
+    if (s < P.S && P.S > 1) {
+      const int kind = P.scaler_kind[s];
+      cf = (kind == DGN_SCALE_AMPLIFICATION) ? __fdiv_rn(ld, P.avg_log)
+           : (kind == DGN_SCALE_ATTENUATION) ? __fdiv_rn(P.avg_log, ld) : 1.f;
+    }
+    coef[s] = cf;
+  }
+}
+
+template <int VEC, bool ISO>
+__device__ __forceinline__ void row_mean_var(const Vec<VEC>& sum, const Vec<VEC>& sq, float fD, float rD, Vec<VEC>& mean,
+                                             Vec<VEC>& var) {
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    mean.a[i] = div_by(sum.a[i], fD, rD);
+    if constexpr (ISO) {
+      const float msq = div_by(sq.a[i], fD, rD);
+      var.a[i] = fmaxf(__fsub_rn(msq, __fmul_rn(mean.a[i], mean.a[i])), 0.f);
+    } else {
+      var.a[i] = 0.f;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------------
+// SS = number of scalers known at compile time (0 = runtime P.S)
+template <int VEC, int NS, bool ISO, int SS>
+__device__ __forceinline__ void fwd_epilogue(const RowPlan& P, const Acc<VEC, NS, ISO>& R, const Vec<VEC>& hv,
+                                             const float* wsumv, int D, float ld, float* __restrict__ orow) {
+  const int S = SS > 0 ? SS : P.S;
+  float coef[DGN_MAX_SCALERS];
+  row_scaler_coefs(P, ld, coef);
+  const float fD = (float)D, rD = __frcp_rn(fD);
+  Vec<VEC> mean, var;
+  row_mean_var<VEC, ISO>(R.sum, R.sq, fD, rD, mean, var);
+  const int scaler_stride = P.A * P.Fg;
+  auto store_scaled = [&](int a, const Vec<VEC>& y) {
+    float* dst = orow + a * P.Fg;
+#pragma unroll
+    for (int s = 0; s < DGN_MAX_SCALERS; ++s) {
+      if (s < S) {
+        Vec<VEC> o;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) o.a[i] = y.a[i] * coef[s];
+        vstore_stream<VEC>(dst + s * scaler_stride, o);
+      }
+    }
+  };
+  int pos = 0;
+  for (; pos < P.n_iso; ++pos) {
+    Vec<VEC> y;
+    switch (P.op[pos]) {
+      case DGN_AGG_MEAN: y = mean; break;
+      case DGN_AGG_SUM: y = R.sum; break;
+      case DGN_AGG_MAX: y = ISO ? R.mx : mean; break;
+      case DGN_AGG_MIN: y = ISO ? R.mn : mean; break;
+      case DGN_AGG_VAR: y = var; break;
+      default:
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) y.a[i] = sqrtf(var.a[i] + DGN_EPS);
+    }
+    store_scaled(P.order[pos], y);
+  }
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    const int end = P.slot_end[s];
+    for (; pos < end; ++pos) {
+      const int op = P.op[pos];
+      Vec<VEC> y = R.w[s];
+      if (op != OP_WSUM) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+          const float sv = y.a[i] - wsumv[s] * hv.a[i];
+          y.a[i] = (op == OP_DX_ABS) ? fabsf(sv) : sv;
+        }
+      }
+      store_scaled(P.order[pos], y);
+    }
+  }
+}
+
+template <int MODE, int VEC, int NS, bool ISO>
+__global__ void __launch_bounds__(256) agg_fwd_row_kernel(const __grid_constant__ RowArgs k) {
+  constexpr int NSA = NS > 0 ? NS : 1;
+  const RowPlan& P = k.rp;
+  const int v = blockIdx.x * blockDim.y + threadIdx.y;
+  if (v >= k.N) return;
+  const int c = threadIdx.x * VEC;
+  int tower = 0, cg = c;
+  if (P.Fg != P.F) { tower = c / P.Fg; cg = c - tower * P.Fg; }
+
+  // everything that does not depend on the in-edges is requested first
+  const int ovf0 = __ldg(k.ovf_ptr + v), ovf1 = __ldg(k.ovf_ptr + v + 1);
+  const bool need_e0 = (MODE == DGN_MSG_DENSE) || (MODE == DGN_MSG_AFFINE && k.r != nullptr);
+  const int e0 = need_e0 ? __ldg(k.in_ptr + v) : 0;
+  const Vec<VEC> hv = vload<VEC>(k.h_in + (size_t)v * k.ld_h + c);
+  Vec<VEC> qv = vfill<VEC>(0.f);
+  if constexpr (MODE == DGN_MSG_AFFINE) {
+    qv = vload<VEC>(k.q + (size_t)v * k.ld_q + c);
+    if (k.q_bias) {
+      const Vec<VEC> bv = vload<VEC>(k.q_bias + c);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) qv.a[i] += bv.a[i];
+    }
+  }
+  const float ld = (P.S > 1) ? __ldg(k.log_deg + v) : 1.f;
+  float wsumv[NSA];
+#pragma unroll
+  for (int s = 0; s < NSA; ++s) wsumv[s] = (s < P.n_slots) ? __ldg(k.wsum + (size_t)s * k.N + v) : 0.f;
+  if (k.h_copy) vstore<VEC>(k.h_copy + (size_t)v * k.ld_hc + (size_t)tower * k.hc_gs + cg, hv);
+
+  Acc<VEC, NS, ISO> R;
+  acc_clear(R);
+  int D = 0;
+  walk_groups<MODE, VEC, NS>(k, v, c, qv, e0, ovf0, ovf1, [&](int, const Vec<VEC>& m, const float* wj) {
+    ++D;
+    acc_add<VEC, NS, ISO>(R, m, wj);
+  });
+
+  float* orow = k.out + (size_t)v * k.ld_out + (size_t)tower * k.out_gs + cg;
+  if (D == 0) {                                        // DGL: zero rows for isolated nodes
+    const Vec<VEC> z = vfill<VEC>(0.f);
+    for (int j = 0; j < P.S * P.A; ++j) vstore_stream<VEC>(orow + (size_t)j * P.Fg, z);
+    return;
+  }
+  if (P.S == 3) fwd_epilogue<VEC, NS, ISO, 3>(P, R, hv, wsumv, D, ld, orow);
+  else if (P.S == 1) fwd_epilogue<VEC, NS, ISO, 1>(P, R, hv, wsumv, D, ld, orow);
+  else fwd_epilogue<VEC, NS, ISO, 0>(P, R, hv, wsumv, D, ld, orow);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// backward, destination side (the source-side gather stays agg_bwd_src_kernel)
+// ------------------------------------------------------------------------------------------------------
+template <int VEC, int SS>
+__device__ __forceinline__ void load_slabs(const float* __restrict__ grow, int a, int Fg, int scaler_stride, int S,
+                                           Vec<VEC> (&g)[DGN_MAX_SCALERS]) {
+#pragma unroll
+  for (int s = 0; s < DGN_MAX_SCALERS; ++s)
+    if (s < (SS > 0 ? SS : S)) g[s] = vload_stream<VEC>(grow + a * Fg + s * scaler_stride);
+}
+
+template <int VEC, int NS, bool ISO, int SS>
+__device__ __forceinline__ void bwd_fold(const RowPlan& P, const Acc<VEC, NS, ISO>& R, const Vec<VEC>& hv, const float* wsumv,
+                                         int D, float ld, const float* __restrict__ grow, Vec<VEC>& c0, Vec<VEC>& c1,
+                                         Vec<VEC>& gmx, Vec<VEC>& gmn, Vec<VEC> (&cs)[NS > 0 ? NS : 1], Vec<VEC>& dh) {
+  const int S = SS > 0 ? SS : P.S;
+  float coef[DGN_MAX_SCALERS];
+  row_scaler_coefs(P, ld, coef);
+  const float fD = (float)D, rD = __frcp_rn(fD);
+  Vec<VEC> mean, var;
+  row_mean_var<VEC, ISO>(R.sum, R.sq, fD, rD, mean, var);
+  const int scaler_stride = P.A * P.Fg;
+  // software pipeline over the op table: the slabs of the next aggregator are in flight while this one is folded
+  Vec<VEC> gnext[DGN_MAX_SCALERS], gcur[DGN_MAX_SCALERS];
+  load_slabs<VEC, SS>(grow, P.order[0], P.Fg, scaler_stride, S, gnext);
+  auto next_G = [&](int pos) {
+#pragma unroll
+    for (int s = 0; s < DGN_MAX_SCALERS; ++s) gcur[s] = gnext[s];
+    if (pos + 1 < P.A) load_slabs<VEC, SS>(grow, P.order[pos + 1], P.Fg, scaler_stride, S, gnext);
+    Vec<VEC> G = vfill<VEC>(0.f);
+#pragma unroll
+    for (int s = 0; s < DGN_MAX_SCALERS; ++s) {
+      if (s < S) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) G.a[i] = fmaf(coef[s], gcur[s].a[i], G.a[i]);
+      }
+    }
+    return G;
+  };
+  int pos = 0;
+  for (; pos < P.n_iso; ++pos) {
+    const int kind = P.op[pos];
+    const Vec<VEC> G = next_G(pos);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      if (kind == DGN_AGG_MEAN) c0.a[i] += G.a[i] * rD;
+      else if (kind == DGN_AGG_SUM) c0.a[i] += G.a[i];
+      else if (kind == DGN_AGG_MAX) gmx.a[i] += G.a[i];
+      else if (kind == DGN_AGG_MIN) gmn.a[i] += G.a[i];
+      else {
+        // var = relu(t), t = E[m^2] - E[m]^2 ; dt/dm_u = 2 (m_u - mean) / D ; relu'(0) = 0
+        float gv = (var.a[i] > 0.f) ? G.a[i] : 0.f;
+        if (kind == DGN_AGG_STD) gv *= 0.5f * rsqrtf(var.a[i] + DGN_EPS);
+        const float two_over_d = 2.f * gv * rD;
+        c1.a[i] += two_over_d;
+        c0.a[i] -= two_over_d * mean.a[i];
+      }
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    const int end = P.slot_end[s];
+    for (; pos < end; ++pos) {
+      const int op = P.op[pos];
+      Vec<VEC> G = next_G(pos);
+      if (op != OP_WSUM) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+          if (op == OP_DX_ABS) G.a[i] *= sign0(R.w[s].a[i] - wsumv[s] * hv.a[i]);     // same expression as the forward
+          dh.a[i] -= wsumv[s] * G.a[i];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) cs[s].a[i] += G.a[i];
+    }
+  }
+}
+
+template <int MODE, int VEC, int NS, bool ISO>
+__global__ void __launch_bounds__(256) agg_bwd_row_kernel(const __grid_constant__ RowArgs k) {
+  constexpr int NSA = NS > 0 ? NS : 1;
+  const RowPlan& P = k.rp;
+  const int v = blockIdx.x * blockDim.y + threadIdx.y;
+  if (v >= k.N) return;
+  const int c = threadIdx.x * VEC;
+  int tower = 0, cg = c;
+  if (P.Fg != P.F) { tower = c / P.Fg; cg = c - tower * P.Fg; }
+
+  const int ovf0 = __ldg(k.ovf_ptr + v), ovf1 = __ldg(k.ovf_ptr + v + 1);
+  const int e0 = __ldg(k.in_ptr + v);
+  const Vec<VEC> hv = vload<VEC>(k.h_in + (size_t)v * k.ld_h + c);
+  Vec<VEC> qv = vfill<VEC>(0.f);
+  if constexpr (MODE == DGN_MSG_AFFINE) {
+    qv = vload<VEC>(k.q + (size_t)v * k.ld_q + c);
+    if (k.q_bias) {
+      const Vec<VEC> bv = vload<VEC>(k.q_bias + c);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) qv.a[i] += bv.a[i];
+    }
+  }
+  const float ld = (P.S > 1) ? __ldg(k.log_deg + v) : 1.f;
+  float wsumv[NSA];
+#pragma unroll
+  for (int s = 0; s < NSA; ++s) wsumv[s] = (s < P.n_slots) ? __ldg(k.wsum + (size_t)s * k.N + v) : 0.f;
+  Vec<VEC> dh = vfill<VEC>(0.f);
+  if (k.g_hcopy) dh = vload_stream<VEC>(k.g_hcopy + (size_t)v * k.ld_hc + (size_t)tower * k.hc_gs + cg);
+  if (k.d_h_add) {
+    const Vec<VEC> t = vload_stream<VEC>(k.d_h_add + (size_t)v * k.ld_dha + c);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) dh.a[i] += t.a[i];
+  }
+
+  // ---- pass 1: recompute the row statistics ------------------------------------------------------------
+  Acc<VEC, NS, ISO> R;
+  acc_clear(R);
+  int D = 0;
+  walk_groups<MODE, VEC, NS>(k, v, c, qv, e0, ovf0, ovf1, [&](int, const Vec<VEC>& m, const float* wj) {
+    ++D;
+    acc_add<VEC, NS, ISO>(R, m, wj);
+  });
+
+  Vec<VEC> dq = vfill<VEC>(0.f);
+  if (D > 0) {
+    // ---- fold the S*A gradient slabs into per-column coefficients -------------------------------------
+    Vec<VEC> c0 = vfill<VEC>(0.f), c1 = vfill<VEC>(0.f), gmx = vfill<VEC>(0.f), gmn = vfill<VEC>(0.f);
+    Vec<VEC> cs[NSA];
+#pragma unroll
+    for (int s = 0; s < NSA; ++s) cs[s] = vfill<VEC>(0.f);
+    const float* grow = k.g_out + (size_t)v * k.ld_out + (size_t)tower * k.out_gs + cg;
+    if (P.S == 3) bwd_fold<VEC, NS, ISO, 3>(P, R, hv, wsumv, D, ld, grow, c0, c1, gmx, gmn, cs, dh);
+    else if (P.S == 1) bwd_fold<VEC, NS, ISO, 1>(P, R, hv, wsumv, D, ld, grow, c0, c1, gmx, gmn, cs, dh);
+    else bwd_fold<VEC, NS, ISO, 0>(P, R, hv, wsumv, D, ld, grow, c0, c1, gmx, gmn, cs, dh);
+
+    // ---- pass 2: per-edge message gradients (rows and weights come back from L1 / L2) -------------------
+    unsigned given = 0u;          // bit i: max gradient of column i already routed; bit VEC+i: min
+    walk_groups<MODE, VEC, NS>(k, v, c, qv, e0, ovf0, ovf1, [&](int jg, const Vec<VEC>& m, const float* wj) {
+      Vec<VEC> dm;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        float g = fmaf(c1.a[i], m.a[i], c0.a[i]);
+        if constexpr (ISO) {
+          // torch.max / torch.min send the whole gradient to the FIRST extremal mailbox entry
+          if (m.a[i] == R.mx.a[i] && !(given & (1u << i))) { g += gmx.a[i]; given |= 1u << i; }
+          if (m.a[i] == R.mn.a[i] && !(given & (16u << i))) { g += gmn.a[i]; given |= 16u << i; }
+        }
+        dm.a[i] = g;
+      }
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) dm.a[i] = fmaf(wj[s], cs[s].a[i], dm.a[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) dq.a[i] += dm.a[i];
+      const int e = e0 + jg;
+      if (k.edge_ws) vstore<VEC>(k.edge_ws + (size_t)e * P.F + c, dm);
+      if (k.d_r) {
+        const int id = k.in_eid ? __ldg(k.in_eid + e) : e;
+        vstore<VEC>(k.d_r + (size_t)id * k.ld_dr + c, dm);
+      }
+    });
+  }
+  if (k.d_q) vstore<VEC>(k.d_q + (size_t)v * k.ld_dq + c, dq);
+  if (k.d_h) vstore<VEC>(k.d_h + (size_t)v * k.ld_dh + c, dh);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------
+static bool row_needs_iso(const RowPlan& P) {
+  for (int i = 0; i < P.n_iso; ++i) {
+    const int kd = P.op[i];
+    if (kd == DGN_AGG_MAX || kd == DGN_AGG_MIN || kd == DGN_AGG_STD || kd == DGN_AGG_VAR) return true;
+  }
+  return false;
+}
+
+template <bool BWD, int MODE, int VEC, int NS>
+static int launch_row_iso(const RowArgs& k, cudaStream_t st) {
+  if (k.N == 0) return DGN_OK;
+  const int chunks = k.rp.F / VEC;
+  if (chunks <= 0 || chunks > 256) return DGN_ERR_UNSUPPORTED;
+  const dim3 block((unsigned)chunks, (unsigned)(256 / chunks > 0 ? 256 / chunks : 1));
+  const unsigned grid = (unsigned)((k.N + block.y - 1) / block.y);
+  const bool iso = row_needs_iso(k.rp);
+  if constexpr (BWD) {
+    if (iso) agg_bwd_row_kernel<MODE, VEC, NS, true><<<grid, block, 0, st>>>(k);
+    else agg_bwd_row_kernel<MODE, VEC, NS, false><<<grid, block, 0, st>>>(k);
+  } else {
+    if (iso) agg_fwd_row_kernel<MODE, VEC, NS, true><<<grid, block, 0, st>>>(k);
+    else agg_fwd_row_kernel<MODE, VEC, NS, false><<<grid, block, 0, st>>>(k);
+  }
+  return cudaGetLastError() == cudaSuccess ? DGN_OK : DGN_ERR_CUDA;
+}
+
+template <bool BWD, int MODE, int VEC>
+static int launch_row_slots(const RowArgs& k, cudaStream_t st) {
+  const int ns = k.rp.n_slots;
+  if (ns == 0) return launch_row_iso<BWD, MODE, VEC, 0>(k, st);
+  if (ns <= 2) return launch_row_iso<BWD, MODE, VEC, 2>(k, st);
+  if (ns <= 4) return launch_row_iso<BWD, MODE, VEC, 4>(k, st);
+  return launch_row_iso<BWD, MODE, VEC, 8>(k, st);
+}
+
+template <bool BWD, int VEC>
+static int launch_row_mode(const RowArgs& k, cudaStream_t st) {
+  if (k.mode == DGN_MSG_SOURCE) return launch_row_slots<BWD, DGN_MSG_SOURCE, VEC>(k, st);
+  if (k.mode == DGN_MSG_AFFINE) return launch_row_slots<BWD, DGN_MSG_AFFINE, VEC>(k, st);
+  return launch_row_slots<BWD, DGN_MSG_DENSE, VEC>(k, st);
+}
+
+static int fill_row_args(const KernelArgs& ka, const DgnAggSpec* spec, const DgnField* f, RowArgs& k) {
+  memset(&k, 0, sizeof(k));
+  FieldPlan fp;
+  if (int rc = make_row_plan(spec, fp, &k.rp)) return rc;
+  if (!f->groups || !f->ovf_ptr || f->n_slots != fp.n_slots || (fp.n_slots > 0 && !f->wsum)) return DGN_ERR_INVALID;
+  if (reinterpret_cast<uintptr_t>(f->groups) % 16 != 0) return DGN_ERR_ALIGNMENT;
+  k.N = ka.N; k.mode = ka.mode; k.gstride = 1 + fp.n_slots;
+  k.in_ptr = ka.in_ptr; k.in_eid = ka.in_eid; k.ovf_ptr = f->ovf_ptr;
+  k.groups = reinterpret_cast<const float4*>(f->groups); k.wsum = f->wsum; k.log_deg = ka.log_deg;
+  k.x = ka.x; k.ld_x = ka.ld_x; k.q = ka.q; k.ld_q = ka.ld_q; k.q_bias = ka.q_bias; k.r = ka.r; k.ld_r = ka.ld_r;
+  k.h_in = ka.h_in; k.ld_h = ka.ld_h;
+  k.out = ka.out; k.ld_out = ka.ld_out; k.out_gs = ka.out_gs;
+  k.h_copy = ka.h_copy; k.ld_hc = ka.ld_hc; k.hc_gs = ka.hc_gs;
+  k.g_out = ka.g_out; k.g_hcopy = ka.g_hcopy;
+  k.d_q = ka.d_q; k.ld_dq = ka.ld_dq; k.d_r = ka.d_r; k.ld_dr = ka.ld_dr; k.d_h = ka.d_h; k.ld_dh = ka.ld_dh;
+  k.d_h_add = ka.d_h_add; k.ld_dha = ka.ld_dha; k.edge_ws = ka.edge_ws;
+  return DGN_OK;
+}
+
+int launch_forward_row(const KernelArgs& ka, const DgnAggSpec* spec, const DgnField* f, int vec, cudaStream_t st) {
+  RowArgs k;
+  if (int rc = fill_row_args(ka, spec, f, k)) return rc;
+  if (vec == 4) return launch_row_mode<false, 4>(k, st);
+  if (vec == 2) return launch_row_mode<false, 2>(k, st);
+  return launch_row_mode<false, 1>(k, st);
+}
+
+int launch_backward_row_dst(const KernelArgs& ka, const DgnAggSpec* spec, const DgnField* f, int vec, cudaStream_t st) {
+  RowArgs k;
+  if (int rc = fill_row_args(ka, spec, f, k)) return rc;
+  if (vec == 4) return launch_row_mode<true, 4>(k, st);
+  if (vec == 2) return launch_row_mode<true, 2>(k, st);
+  return launch_row_mode<true, 1>(k, st);
+}
+
+}  // namespace dgn
+
+using namespace dgn;
+
+extern "C" int dgn_field_slots(const DgnAggSpec* spec) {
+  if (!spec) return DGN_ERR_INVALID;
+  FieldPlan fp;
+  if (int rc = make_row_plan(spec, fp, nullptr)) return rc;
+  return fp.n_slots;
+}
+
+// HOST: overflow-group offsets of the eigen-field layout: node v has max(0, ceil((D_v - 4) / 4)) overflow groups.
+extern "C" int dgn_build_groups_host(int32_t n_nodes, const int32_t* in_ptr, int32_t* ovf_ptr) {
+  if (n_nodes < 0 || !in_ptr || !ovf_ptr) return DGN_ERR_INVALID;
+  int32_t n = 0;
+  for (int v = 0; v < n_nodes; ++v) {
+    ovf_ptr[v] = n;
+    const int D = in_ptr[v + 1] - in_ptr[v];
+    if (D < 0) return DGN_ERR_INVALID;
+    if (D > 4) n += (D - 4 + 3) / 4;
+  }
+  ovf_ptr[n_nodes] = n;
+  return n;
+}
+
+extern "C" int dgn_field_build(const DgnGraph* g, const DgnAggSpec* spec, const float* eig, int32_t ld_eig,
+                               const DgnField* f, void* stream) {
+  if (!g || !spec || !f || !g->in_ptr || (g->n_edges > 0 && !g->in_src)) return DGN_ERR_INVALID;
+  FieldArgs k;
+  memset(&k, 0, sizeof(k));
+  if (int rc = make_row_plan(spec, k.fp, nullptr)) return rc;
+  if (!f->groups || !f->ovf_ptr || f->n_slots != k.fp.n_slots) return DGN_ERR_INVALID;
+  if (k.fp.n_slots > 0 && (!eig || !f->wsum)) return DGN_ERR_INVALID;
+  if (reinterpret_cast<uintptr_t>(f->groups) % 16 != 0) return DGN_ERR_ALIGNMENT;
+  if (f->n_groups < g->n_nodes) return DGN_ERR_INVALID;
+  k.N = g->n_nodes; k.in_ptr = g->in_ptr; k.in_src = g->in_src; k.ovf_ptr = f->ovf_ptr;
+  k.eig = eig; k.ld_eig = ld_eig; k.groups = f->groups; k.wsum = f->wsum;
+  if (k.N == 0) return DGN_OK;
+  const long long threads = (long long)k.N * (k.fp.n_slots > 0 ? k.fp.n_slots : 1);
+  field_build_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(k);
+  if (cudaGetLastError() != cudaSuccess) { g_dgn_last_cuda = cudaPeekAtLastError(); return DGN_ERR_CUDA; }
+  return DGN_OK;
+}

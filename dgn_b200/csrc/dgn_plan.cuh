@@ -255,6 +255,13 @@ int launch_forward(const KernelArgs& k, int vec, cudaStream_t st);
 int launch_backward(const KernelArgs& k, int vec, float* d_x, int ld_dx, const float* addend, int ld_add,
                     cudaStream_t st);
 
+int launch_backward_src(const KernelArgs& k, int vec, float* d_x, int ld_dx, const float* addend, int ld_add,
+                        cudaStream_t st);
+
+// Row kernels over a precomputed eigen-field (dgn_agg_row.cu): the default path when DgnAggIO.field is given.
+int launch_forward_row(const KernelArgs& k, const DgnAggSpec* spec, const DgnField* f, int vec, cudaStream_t st);
+int launch_backward_row_dst(const KernelArgs& k, const DgnAggSpec* spec, const DgnField* f, int vec, cudaStream_t st);
+
 // Tile kernels (dgn_agg_tile.cu): the fast path.  Return DGN_ERR_UNSUPPORTED when they do not cover the request
 // (softmax aggregators, F/VEC > 256) - the generic kernels above then take over.  DGN_NO_TILE=1 disables them.
 int launch_forward_tile(const KernelArgs& k, int vec, cudaStream_t st);

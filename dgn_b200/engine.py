@@ -78,6 +78,7 @@ class TrainStep:
     # one optimisation step on whatever currently sits in the static batch buffers
     def _fwd_bwd(self):
         g = self.g
+        g.invalidate_fields()                 # new batch in the static buffers: the eigen-field is rebuilt (1 launch)
         self.flat_g.zero_()
         scores = self.net(g, g.ndata[self.node_key], g.edata[self.edge_key], g.snorm_n, None)
         loss = self.net.loss(scores, self.targets)

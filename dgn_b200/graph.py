@@ -10,7 +10,9 @@ kernel-side layout:
 * ``in_ptr [N+1]``, ``in_src [E]``, ``in_eid [E]``  in-edge slots grouped by destination; slots of
   one node keep edge-id order (the order of the reference's mailbox);
 * ``out_ptr [N+1]``, ``out_slot [E]``                by-source transpose for the backward pass;
-* ``log_deg [N]``, ``snorm_n [N,1]``, ``graph_ptr [B+1]``.
+* ``log_deg [N]``, ``snorm_n [N,1]``, ``graph_ptr [B+1]``;
+* ``ovf_ptr [N+1]``                                  overflow-group offsets of the eigen-field layout (``DgnField``):
+  the per-batch table of normalised eigenvector weights that ``field()`` builds once and all layers share.
 
 Everything a step needs is packed into ONE pinned host buffer and moved with ONE
 host-to-device copy; the device arrays are views into that single allocation.
@@ -64,7 +66,7 @@ class BatchedGraph:
     """A mini-batch of graphs with contiguous node ranges (block-diagonal adjacency)."""
 
     _STRUCT = ("in_ptr", "in_src", "in_eid", "out_ptr", "out_slot", "graph_ptr", "src", "dst", "log_deg", "snorm_n",
-               "meta")
+               "meta", "ovf_ptr")
 
     def __init__(self, n_nodes, src, dst, batch_num_nodes=None, batch_num_edges=None, ndata=None, edata=None,
                  pin_memory=None, capacity=None):
@@ -99,7 +101,7 @@ class BatchedGraph:
                                 ("out_ptr", (N + 1,), np.int32), ("out_slot", (E,), np.int32),
                                 ("graph_ptr", (B + 1,), np.int32), ("src", (E,), np.int32), ("dst", (E,), np.int32),
                                 ("log_deg", (N,), np.float32), ("snorm_n", (N, 1), np.float32),
-                                ("meta", (4,), np.int32)):
+                                ("meta", (4,), np.int32), ("ovf_ptr", (N + 1,), np.int32)):
             pack.add(name, shape, dt)
         for k, v in ndata.items():
             v = np.asarray(v)
@@ -137,6 +139,11 @@ class BatchedGraph:
         if self.padded:
             hv["in_ptr"][Nr + 1:] = Er
             hv["out_ptr"][Nr + 1:] = Er
+        n_ovf = _lib.lib.dgn_build_groups_host(N, p(hv["in_ptr"]), p(hv["ovf_ptr"]))
+        _lib.check(min(n_ovf, 0), "dgn_build_groups_host")
+        # eigen-field capacity in groups: one per node + overflow groups (<= E/4; fixed for padded layouts)
+        self.n_groups = N + (E // 4 + 1 if self.padded else n_ovf)
+        self._fields = {}
         self._host = hv
         self.device = torch.device("cpu")
         self._bind(pack.device_views(self._host_blob))
@@ -147,6 +154,7 @@ class BatchedGraph:
         self.ndata = {k[2:]: v for k, v in views.items() if k.startswith("n:")}
         self.edata = {k[2:]: v for k, v in views.items() if k.startswith("e:")}
         self._c_graph = None
+        self._fields = {}
 
     def to(self, device, non_blocking=True):
         """One host-to-device copy of the packed buffer; returns self (like DGLGraph.to in later DGLs)."""
@@ -221,6 +229,41 @@ class BatchedGraph:
                                           t["in_eid"].data_ptr(), t["out_ptr"].data_ptr(), t["out_slot"].data_ptr(),
                                           t["log_deg"].data_ptr())
         return self._c_graph
+
+    # ---- eigen-field (DgnField): per-batch normalised eigenvector weights shared by all layers -------------
+    def field(self, spec, eig):
+        """The ``DgnField`` of this batch for ``spec``'s directional aggregators, built on first use (one launch of
+        ``dgn_field_build``) and shared by every layer / direction that aggregates with the same directional list.
+        Rebuilt when ``eig`` was modified in place (sign flips, rb/train/train_molecules_graph_regression.py:29-33)
+        or after ``invalidate_fields()``; the device buffers are allocated once per graph object."""
+        key = tuple((a.kind, a.eig_idx, a.alpha) for a in spec.aggregators if a.kind >= _lib.AGG_DIR_AV)
+        ent = self._fields.get(key)
+        if ent is None:
+            ns = _lib.lib.dgn_field_slots(ctypes.byref(spec.c))
+            _lib.check(min(ns, 0), "dgn_field_slots")
+            dev = self._t["ovf_ptr"].device
+            groups = torch.empty(self.n_groups * (1 + ns) * 4, device=dev, dtype=torch.float32)
+            wsum = torch.empty(max(ns * self._n, 1), device=dev, dtype=torch.float32)
+            cf = _lib.DgnField(self.n_groups, ns, self._t["ovf_ptr"].data_ptr(), groups.data_ptr(),
+                               wsum.data_ptr() if ns > 0 else None)
+            ent = {"c": cf, "groups": groups, "wsum": wsum, "stamp": None}
+            self._fields[key] = ent
+        stamp = (eig.data_ptr(), eig._version, eig.stride(0)) if eig is not None else (0, 0, 0)
+        if ent["stamp"] != stamp:
+            from . import ops
+            _lib.check(_lib.lib.dgn_field_build(ctypes.byref(self.c_graph()), ctypes.byref(spec.c),
+                                                eig.data_ptr() if eig is not None else None,
+                                                eig.stride(0) if eig is not None else 0, ctypes.byref(ent["c"]),
+                                                torch.cuda.current_stream(self.device).cuda_stream), "dgn_field_build")
+            ops._count(1)
+            ent["stamp"] = stamp
+        return ent["c"]
+
+    def invalidate_fields(self):
+        """Forget which eigen-fields are current (the batch buffers were overwritten, or a CUDA-graph capture
+        starts and must record the build launch); the device buffers are kept."""
+        for ent in self._fields.values():
+            ent["stamp"] = None
 
     @property
     def max_in_degree(self):

@@ -6,6 +6,7 @@ graph.  All arithmetic of the hot path happens inside ``libdgn_b200.so``.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
@@ -70,9 +71,15 @@ class AggSpec:
         return self.S * self.A * self.Fg
 
 
-def _agg_io(mode, x, q, r, h_in, eig, out, lead, Wt, cat_input, q_bias=None):
+# False (or DGN_NO_FIELD=1): the kernels derive the eigen-weights from eig inside every launch (the ABI v2 kernels)
+FIELD_ENABLED = os.environ.get("DGN_NO_FIELD", "0") != "1"
+
+
+def _agg_io(mode, x, q, r, h_in, eig, out, lead, Wt, cat_input, q_bias=None, field=None):
     io = _lib.DgnAggIO()
     io.msg_mode = mode
+    if field is not None:
+        io.field = C.addressof(field)
     if q_bias is not None:
         io.q_bias = q_bias.data_ptr()
     if x is not None:
@@ -98,7 +105,8 @@ def agg_forward_raw(graph, spec, mode, x, q, r, h_in, eig, out, cat_input, q_bia
         return                                   # empty batch: nothing to launch (zero-size tensors have no address)
     lead = spec.Fg if cat_input else 0
     Wt = lead + spec.out_width
-    io = _agg_io(mode, x, q, r, h_in, eig, out, lead, Wt, cat_input, q_bias)
+    field = graph.field(spec, eig) if FIELD_ENABLED else None
+    io = _agg_io(mode, x, q, r, h_in, eig, out, lead, Wt, cat_input, q_bias, field)
     check(lib.dgn_agg_forward(C.byref(graph.c_graph()), C.byref(spec.c), C.byref(io), _stream(h_in)),
           "dgn_agg_forward")
     _count(1)
@@ -111,7 +119,8 @@ def agg_backward_raw(graph, spec, mode, x, q, r, h_in, eig, g_out, cat_input, d_
         return
     lead = spec.Fg if cat_input else 0
     Wt = lead + spec.out_width
-    io = _agg_io(mode, x, q, r, h_in, eig, g_out, lead, Wt, False, q_bias)     # io.out is never written here
+    field = graph.field(spec, eig) if FIELD_ENABLED else None
+    io = _agg_io(mode, x, q, r, h_in, eig, g_out, lead, Wt, False, q_bias, field)     # io.out is never written here
     gr = _lib.DgnAggGrad()
     gr.g_out = g_out.data_ptr() + 4 * lead
     if cat_input:

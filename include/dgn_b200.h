@@ -13,6 +13,10 @@
  *   dgn_agg_backward  - what torch.autograd derives for the same code.
  *   dgn_build_csr     - the edge grouping DGL 0.4.2 does inside update_all (degree bucketing)
  *                       and dgl.batch (rb/data/molecules.py:229).
+ *   dgn_field_build   - the eigenvector weights of every edge, rb/nets/aggregators.py:35-71 (the
+ *                       |eig_s - eig_d| / sum ... expressions every directional aggregator of every
+ *                       layer re-evaluates on the mailbox), and the copy of ndata['eig'] onto the edges in
+ *                       rb/nets/dgn_layer.py:75-84: evaluated ONCE per batch and shared by all layers.
  *   dgn_norm_*        - rb/nets/dgn_layer.py:122-130 (graph norm, BatchNorm1d, ReLU, residual).
  *   dgn_readout_*     - dgl.{mean,sum,max}_nodes at rb/nets/molecules_graph_regression/dgn_net.py:71-86.
  *   dgn_gemm_tf32x3   - the Linear layers of pretrans / posttrans (FCLayer, rb/nets/layers.py:76-100) in fp32
@@ -37,7 +41,7 @@
 extern "C" {
 #endif
 
-#define DGN_ABI_VERSION 2
+#define DGN_ABI_VERSION 3
 #define DGN_MAX_AGG 32      /* aggregators per layer (the reference registry has 24)        */
 #define DGN_MAX_SCALERS 4   /* scalers per layer (the reference registry has 3)             */
 #define DGN_MAX_SLOTS 8     /* distinct eigen-weighted feature sums one launch can carry    */
@@ -93,6 +97,24 @@ typedef struct {
   const float* log_deg;    /* [n_nodes]   (float)log(in_degree + 1), the scalers' per-node factor       */
 } DgnGraph;
 
+/* Eigen-field of one batch: the normalised eigenvector weight w_s(u->v) of every in-edge for every distinct
+ * (eigenvector column, weight kind) pair ("slot") the spec's directional aggregators need, laid out in groups of
+ * DGN_FIELD_GROUP in-edge slots for 128-bit loads.  Group g is (1 + n_slots) * 4 words:
+ *   int32 src[4] (source node of the slot, -1 = padding), then float w_s[4] for s = 0 .. n_slots-1.
+ * Node v owns group v (its first 4 in-edges) and the overflow groups N + ovf_ptr[v] .. N + ovf_ptr[v+1]-1.
+ * Slots are numbered in order of first use by the spec's aggregator list: dirK-av -> |d|/(sum|d|+eps);
+ * dirK-dx and dirK-dx-no-abs share d/(sum|d|+eps); dirK-dx-balanced; dirK-(neg-)0.1 -> softmax(alpha |d|).
+ * All memory is caller-owned device memory; `groups` must be 16 B aligned.  Built by dgn_field_build, consumed
+ * by dgn_agg_forward / dgn_agg_backward through DgnAggIO.field. */
+#define DGN_FIELD_GROUP 4
+typedef struct {
+  int32_t n_groups;        /* capacity of `groups`: >= n_nodes + ovf_ptr[n_nodes]                              */
+  int32_t n_slots;         /* dgn_field_slots(spec)                                                            */
+  const int32_t* ovf_ptr;  /* [n_nodes+1] from dgn_build_groups_host                                           */
+  float* groups;           /* [n_groups][1 + n_slots][4]                                                       */
+  float* wsum;             /* [n_slots][n_nodes]: sum of w_s over the in-edges of every node (NULL if n_slots == 0) */
+} DgnField;
+
 /* Which aggregators / scalers to compute: the AGGREGATORS / SCALERS names resolved to op-codes. */
 typedef struct {
   int32_t n_feat;         /* F: feature columns aggregated (all towers together)                        */
@@ -130,6 +152,9 @@ typedef struct {
                              fuses the torch.cat([h, agg]) of rb/nets/dgn_layer.py:116                    */
   int32_t ld_hcopy;
   int32_t hcopy_group_stride;
+  const DgnField* field;  /* optional (host pointer to the struct): eigen-field of this batch built with a spec that
+                             has the same directional aggregators.  With it the kernels read precomputed weights
+                             (the fast path); NULL = weights are derived from eig inside every launch.          */
 } DgnAggIO;
 
 /* Gradients for dgn_agg_backward.  Any output pointer may be NULL when that gradient is not needed. */
@@ -170,6 +195,17 @@ int dgn_agg_backward(const DgnGraph* g, const DgnAggSpec* spec, const DgnAggIO* 
 int dgn_build_csr_host(int32_t n_nodes, int32_t n_edges, const int32_t* src, const int32_t* dst,
                        int32_t* in_ptr, int32_t* in_src, int32_t* in_eid, int32_t* out_ptr, int32_t* out_slot,
                        float* log_deg);
+
+/* Number of eigen-field slots of a spec (0 .. DGN_MAX_SLOTS), negative DgnStatus on error. */
+int dgn_field_slots(const DgnAggSpec* spec);
+
+/* HOST: overflow-group offsets of the eigen-field layout from the in-edge ranges: node v gets
+ * max(0, ceil((D_v - 4) / 4)) overflow groups.  Returns their total (>= 0) or a negative DgnStatus. */
+int dgn_build_groups_host(int32_t n_nodes, const int32_t* in_ptr, int32_t* ovf_ptr);
+
+/* Fills f->groups and f->wsum for the batch (one launch).  eig is [n_nodes, n_eig] with row stride ld_eig. */
+int dgn_field_build(const DgnGraph* g, const DgnAggSpec* spec, const float* eig, int32_t ld_eig, const DgnField* f,
+                    void* stream);
 
 /* Fused layer epilogue, rb/nets/dgn_layer.py:122-130:
  *   z = y * snorm_n ; BatchNorm1d(z) (batch statistics, running stats updated) ; ReLU ; + residual.

@@ -30,7 +30,7 @@ def test_every_declared_symbol_is_exported_and_bound():
 
 
 def test_abi_version_and_status_strings():
-    assert _lib.lib.dgn_abi_version() == _lib.ABI_VERSION == 2
+    assert _lib.lib.dgn_abi_version() == _lib.ABI_VERSION == 3
     assert _lib.lib.dgn_status_string(0) == b"ok"
     assert b"invalid" in _lib.lib.dgn_status_string(-1)
 
@@ -39,6 +39,32 @@ def test_struct_sizes_match_header_layout():
     # 5 int32 + 32 + 32 + 32*4 + 4 (+pad) + float
     assert C.sizeof(_lib.DgnAggSpec) == 20 + 32 + 32 + 128 + 4 + 4
     assert C.sizeof(_lib.DgnGraph) == 8 + 6 * 8
+    assert C.sizeof(_lib.DgnField) == 8 + 3 * 8
+
+
+def test_group_builder_and_field_slots():
+    # overflow groups of the eigen-field layout: max(0, ceil((D - 4) / 4)) per node
+    deg = np.array([0, 1, 4, 5, 8, 9, 51, 3], np.int32)
+    in_ptr = np.concatenate([[0], np.cumsum(deg)]).astype(np.int32)
+    ovf = np.zeros(len(deg) + 1, np.int32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    tot = _lib.lib.dgn_build_groups_host(len(deg), p(in_ptr), p(ovf))
+    want = np.maximum(0, -(-(deg - 4) // 4))
+    assert tot == want.sum() and np.array_equal(ovf, np.concatenate([[0], np.cumsum(want)]))
+    assert _lib.lib.dgn_build_groups_host(3, None, p(ovf)) == -1
+    # slots: dx and dx-no-abs of one eigenvector share a slot, av has its own, balanced is a single slot
+    from dgn_b200.nets.aggregators import AGGREGATORS
+    from dgn_b200.nets.scalers import SCALERS
+    from dgn_b200.ops import AggSpec
+
+    def slots(names):
+        spec = AggSpec([AGGREGATORS[n] for n in names.split()], [SCALERS["identity"]], 1.0, 8, 4)
+        return _lib.lib.dgn_field_slots(C.byref(spec.c))
+    assert slots("mean max") == 0
+    assert slots("mean dir1-dx dir1-dx-no-abs") == 1
+    assert slots("dir1-dx dir2-dx dir1-dx-no-abs dir2-dx-no-abs dir1-av dir2-av") == 4
+    assert slots("dir1-dx-balanced dir1-0.1 dir1-neg-0.1 dir1-av") == 4
+    assert _lib.lib.dgn_field_slots(None) == -1
 
 
 def test_null_arguments_are_rejected_without_a_gpu():

@@ -268,18 +268,38 @@ def test_too_many_slots_is_reported():
         aggregate(g, spec, _lib.MSG_SOURCE, x, g.ndata["eig"], x=x)
 
 
-def test_generic_kernels_still_match_oracle_when_tile_kernels_are_disabled():
-    """The tile kernels are the default path; DGN_NO_TILE=1 forces the generic per-(node,chunk) kernels,
-    which remain the fallback for softmax aggregators / very wide rows.  Re-run the oracle comparison on them."""
+@pytest.mark.parametrize("env", [{"DGN_NO_FIELD": "1"}, {"DGN_NO_FIELD": "1", "DGN_NO_TILE": "1"}],
+                         ids=["tile_kernels", "generic_kernels"])
+def test_in_kernel_weight_paths_still_match_oracle(env):
+    """The row kernels over the precomputed eigen-field are the default path.  DGN_NO_FIELD=1 selects the kernels
+    that derive the eigen-weights inside every launch (DgnAggIO.field == NULL): the shared-memory tile kernels, or -
+    with DGN_NO_TILE=1 - the generic per-(node, chunk) kernels.  Re-run the oracle comparison on both."""
     import os
     import subprocess
     import sys
     repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, DGN_NO_TILE="1")
     out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(repo, "tests", "test_agg_gpu.py"), "-q", "-x",
                           "-m", "gpu", "-k", "aggregate_matches_oracle or cat_input or towers_group or registry_callable"],
-                         env=env, capture_output=True, text=True, cwd=repo)
+                         env=dict(os.environ, **env), capture_output=True, text=True, cwd=repo)
     assert out.returncode == 0, out.stdout[-3000:]
+
+
+def test_field_is_rebuilt_when_eig_changes_in_place():
+    """The eigen-field is cached per batch; an in-place change of eig (the sign-flip augmentation,
+    rb/train/train_molecules_graph_regression.py:29-33) must invalidate it."""
+    g, samples, eig, h, P, Q, R, avg = _graph_case("zinc", 6, 3, 8)
+    g.to(DEV)
+    aggs = ["mean", "dir1-dx", "dir2-av", "dir1-dx-no-abs"]
+    spec = AggSpec([AGGREGATORS[a] for a in aggs], [SCALERS["identity"]], avg, 8, eig.shape[1])
+    src, dst = g.host("src").astype(np.int64), g.host("dst").astype(np.int64)
+    eig_d, hd = eig.to(DEV), h.to(DEV)
+    out1 = aggregate(g, spec, _lib.MSG_SOURCE, hd, eig_d, x=hd)
+    assert_close(out1, oracle_aggregate(g.number_of_nodes(), src, dst, eig, h, h[src], aggs, ["identity"], avg), what="before")
+    flip = torch.where(torch.rand(eig.shape) < 0.5, -1.0, 1.0)
+    eig_d.mul_(flip.to(DEV))
+    out2 = aggregate(g, spec, _lib.MSG_SOURCE, hd, eig_d, x=hd)
+    assert_close(out2, oracle_aggregate(g.number_of_nodes(), src, dst, eig * flip, h, h[src], aggs, ["identity"], avg),
+                 what="after flip")
 
 
 def test_empty_and_degenerate_graphs():

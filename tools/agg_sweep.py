@@ -17,7 +17,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
-from dgn_b200 import _lib                                           # noqa: E402
+from dgn_b200 import _lib, ops                                           # noqa: E402
 from dgn_b200.data.synthetic import make_samples, avg_log_degree    # noqa: E402
 from dgn_b200.graph import collate                                  # noqa: E402
 from dgn_b200.nets.aggregators import AGGREGATORS                   # noqa: E402
@@ -91,11 +91,22 @@ def run_case(name, scale, dev):
     tf = time_graph(lambda t: agg_forward_raw(g, spec, _lib.MSG_AFFINE, t["P"], t["Q"], None, t["h"], eig, t["out"], True), sets)
     tb = time_graph(lambda t: agg_backward_raw(g, spec, _lib.MSG_AFFINE, t["P"], t["Q"], None, t["h"], eig, t["gy"], True,
                                                d_x=t["dP"], d_q=t["dQ"], d_h=t["dh"], edge_ws=t["ws"]), sets)
+    # the per-batch eigen-field build (one launch shared by all layers of a step), timed on its own
+    t_field = 0.0
+    if ops.FIELD_ENABLED:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(10):
+            g.invalidate_fields()
+            g.field(spec, eig)
+        b.record()
+        torch.cuda.synchronize()
+        t_field = a.elapsed_time(b) * 1e-3 / 10
     bf = 4 * (E + N * (3 * F + k_used + 1) + N * S * A * F)
     bb = bf + 4 * N * 3 * F
     pk = peak()
     return {"case": name, "scale": scale, "graphs": len(samples), "N": N, "E": E, "F": F, "A": A, "S": S, "rot": rot,
-            "fwd_us": tf * 1e6, "bwd_us": tb * 1e6, "bytes_fwd": bf, "bytes_bwd": bb,
+            "fwd_us": tf * 1e6, "bwd_us": tb * 1e6, "field_build_us": t_field * 1e6, "bytes_fwd": bf, "bytes_bwd": bb,
             "fwd_gbs": bf / tf / 1e9, "bwd_gbs": bb / tb / 1e9, "fwd_frac": bf / tf / 1e9 / pk,
             "bwd_frac": bb / tb / 1e9 / pk, "frac": (bf + bb) / (tf + tb) / 1e9 / pk, "peak_gbs": pk,
             "edges_per_s_fwd_bwd": E / (tf + tb)}
