@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdgn_b200.so")
+# DGN_LIB_PATH: an alternative build of the same ABI (kernel tuning experiments, tools/ only)
+LIB_PATH = os.environ.get("DGN_LIB_PATH") or os.path.join(_HERE, "libdgn_b200.so")
 
 MAX_AGG, MAX_SCALERS, MAX_SLOTS = 32, 4, 8
 ABI_VERSION = 3

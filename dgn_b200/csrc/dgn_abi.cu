@@ -160,7 +160,9 @@ extern "C" int dgn_agg_backward(const DgnGraph* g, const DgnAggSpec* spec, const
   if (k.d_h) vec = imin(vec, imin(vwp(k.d_h), vw(k.ld_dh)));
   if (k.d_h_add) vec = imin(vec, imin(vwp(k.d_h_add), vw(k.ld_dha)));
   if (grad->d_x) vec = imin(vec, imin(imin(vwp(grad->d_x), vw(grad->ld_dx)), vwp(grad->edge_ws)));
-  vec = choose_vec(vec, k.N, k.plan.F, true);
+  // measured (profiles/README.md): the row backward is fastest with 16 B lanes at every size; the kernels that derive
+  // the weights in the launch prefer 8 B lanes for small launches
+  vec = choose_vec(vec, k.N, k.plan.F, io->field == nullptr);
   k.plan.chunks = k.plan.F / vec;
   int rc;
   if (io->field) {

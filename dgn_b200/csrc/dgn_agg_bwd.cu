@@ -290,9 +290,7 @@ int launch_backward(const KernelArgs& k, int vec, float* d_x, int ld_dx, const f
     const int kd = k.plan.agg_kind[a];
     iso |= (kd == DGN_AGG_MAX || kd == DGN_AGG_MIN || kd == DGN_AGG_STD || kd == DGN_AGG_VAR);
   }
-  int rc = tile_kernels_enabled() ? launch_backward_tile_dst(k, vec, st) : DGN_ERR_UNSUPPORTED;
-  if (rc == DGN_ERR_UNSUPPORTED)
-    rc = vec == 4 ? dispatch_mode<4>(k, iso, st) : vec == 2 ? dispatch_mode<2>(k, iso, st) : dispatch_mode<1>(k, iso, st);
+  int rc = vec == 4 ? dispatch_mode<4>(k, iso, st) : vec == 2 ? dispatch_mode<2>(k, iso, st) : dispatch_mode<1>(k, iso, st);
   if (rc != DGN_OK || !d_x) return rc;
   return launch_backward_src(k, vec, d_x, ld_dx, addend, ld_add, st);
 }

@@ -196,16 +196,7 @@ static int dispatch_mode(const KernelArgs& k, bool iso, cudaStream_t st) {
   return dispatch_slots<DGN_MSG_DENSE, VEC>(k, iso, st);
 }
 
-bool tile_kernels_enabled() {
-  static const bool on = [] { const char* e = getenv("DGN_NO_TILE"); return !(e && atoi(e) != 0); }();
-  return on;
-}
-
 int launch_forward(const KernelArgs& k, int vec, cudaStream_t st) {
-  if (tile_kernels_enabled()) {
-    const int rc = launch_forward_tile(k, vec, st);
-    if (rc != DGN_ERR_UNSUPPORTED) return rc;
-  }
   const bool iso = needs_iso(k.plan);
   if (vec == 4) return dispatch_mode<4>(k, iso, st);
   if (vec == 2) return dispatch_mode<2>(k, iso, st);

@@ -8,7 +8,7 @@
 //   group g = 4 consecutive in-edge slots of one destination node:  [ int32 src[4] | float w_0[4] | ... | w_{ns-1}[4] ]
 //   node v owns group v (its first 4 in-edges; src = -1 pads) - no pointer chase for molecules (degree <= 4) -
 //   and the overflow groups N + ovf_ptr[v] .. N + ovf_ptr[v+1] (degree > 4: superpixel kNN, SBM PATTERN).
-//   wsum[s][v] = sum_u w_s(u->v), the factor of h_in in the dx aggregators.
+//   wsum[v][s] = sum_u w_s(u->v), the factor of h_in in the dx aggregators (row stride 4 * ceil(ns / 4)).
 //
 // With that, a (node, column chunk) thread's dependent chain is group -> message rows -> stores: no in_ptr ->
 // in_src -> eig[u] chain, no per-launch abs / relu / exp / division, no shared memory, no block barrier.  The
@@ -20,6 +20,16 @@
 #include "dgn_plan.cuh"
 
 extern thread_local cudaError_t g_dgn_last_cuda;
+
+#ifndef ROW_MINB_FWD
+#define ROW_MINB_FWD 8
+#endif
+#ifndef ROW_MINB_BWD
+#define ROW_MINB_BWD 6
+#endif
+#ifndef ROW_THREADS
+#define ROW_THREADS 128
+#endif
 
 namespace dgn {
 
@@ -44,6 +54,14 @@ struct FieldPlan {
 
 struct RowPlan {
   int F, Fg, A, S, n_slots;
+  // forward: static op layout - the output block (aggregator index) of every isotropic kind and of every op of
+  // every slot, -1 = absent.  A repeated directional aggregator gets a slot of its own; repeated isotropic names
+  // (never used by the reference configs) go to the `extra` list.
+  int16_t iso_pos[6];                 // indexed by DgnAggKind MEAN .. VAR
+  int16_t slot_pos[DGN_MAX_SLOTS][3]; // indexed by RowOp
+  int n_extra;
+  uint8_t extra_kind[DGN_MAX_AGG], extra_pos[DGN_MAX_AGG];
+  // backward: the same aggregators as a table walked with a software-pipelined loop
   int n_iso;                          // order[0, n_iso): isotropic aggregators
   int slot_end[DGN_MAX_SLOTS];        // order[slot_end[s-1], slot_end[s]) read slot s
   uint8_t order[DGN_MAX_AGG];         // aggregator index (output block) of every position
@@ -70,6 +88,7 @@ struct RowArgs {
   float* h_copy; int ld_hc; int hc_gs;
   const float* g_out;
   const float* g_hcopy;
+  int pf_bytes;                       // > 0: bytes of a node's gradient row to prefetch into L2 (16 B multiple)
   float* d_q; int ld_dq;
   float* d_r; int ld_dr;
   float* d_h; int ld_dh;
@@ -77,10 +96,15 @@ struct RowArgs {
   float* edge_ws;
 };
 
-static int field_slot(FieldPlan& f, int eig, int kind, float alpha) {
+// slot with these weights whose op `op` is still free (a repeated aggregator opens a new slot with equal weights)
+static int field_slot(FieldPlan& f, int eig, int kind, float alpha, int op, unsigned (&used)[DGN_MAX_SLOTS]) {
   for (int s = 0; s < f.n_slots; ++s)
-    if (f.eig[s] == eig && f.kind[s] == kind && (kind != FW_SOFT || f.alpha[s] == alpha)) return s;
+    if (f.eig[s] == eig && f.kind[s] == kind && (kind != FW_SOFT || f.alpha[s] == alpha) && !(used[s] & (1u << op))) {
+      used[s] |= 1u << op;
+      return s;
+    }
   if (f.n_slots >= DGN_MAX_SLOTS) return -1;
+  used[f.n_slots] = 1u << op;
   const int s = f.n_slots++;
   f.eig[s] = eig; f.kind[s] = kind; f.alpha[s] = alpha;
   return s;
@@ -94,6 +118,7 @@ int make_row_plan(const DgnAggSpec* spec, FieldPlan& fp, RowPlan* rp) {
       spec->n_scalers > DGN_MAX_SCALERS || spec->n_eig < 0)
     return DGN_ERR_INVALID;
   int slot_of[DGN_MAX_AGG], op_of[DGN_MAX_AGG];
+  unsigned used[DGN_MAX_SLOTS] = {0};
   for (int a = 0; a < spec->n_agg; ++a) {
     const int kind = spec->agg_kind[a], eig = spec->agg_eig[a];
     slot_of[a] = -1; op_of[a] = kind;
@@ -101,11 +126,11 @@ int make_row_plan(const DgnAggSpec* spec, FieldPlan& fp, RowPlan* rp) {
     if (kind < DGN_AGG_DIR_AV) continue;
     if (eig >= spec->n_eig) return DGN_ERR_INVALID;
     switch (kind) {
-      case DGN_AGG_DIR_AV: slot_of[a] = field_slot(fp, eig, FW_ABS, 0.f); op_of[a] = OP_WSUM; break;
-      case DGN_AGG_DIR_DX: slot_of[a] = field_slot(fp, eig, FW_SGN, 0.f); op_of[a] = OP_DX_ABS; break;
-      case DGN_AGG_DIR_DX_NO_ABS: slot_of[a] = field_slot(fp, eig, FW_SGN, 0.f); op_of[a] = OP_DX; break;
-      case DGN_AGG_DIR_DX_BALANCED: slot_of[a] = field_slot(fp, eig, FW_BAL, 0.f); op_of[a] = OP_DX_ABS; break;
-      default: slot_of[a] = field_slot(fp, eig, FW_SOFT, spec->agg_alpha[a]); op_of[a] = OP_WSUM; break;
+      case DGN_AGG_DIR_AV: op_of[a] = OP_WSUM; slot_of[a] = field_slot(fp, eig, FW_ABS, 0.f, OP_WSUM, used); break;
+      case DGN_AGG_DIR_DX: op_of[a] = OP_DX_ABS; slot_of[a] = field_slot(fp, eig, FW_SGN, 0.f, OP_DX_ABS, used); break;
+      case DGN_AGG_DIR_DX_NO_ABS: op_of[a] = OP_DX; slot_of[a] = field_slot(fp, eig, FW_SGN, 0.f, OP_DX, used); break;
+      case DGN_AGG_DIR_DX_BALANCED: op_of[a] = OP_DX_ABS; slot_of[a] = field_slot(fp, eig, FW_BAL, 0.f, OP_DX_ABS, used); break;
+      default: op_of[a] = OP_WSUM; slot_of[a] = field_slot(fp, eig, FW_SOFT, spec->agg_alpha[a], OP_WSUM, used); break;
     }
     if (slot_of[a] < 0) return DGN_ERR_UNSUPPORTED;
   }
@@ -121,6 +146,13 @@ int make_row_plan(const DgnAggSpec* spec, FieldPlan& fp, RowPlan* rp) {
   for (int s = 0; s < spec->n_scalers; ++s) {
     if (spec->scaler_kind[s] > DGN_SCALE_ATTENUATION) return DGN_ERR_INVALID;
     rp->scaler_kind[s] = spec->scaler_kind[s];
+  }
+  for (int i = 0; i < 6; ++i) rp->iso_pos[i] = -1;
+  for (int t = 0; t < DGN_MAX_SLOTS; ++t) rp->slot_pos[t][0] = rp->slot_pos[t][1] = rp->slot_pos[t][2] = -1;
+  for (int a = 0; a < rp->A; ++a) {
+    if (slot_of[a] >= 0) rp->slot_pos[slot_of[a]][op_of[a]] = (int16_t)a;
+    else if (rp->iso_pos[op_of[a]] < 0) rp->iso_pos[op_of[a]] = (int16_t)a;
+    else { rp->extra_kind[rp->n_extra] = (uint8_t)op_of[a]; rp->extra_pos[rp->n_extra] = (uint8_t)a; ++rp->n_extra; }
   }
   int n = 0;
   for (int a = 0; a < rp->A; ++a)
@@ -199,7 +231,7 @@ __global__ void __launch_bounds__(256) field_build_kernel(const __grid_constant_
     }
     k.groups[((size_t)group_of(j) * gstride + 1 + s) * 4 + (j & 3)] = w;
   }
-  k.wsum[(size_t)s * k.N + v] = ws;
+  k.wsum[(size_t)v * ((ns + 3) & ~3) + s] = ws;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -234,55 +266,82 @@ __device__ __forceinline__ float div_by(float x, float fD, float rD) {
 
 // Walks the in-edge groups of node v: the node-aligned first group, then its overflow groups.  fn(jg, m, wts) is
 // called for every real in-edge in mailbox order with its message (this thread's columns) and slot weights.
-template <int MODE, int VEC, int NS, typename Fn>
+// The message mode is a launch-uniform runtime branch: SOURCE is AFFINE with q = 0 (qv stays zero), DENSE reads R[eid].
+template <int VEC, int NS, typename Fn>
 __device__ __forceinline__ void walk_groups(const RowArgs& k, int v, int c, const Vec<VEC>& qv, int e0, int ovf0, int ovf1,
                                             Fn&& fn) {
   constexpr int NSA = NS > 0 ? NS : 1;
-  const bool need_eid = (MODE == DGN_MSG_DENSE) || (MODE == DGN_MSG_AFFINE && k.r != nullptr);
+  const bool dense = k.mode == DGN_MSG_DENSE;
+  const bool edge_term = !dense && k.r != nullptr;
   int g = v, o = ovf0, jbase = 0;
   while (true) {
     const float4* gp = k.groups + (size_t)g * k.gstride;
-    const int4 su = __ldg(reinterpret_cast<const int4*>(gp));
-    float4 wv[NSA];
+    const int4 su4 = __ldg(reinterpret_cast<const int4*>(gp));
+    // the group is consumed as two pairs of in-edge slots: half the staging registers of a 4-wide pass (occupancy is
+    // what hides the gather latency), and no gathers at all for the padding pair of a degree <= 2 node
 #pragma unroll
-    for (int s = 0; s < NS; ++s) wv[s] = (s < k.rp.n_slots) ? __ldg(gp + 1 + s) : make_float4(0.f, 0.f, 0.f, 0.f);
-    Vec<VEC> m[4];
+    for (int h = 0; h < 2; ++h) {
+      const int u0 = h == 0 ? su4.x : su4.z, u1 = h == 0 ? su4.y : su4.w;
+      if (u0 < 0) break;
+      float2 wv[NSA];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {                 // the 4 gathers of the group are issued back to back
-      const int u = lane_of(su, j);
-      if constexpr (MODE == DGN_MSG_DENSE) {
-        int id = e0 + jbase + j;
-        if (k.in_eid && u >= 0) id = __ldg(k.in_eid + id);
-        m[j] = vload<VEC>(k.r + (size_t)(u >= 0 ? id : 0) * k.ld_r + c);
-      } else {
-        m[j] = vload<VEC>(k.x + (size_t)max(u, 0) * k.ld_x + c);
+      for (int s = 0; s < NS; ++s)
+        wv[s] = (s < k.rp.n_slots) ? __ldg(reinterpret_cast<const float2*>(gp + 1 + s) + h) : make_float2(0.f, 0.f);
+      Vec<VEC> m[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {               // both gathers of the pair are issued back to back
+        const int u = j == 0 ? u0 : u1;
+        if (dense) {
+          int id = e0 + jbase + 2 * h + j;
+          if (k.in_eid && u >= 0) id = __ldg(k.in_eid + id);
+          m[j] = vload<VEC>(k.r + (size_t)(u >= 0 ? id : 0) * k.ld_r + c);
+        } else {
+          m[j] = vload<VEC>(k.x + (size_t)max(u, 0) * k.ld_x + c);
+        }
       }
-    }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (lane_of(su, j) >= 0) {
-        Vec<VEC> mm = m[j];
-        if constexpr (MODE == DGN_MSG_AFFINE) {
+      for (int j = 0; j < 2; ++j) {
+        if ((j == 0 ? u0 : u1) >= 0) {
+          Vec<VEC> mm = m[j];
 #pragma unroll
           for (int i = 0; i < VEC; ++i) mm.a[i] += qv.a[i];
-          if (need_eid) {
-            const int e = e0 + jbase + j;
+          if (edge_term) {
+            const int e = e0 + jbase + 2 * h + j;
             const int id = k.in_eid ? __ldg(k.in_eid + e) : e;
             const Vec<VEC> rv = vload<VEC>(k.r + (size_t)id * k.ld_r + c);
 #pragma unroll
             for (int i = 0; i < VEC; ++i) mm.a[i] += rv.a[i];
           }
-        }
-        float wj[NSA];
+          float wj[NSA];
 #pragma unroll
-        for (int s = 0; s < NSA; ++s) wj[s] = lane_of(wv[s], j);
-        fn(jbase + j, mm, wj);
+          for (int s = 0; s < NSA; ++s) wj[s] = j == 0 ? wv[s].x : wv[s].y;
+          fn(jbase + 2 * h + j, mm, wj);
+        }
       }
     }
     if (o >= ovf1) break;
     g = k.N + o;
     ++o;
     jbase += 4;
+  }
+}
+
+// wsum row of node v: one 128-bit load per 4 slots
+template <int NS>
+__device__ __forceinline__ void load_wsum(const RowArgs& k, int v, float (&w)[NS > 0 ? NS : 1]) {
+  if constexpr (NS == 0) {
+    w[0] = 0.f;
+  } else if constexpr (NS == 2) {
+    const float2 t = __ldg(reinterpret_cast<const float2*>(k.wsum + (size_t)v * 4));
+    w[0] = t.x; w[1] = t.y;
+  } else {
+    const int nsp = (k.rp.n_slots + 3) & ~3;
+#pragma unroll
+    for (int q = 0; q < NS / 4; ++q) {
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (4 * q < nsp) t = __ldg(reinterpret_cast<const float4*>(k.wsum + (size_t)v * nsp) + q);
+      w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w;
+    }
   }
 }
 
@@ -335,33 +394,71 @@ __device__ __forceinline__ void row_mean_var(const Vec<VEC>& sum, const Vec<VEC>
 // ------------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------------
-// SS = number of scalers known at compile time (0 = runtime P.S)
+__device__ __forceinline__ float sqrt_approx(float x) {      // 1 ulp; the IEEE sqrtf costs ~10 instructions per column
+  float y;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// SS = number of scalers known at compile time (0 = runtime P.S).  Straight-line code: every possible op is a
+// launch-uniform "is it requested" test on the plan followed by S scaled 128-bit streaming stores; the S slab base
+// pointers are formed once, every store address is base + (block * Fg) in one IMAD.WIDE.
 template <int VEC, int NS, bool ISO, int SS>
 __device__ __forceinline__ void fwd_epilogue(const RowPlan& P, const Acc<VEC, NS, ISO>& R, const Vec<VEC>& hv,
                                              const float* wsumv, int D, float ld, float* __restrict__ orow) {
   const int S = SS > 0 ? SS : P.S;
   float coef[DGN_MAX_SCALERS];
   row_scaler_coefs(P, ld, coef);
-  const float fD = (float)D, rD = __frcp_rn(fD);
-  Vec<VEC> mean, var;
-  row_mean_var<VEC, ISO>(R.sum, R.sq, fD, rD, mean, var);
-  const int scaler_stride = P.A * P.Fg;
+  // one opaque 64-bit row base + 32-bit element offsets: each store address is a single IMAD.WIDE (left to itself the
+  // compiler re-derives every address from k.out with 64-bit index arithmetic, 4 instructions per store)
+  asm volatile("" : "+l"(orow));
+  const unsigned scaler_stride = (unsigned)(P.A * P.Fg);
   auto store_scaled = [&](int a, const Vec<VEC>& y) {
-    float* dst = orow + a * P.Fg;
+    const unsigned off = (unsigned)a * (unsigned)P.Fg;
 #pragma unroll
     for (int s = 0; s < DGN_MAX_SCALERS; ++s) {
       if (s < S) {
         Vec<VEC> o;
 #pragma unroll
         for (int i = 0; i < VEC; ++i) o.a[i] = y.a[i] * coef[s];
-        vstore_stream<VEC>(dst + s * scaler_stride, o);
+        vstore_stream<VEC>(orow + (off + (unsigned)s * scaler_stride), o);
       }
     }
   };
-  int pos = 0;
-  for (; pos < P.n_iso; ++pos) {
+  const float fD = (float)D, rD = __frcp_rn(fD);
+  Vec<VEC> mean, var;
+  row_mean_var<VEC, ISO>(R.sum, R.sq, fD, rD, mean, var);
+  if (P.iso_pos[DGN_AGG_MEAN] >= 0) store_scaled(P.iso_pos[DGN_AGG_MEAN], mean);
+  if (P.iso_pos[DGN_AGG_SUM] >= 0) store_scaled(P.iso_pos[DGN_AGG_SUM], R.sum);
+  if constexpr (ISO) {
+    if (P.iso_pos[DGN_AGG_MAX] >= 0) store_scaled(P.iso_pos[DGN_AGG_MAX], R.mx);
+    if (P.iso_pos[DGN_AGG_MIN] >= 0) store_scaled(P.iso_pos[DGN_AGG_MIN], R.mn);
+    if (P.iso_pos[DGN_AGG_VAR] >= 0) store_scaled(P.iso_pos[DGN_AGG_VAR], var);
+    if (P.iso_pos[DGN_AGG_STD] >= 0) {
+      Vec<VEC> y;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) y.a[i] = sqrt_approx(var.a[i] + DGN_EPS);
+      store_scaled(P.iso_pos[DGN_AGG_STD], y);
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    if (P.slot_pos[s][OP_WSUM] >= 0) store_scaled(P.slot_pos[s][OP_WSUM], R.w[s]);
+    if (P.slot_pos[s][OP_DX] >= 0 || P.slot_pos[s][OP_DX_ABS] >= 0) {
+      Vec<VEC> sv;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) sv.a[i] = R.w[s].a[i] - wsumv[s] * hv.a[i];
+      if (P.slot_pos[s][OP_DX] >= 0) store_scaled(P.slot_pos[s][OP_DX], sv);
+      if (P.slot_pos[s][OP_DX_ABS] >= 0) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) sv.a[i] = fabsf(sv.a[i]);
+        store_scaled(P.slot_pos[s][OP_DX_ABS], sv);
+      }
+    }
+  }
+  for (int x = 0; x < P.n_extra; ++x) {                // repeated isotropic names
     Vec<VEC> y;
-    switch (P.op[pos]) {
+    switch (P.extra_kind[x]) {
       case DGN_AGG_MEAN: y = mean; break;
       case DGN_AGG_SUM: y = R.sum; break;
       case DGN_AGG_MAX: y = ISO ? R.mx : mean; break;
@@ -369,30 +466,14 @@ __device__ __forceinline__ void fwd_epilogue(const RowPlan& P, const Acc<VEC, NS
       case DGN_AGG_VAR: y = var; break;
       default:
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) y.a[i] = sqrtf(var.a[i] + DGN_EPS);
+        for (int i = 0; i < VEC; ++i) y.a[i] = sqrt_approx(var.a[i] + DGN_EPS);
     }
-    store_scaled(P.order[pos], y);
-  }
-#pragma unroll
-  for (int s = 0; s < NS; ++s) {
-    const int end = P.slot_end[s];
-    for (; pos < end; ++pos) {
-      const int op = P.op[pos];
-      Vec<VEC> y = R.w[s];
-      if (op != OP_WSUM) {
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-          const float sv = y.a[i] - wsumv[s] * hv.a[i];
-          y.a[i] = (op == OP_DX_ABS) ? fabsf(sv) : sv;
-        }
-      }
-      store_scaled(P.order[pos], y);
-    }
+    store_scaled(P.extra_pos[x], y);
   }
 }
 
-template <int MODE, int VEC, int NS, bool ISO>
-__global__ void __launch_bounds__(256) agg_fwd_row_kernel(const __grid_constant__ RowArgs k) {
+template <int VEC, int NS, bool ISO>
+__global__ void __launch_bounds__(ROW_THREADS, ROW_MINB_FWD) agg_fwd_row_kernel(const __grid_constant__ RowArgs k) {
   constexpr int NSA = NS > 0 ? NS : 1;
   const RowPlan& P = k.rp;
   const int v = blockIdx.x * blockDim.y + threadIdx.y;
@@ -403,11 +484,10 @@ __global__ void __launch_bounds__(256) agg_fwd_row_kernel(const __grid_constant_
 
   // everything that does not depend on the in-edges is requested first
   const int ovf0 = __ldg(k.ovf_ptr + v), ovf1 = __ldg(k.ovf_ptr + v + 1);
-  const bool need_e0 = (MODE == DGN_MSG_DENSE) || (MODE == DGN_MSG_AFFINE && k.r != nullptr);
-  const int e0 = need_e0 ? __ldg(k.in_ptr + v) : 0;
+  const int e0 = (k.r != nullptr) ? __ldg(k.in_ptr + v) : 0;      // edge ids are only needed for R[eid]
   const Vec<VEC> hv = vload<VEC>(k.h_in + (size_t)v * k.ld_h + c);
   Vec<VEC> qv = vfill<VEC>(0.f);
-  if constexpr (MODE == DGN_MSG_AFFINE) {
+  if (k.q) {
     qv = vload<VEC>(k.q + (size_t)v * k.ld_q + c);
     if (k.q_bias) {
       const Vec<VEC> bv = vload<VEC>(k.q_bias + c);
@@ -417,14 +497,13 @@ __global__ void __launch_bounds__(256) agg_fwd_row_kernel(const __grid_constant_
   }
   const float ld = (P.S > 1) ? __ldg(k.log_deg + v) : 1.f;
   float wsumv[NSA];
-#pragma unroll
-  for (int s = 0; s < NSA; ++s) wsumv[s] = (s < P.n_slots) ? __ldg(k.wsum + (size_t)s * k.N + v) : 0.f;
+  load_wsum<NS>(k, v, wsumv);
   if (k.h_copy) vstore<VEC>(k.h_copy + (size_t)v * k.ld_hc + (size_t)tower * k.hc_gs + cg, hv);
 
   Acc<VEC, NS, ISO> R;
   acc_clear(R);
   int D = 0;
-  walk_groups<MODE, VEC, NS>(k, v, c, qv, e0, ovf0, ovf1, [&](int, const Vec<VEC>& m, const float* wj) {
+  walk_groups<VEC, NS>(k, v, c, qv, e0, ovf0, ovf1, [&](int, const Vec<VEC>& m, const float* wj) {
     ++D;
     acc_add<VEC, NS, ISO>(R, m, wj);
   });
@@ -446,12 +525,15 @@ __global__ void __launch_bounds__(256) agg_fwd_row_kernel(const __grid_constant_
 template <int VEC, int SS>
 __device__ __forceinline__ void load_slabs(const float* __restrict__ grow, int a, int Fg, int scaler_stride, int S,
                                            Vec<VEC> (&g)[DGN_MAX_SCALERS]) {
+  const unsigned off = (unsigned)a * (unsigned)Fg;
 #pragma unroll
   for (int s = 0; s < DGN_MAX_SCALERS; ++s)
-    if (s < (SS > 0 ? SS : S)) g[s] = vload_stream<VEC>(grow + a * Fg + s * scaler_stride);
+    if (s < (SS > 0 ? SS : S)) g[s] = vload_stream<VEC>(grow + (off + (unsigned)s * (unsigned)scaler_stride));
 }
 
-template <int VEC, int NS, bool ISO, int SS>
+// PIPE: the slab loads of the next aggregator are in flight while this one is folded.  Costs 12 registers (occupancy),
+// so it is used for launches that fit in one wave anyway, where the serial load latency is what is left.
+template <int VEC, int NS, bool ISO, int SS, bool PIPE>
 __device__ __forceinline__ void bwd_fold(const RowPlan& P, const Acc<VEC, NS, ISO>& R, const Vec<VEC>& hv, const float* wsumv,
                                          int D, float ld, const float* __restrict__ grow, Vec<VEC>& c0, Vec<VEC>& c1,
                                          Vec<VEC>& gmx, Vec<VEC>& gmn, Vec<VEC> (&cs)[NS > 0 ? NS : 1], Vec<VEC>& dh) {
@@ -462,13 +544,29 @@ __device__ __forceinline__ void bwd_fold(const RowPlan& P, const Acc<VEC, NS, IS
   Vec<VEC> mean, var;
   row_mean_var<VEC, ISO>(R.sum, R.sq, fD, rD, mean, var);
   const int scaler_stride = P.A * P.Fg;
-  // software pipeline over the op table: the slabs of the next aggregator are in flight while this one is folded
-  Vec<VEC> gnext[DGN_MAX_SCALERS], gcur[DGN_MAX_SCALERS];
-  load_slabs<VEC, SS>(grow, P.order[0], P.Fg, scaler_stride, S, gnext);
-  auto next_G = [&](int pos) {
+  // sign(sum w m - W h) of every (slot, column), packed: bit s*VEC+i of `pos_m` / `neg_m`.  Frees the NS
+  // accumulators before the fold starts (registers decide the occupancy of this kernel).
+  unsigned pos_m = 0u, neg_m = 0u;
 #pragma unroll
-    for (int s = 0; s < DGN_MAX_SCALERS; ++s) gcur[s] = gnext[s];
-    if (pos + 1 < P.A) load_slabs<VEC, SS>(grow, P.order[pos + 1], P.Fg, scaler_stride, S, gnext);
+  for (int s = 0; s < NS; ++s) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const float sv = R.w[s].a[i] - wsumv[s] * hv.a[i];        // same expression as the forward
+      pos_m |= (sv > 0.f ? 1u : 0u) << (s * VEC + i);
+      neg_m |= (sv < 0.f ? 1u : 0u) << (s * VEC + i);
+    }
+  }
+  Vec<VEC> gnext[DGN_MAX_SCALERS];
+  if constexpr (PIPE) load_slabs<VEC, SS>(grow, P.order[0], P.Fg, scaler_stride, S, gnext);
+  auto next_G = [&](int pos) {
+    Vec<VEC> gcur[DGN_MAX_SCALERS];
+    if constexpr (PIPE) {
+#pragma unroll
+      for (int s = 0; s < DGN_MAX_SCALERS; ++s) gcur[s] = gnext[s];
+      if (pos + 1 < P.A) load_slabs<VEC, SS>(grow, P.order[pos + 1], P.Fg, scaler_stride, S, gnext);
+    } else {
+      load_slabs<VEC, SS>(grow, P.order[pos], P.Fg, scaler_stride, S, gcur);    // L2 hits: the row was prefetched
+    }
     Vec<VEC> G = vfill<VEC>(0.f);
 #pragma unroll
     for (int s = 0; s < DGN_MAX_SCALERS; ++s) {
@@ -508,7 +606,10 @@ __device__ __forceinline__ void bwd_fold(const RowPlan& P, const Acc<VEC, NS, IS
       if (op != OP_WSUM) {
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
-          if (op == OP_DX_ABS) G.a[i] *= sign0(R.w[s].a[i] - wsumv[s] * hv.a[i]);     // same expression as the forward
+          if (op == OP_DX_ABS) {
+            const unsigned b = 1u << (s * VEC + i);
+            G.a[i] = (pos_m & b) ? G.a[i] : ((neg_m & b) ? -G.a[i] : 0.f);
+          }
           dh.a[i] -= wsumv[s] * G.a[i];
         }
       }
@@ -518,8 +619,8 @@ __device__ __forceinline__ void bwd_fold(const RowPlan& P, const Acc<VEC, NS, IS
   }
 }
 
-template <int MODE, int VEC, int NS, bool ISO>
-__global__ void __launch_bounds__(256) agg_bwd_row_kernel(const __grid_constant__ RowArgs k) {
+template <int VEC, int NS, bool ISO, bool PIPE>
+__global__ void __launch_bounds__(ROW_THREADS, PIPE ? 4 : ROW_MINB_BWD) agg_bwd_row_kernel(const __grid_constant__ RowArgs k) {
   constexpr int NSA = NS > 0 ? NS : 1;
   const RowPlan& P = k.rp;
   const int v = blockIdx.x * blockDim.y + threadIdx.y;
@@ -528,11 +629,18 @@ __global__ void __launch_bounds__(256) agg_bwd_row_kernel(const __grid_constant_
   int tower = 0, cg = c;
   if (P.Fg != P.F) { tower = c / P.Fg; cg = c - tower * P.Fg; }
 
+  // The node's gradient row (S*A slabs per tower, contiguous) dominates this kernel's traffic and its address is
+  // known up front: one thread per node asks the L2 for it now, so the slab loads of the fold hit L2 instead of
+  // paying one DRAM round trip per aggregator.
+  if (k.pf_bytes > 0 && threadIdx.x == 0) {
+    const float* grow0 = k.g_out + (size_t)v * k.ld_out;
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(grow0), "r"(k.pf_bytes) : "memory");
+  }
   const int ovf0 = __ldg(k.ovf_ptr + v), ovf1 = __ldg(k.ovf_ptr + v + 1);
   const int e0 = __ldg(k.in_ptr + v);
   const Vec<VEC> hv = vload<VEC>(k.h_in + (size_t)v * k.ld_h + c);
   Vec<VEC> qv = vfill<VEC>(0.f);
-  if constexpr (MODE == DGN_MSG_AFFINE) {
+  if (k.q) {
     qv = vload<VEC>(k.q + (size_t)v * k.ld_q + c);
     if (k.q_bias) {
       const Vec<VEC> bv = vload<VEC>(k.q_bias + c);
@@ -542,8 +650,7 @@ __global__ void __launch_bounds__(256) agg_bwd_row_kernel(const __grid_constant_
   }
   const float ld = (P.S > 1) ? __ldg(k.log_deg + v) : 1.f;
   float wsumv[NSA];
-#pragma unroll
-  for (int s = 0; s < NSA; ++s) wsumv[s] = (s < P.n_slots) ? __ldg(k.wsum + (size_t)s * k.N + v) : 0.f;
+  load_wsum<NS>(k, v, wsumv);
   Vec<VEC> dh = vfill<VEC>(0.f);
   if (k.g_hcopy) dh = vload_stream<VEC>(k.g_hcopy + (size_t)v * k.ld_hc + (size_t)tower * k.hc_gs + cg);
   if (k.d_h_add) {
@@ -556,7 +663,7 @@ __global__ void __launch_bounds__(256) agg_bwd_row_kernel(const __grid_constant_
   Acc<VEC, NS, ISO> R;
   acc_clear(R);
   int D = 0;
-  walk_groups<MODE, VEC, NS>(k, v, c, qv, e0, ovf0, ovf1, [&](int, const Vec<VEC>& m, const float* wj) {
+  walk_groups<VEC, NS>(k, v, c, qv, e0, ovf0, ovf1, [&](int, const Vec<VEC>& m, const float* wj) {
     ++D;
     acc_add<VEC, NS, ISO>(R, m, wj);
   });
@@ -569,13 +676,14 @@ __global__ void __launch_bounds__(256) agg_bwd_row_kernel(const __grid_constant_
 #pragma unroll
     for (int s = 0; s < NSA; ++s) cs[s] = vfill<VEC>(0.f);
     const float* grow = k.g_out + (size_t)v * k.ld_out + (size_t)tower * k.out_gs + cg;
-    if (P.S == 3) bwd_fold<VEC, NS, ISO, 3>(P, R, hv, wsumv, D, ld, grow, c0, c1, gmx, gmn, cs, dh);
-    else if (P.S == 1) bwd_fold<VEC, NS, ISO, 1>(P, R, hv, wsumv, D, ld, grow, c0, c1, gmx, gmn, cs, dh);
-    else bwd_fold<VEC, NS, ISO, 0>(P, R, hv, wsumv, D, ld, grow, c0, c1, gmx, gmn, cs, dh);
+    asm volatile("" : "+l"(grow));                    // opaque base: slab addresses are base + 32-bit offset
+    if (P.S == 3) bwd_fold<VEC, NS, ISO, 3, PIPE>(P, R, hv, wsumv, D, ld, grow, c0, c1, gmx, gmn, cs, dh);
+    else if (P.S == 1) bwd_fold<VEC, NS, ISO, 1, PIPE>(P, R, hv, wsumv, D, ld, grow, c0, c1, gmx, gmn, cs, dh);
+    else bwd_fold<VEC, NS, ISO, 0, PIPE>(P, R, hv, wsumv, D, ld, grow, c0, c1, gmx, gmn, cs, dh);
 
     // ---- pass 2: per-edge message gradients (rows and weights come back from L1 / L2) -------------------
     unsigned given = 0u;          // bit i: max gradient of column i already routed; bit VEC+i: min
-    walk_groups<MODE, VEC, NS>(k, v, c, qv, e0, ovf0, ovf1, [&](int jg, const Vec<VEC>& m, const float* wj) {
+    walk_groups<VEC, NS>(k, v, c, qv, e0, ovf0, ovf1, [&](int jg, const Vec<VEC>& m, const float* wj) {
       Vec<VEC> dm;
 #pragma unroll
       for (int i = 0; i < VEC; ++i) {
@@ -617,38 +725,39 @@ static bool row_needs_iso(const RowPlan& P) {
   return false;
 }
 
-template <bool BWD, int MODE, int VEC, int NS>
+template <bool BWD, int VEC, int NS>
 static int launch_row_iso(const RowArgs& k, cudaStream_t st) {
   if (k.N == 0) return DGN_OK;
   const int chunks = k.rp.F / VEC;
-  if (chunks <= 0 || chunks > 256) return DGN_ERR_UNSUPPORTED;
-  const dim3 block((unsigned)chunks, (unsigned)(256 / chunks > 0 ? 256 / chunks : 1));
+  if (chunks <= 0 || chunks > ROW_THREADS) return DGN_ERR_UNSUPPORTED;
+  const dim3 block((unsigned)chunks, (unsigned)(ROW_THREADS / chunks));
   const unsigned grid = (unsigned)((k.N + block.y - 1) / block.y);
   const bool iso = row_needs_iso(k.rp);
   if constexpr (BWD) {
-    if (iso) agg_bwd_row_kernel<MODE, VEC, NS, true><<<grid, block, 0, st>>>(k);
-    else agg_bwd_row_kernel<MODE, VEC, NS, false><<<grid, block, 0, st>>>(k);
+    // one wave at the lean kernel's occupancy (6 CTAs / SM): latency, not occupancy, is what is left -> pipelined fold
+    static const int force_pipe = [] { const char* e = getenv("DGN_ROW_PIPE"); return e ? atoi(e) : -1; }();
+    const bool pipe = force_pipe >= 0 ? force_pipe != 0 : grid <= 148u * 6u;
+    if (pipe) {
+      if (iso) agg_bwd_row_kernel<VEC, NS, true, true><<<grid, block, 0, st>>>(k);
+      else agg_bwd_row_kernel<VEC, NS, false, true><<<grid, block, 0, st>>>(k);
+    } else {
+      if (iso) agg_bwd_row_kernel<VEC, NS, true, false><<<grid, block, 0, st>>>(k);
+      else agg_bwd_row_kernel<VEC, NS, false, false><<<grid, block, 0, st>>>(k);
+    }
   } else {
-    if (iso) agg_fwd_row_kernel<MODE, VEC, NS, true><<<grid, block, 0, st>>>(k);
-    else agg_fwd_row_kernel<MODE, VEC, NS, false><<<grid, block, 0, st>>>(k);
+    if (iso) agg_fwd_row_kernel<VEC, NS, true><<<grid, block, 0, st>>>(k);
+    else agg_fwd_row_kernel<VEC, NS, false><<<grid, block, 0, st>>>(k);
   }
   return cudaGetLastError() == cudaSuccess ? DGN_OK : DGN_ERR_CUDA;
 }
 
-template <bool BWD, int MODE, int VEC>
+template <bool BWD, int VEC>
 static int launch_row_slots(const RowArgs& k, cudaStream_t st) {
   const int ns = k.rp.n_slots;
-  if (ns == 0) return launch_row_iso<BWD, MODE, VEC, 0>(k, st);
-  if (ns <= 2) return launch_row_iso<BWD, MODE, VEC, 2>(k, st);
-  if (ns <= 4) return launch_row_iso<BWD, MODE, VEC, 4>(k, st);
-  return launch_row_iso<BWD, MODE, VEC, 8>(k, st);
-}
-
-template <bool BWD, int VEC>
-static int launch_row_mode(const RowArgs& k, cudaStream_t st) {
-  if (k.mode == DGN_MSG_SOURCE) return launch_row_slots<BWD, DGN_MSG_SOURCE, VEC>(k, st);
-  if (k.mode == DGN_MSG_AFFINE) return launch_row_slots<BWD, DGN_MSG_AFFINE, VEC>(k, st);
-  return launch_row_slots<BWD, DGN_MSG_DENSE, VEC>(k, st);
+  if (ns == 0) return launch_row_iso<BWD, VEC, 0>(k, st);
+  if (ns <= 2) return launch_row_iso<BWD, VEC, 2>(k, st);
+  if (ns <= 4) return launch_row_iso<BWD, VEC, 4>(k, st);
+  return launch_row_iso<BWD, VEC, 8>(k, st);
 }
 
 static int fill_row_args(const KernelArgs& ka, const DgnAggSpec* spec, const DgnField* f, RowArgs& k) {
@@ -656,7 +765,8 @@ static int fill_row_args(const KernelArgs& ka, const DgnAggSpec* spec, const Dgn
   FieldPlan fp;
   if (int rc = make_row_plan(spec, fp, &k.rp)) return rc;
   if (!f->groups || !f->ovf_ptr || f->n_slots != fp.n_slots || (fp.n_slots > 0 && !f->wsum)) return DGN_ERR_INVALID;
-  if (reinterpret_cast<uintptr_t>(f->groups) % 16 != 0) return DGN_ERR_ALIGNMENT;
+  if (reinterpret_cast<uintptr_t>(f->groups) % 16 != 0 || reinterpret_cast<uintptr_t>(f->wsum) % 16 != 0)
+    return DGN_ERR_ALIGNMENT;
   k.N = ka.N; k.mode = ka.mode; k.gstride = 1 + fp.n_slots;
   k.in_ptr = ka.in_ptr; k.in_eid = ka.in_eid; k.ovf_ptr = f->ovf_ptr;
   k.groups = reinterpret_cast<const float4*>(f->groups); k.wsum = f->wsum; k.log_deg = ka.log_deg;
@@ -667,23 +777,29 @@ static int fill_row_args(const KernelArgs& ka, const DgnAggSpec* spec, const Dgn
   k.g_out = ka.g_out; k.g_hcopy = ka.g_hcopy;
   k.d_q = ka.d_q; k.ld_dq = ka.ld_dq; k.d_r = ka.d_r; k.ld_dr = ka.ld_dr; k.d_h = ka.d_h; k.ld_dh = ka.ld_dh;
   k.d_h_add = ka.d_h_add; k.ld_dha = ka.ld_dha; k.edge_ws = ka.edge_ws;
+  if (k.g_out) {
+    static const bool pf_on = [] { const char* e = getenv("DGN_ROW_NO_PREFETCH"); return !(e && atoi(e) != 0); }();
+    const long long row = ((long long)(k.rp.F / k.rp.Fg - 1) * k.out_gs + (long long)k.rp.S * k.rp.A * k.rp.Fg) * 4;
+    if (pf_on && row % 16 == 0 && (k.ld_out % 4) == 0 && reinterpret_cast<uintptr_t>(k.g_out) % 16 == 0 && row < (1 << 20))
+      k.pf_bytes = (int)row;
+  }
   return DGN_OK;
 }
 
 int launch_forward_row(const KernelArgs& ka, const DgnAggSpec* spec, const DgnField* f, int vec, cudaStream_t st) {
   RowArgs k;
   if (int rc = fill_row_args(ka, spec, f, k)) return rc;
-  if (vec == 4) return launch_row_mode<false, 4>(k, st);
-  if (vec == 2) return launch_row_mode<false, 2>(k, st);
-  return launch_row_mode<false, 1>(k, st);
+  if (vec == 4) return launch_row_slots<false, 4>(k, st);
+  if (vec == 2) return launch_row_slots<false, 2>(k, st);
+  return launch_row_slots<false, 1>(k, st);
 }
 
 int launch_backward_row_dst(const KernelArgs& ka, const DgnAggSpec* spec, const DgnField* f, int vec, cudaStream_t st) {
   RowArgs k;
   if (int rc = fill_row_args(ka, spec, f, k)) return rc;
-  if (vec == 4) return launch_row_mode<true, 4>(k, st);
-  if (vec == 2) return launch_row_mode<true, 2>(k, st);
-  return launch_row_mode<true, 1>(k, st);
+  if (vec == 4) return launch_row_slots<true, 4>(k, st);
+  if (vec == 2) return launch_row_slots<true, 2>(k, st);
+  return launch_row_slots<true, 1>(k, st);
 }
 
 }  // namespace dgn

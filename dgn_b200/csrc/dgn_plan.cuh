@@ -262,12 +262,6 @@ int launch_backward_src(const KernelArgs& k, int vec, float* d_x, int ld_dx, con
 int launch_forward_row(const KernelArgs& k, const DgnAggSpec* spec, const DgnField* f, int vec, cudaStream_t st);
 int launch_backward_row_dst(const KernelArgs& k, const DgnAggSpec* spec, const DgnField* f, int vec, cudaStream_t st);
 
-// Tile kernels (dgn_agg_tile.cu): the fast path.  Return DGN_ERR_UNSUPPORTED when they do not cover the request
-// (softmax aggregators, F/VEC > 256) - the generic kernels above then take over.  DGN_NO_TILE=1 disables them.
-int launch_forward_tile(const KernelArgs& k, int vec, cudaStream_t st);
-int launch_backward_tile_dst(const KernelArgs& k, int vec, cudaStream_t st);
-bool tile_kernels_enabled();
-
 // Picks the vector width: the widest the operands' alignment allows; `narrow_small` lets small launches
 // (that would not fill the 148 SMs) use 8 B lanes for more, shorter threads.  DGN_FORCE_VEC overrides.
 int choose_vec(int max_vec, long long n_nodes, int n_feat, bool narrow_small);

@@ -243,7 +243,7 @@ class BatchedGraph:
             _lib.check(min(ns, 0), "dgn_field_slots")
             dev = self._t["ovf_ptr"].device
             groups = torch.empty(self.n_groups * (1 + ns) * 4, device=dev, dtype=torch.float32)
-            wsum = torch.empty(max(ns * self._n, 1), device=dev, dtype=torch.float32)
+            wsum = torch.empty(max((ns + 3) // 4 * 4 * self._n, 4), device=dev, dtype=torch.float32)
             cf = _lib.DgnField(self.n_groups, ns, self._t["ovf_ptr"].data_ptr(), groups.data_ptr(),
                                wsum.data_ptr() if ns > 0 else None)
             ent = {"c": cf, "groups": groups, "wsum": wsum, "stamp": None}

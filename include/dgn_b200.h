@@ -112,7 +112,8 @@ typedef struct {
   int32_t n_slots;         /* dgn_field_slots(spec)                                                            */
   const int32_t* ovf_ptr;  /* [n_nodes+1] from dgn_build_groups_host                                           */
   float* groups;           /* [n_groups][1 + n_slots][4]                                                       */
-  float* wsum;             /* [n_slots][n_nodes]: sum of w_s over the in-edges of every node (NULL if n_slots == 0) */
+  float* wsum;             /* [n_nodes][4*ceil(n_slots/4)]: sum of w_s over the in-edges of every node, 16 B aligned
+                              (NULL if n_slots == 0)                                                           */
 } DgnField;
 
 /* Which aggregators / scalers to compute: the AGGREGATORS / SCALERS names resolved to op-codes. */

@@ -268,12 +268,11 @@ def test_too_many_slots_is_reported():
         aggregate(g, spec, _lib.MSG_SOURCE, x, g.ndata["eig"], x=x)
 
 
-@pytest.mark.parametrize("env", [{"DGN_NO_FIELD": "1"}, {"DGN_NO_FIELD": "1", "DGN_NO_TILE": "1"}],
-                         ids=["tile_kernels", "generic_kernels"])
-def test_in_kernel_weight_paths_still_match_oracle(env):
+def test_in_kernel_weight_path_still_matches_oracle():
     """The row kernels over the precomputed eigen-field are the default path.  DGN_NO_FIELD=1 selects the kernels
-    that derive the eigen-weights inside every launch (DgnAggIO.field == NULL): the shared-memory tile kernels, or -
-    with DGN_NO_TILE=1 - the generic per-(node, chunk) kernels.  Re-run the oracle comparison on both."""
+    that derive the eigen-weights inside every launch (DgnAggIO.field == NULL, for callers that aggregate a batch
+    only once).  Re-run the oracle comparison on them."""
+    env = {"DGN_NO_FIELD": "1"}
     import os
     import subprocess
     import sys
