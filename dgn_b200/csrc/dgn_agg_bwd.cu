@@ -12,6 +12,7 @@
 //
 // Source-side kernel: d_x[u] = sum over out-edges of dm (by-source CSR), a deterministic gather
 // instead of float atomics, so training is bit-reproducible run to run.
+#include "dgn_launch.cuh"
 #include "dgn_plan.cuh"
 
 namespace dgn {
@@ -226,6 +227,7 @@ __global__ void __launch_bounds__(256) agg_bwd_src_kernel(int N, int F, int chun
                                                           const int32_t* __restrict__ out_slot,
                                                           const float* __restrict__ ws, float* __restrict__ d_x,
                                                           int ld_dx, const float* __restrict__ addend, int ld_add) {
+  pdl_prologue();
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int u = (int)(tid / chunks);
   if (u >= N) return;
@@ -303,14 +305,11 @@ int launch_backward_src(const KernelArgs& k, int vec, float* d_x, int ld_dx, con
   const int block = 256;
   const unsigned grid = (unsigned)((threads + block - 1) / block);
   if (vec == 4)
-    agg_bwd_src_kernel<4><<<grid, block, 0, st>>>(k.N, k.plan.F, k.plan.chunks, k.out_ptr, k.out_slot, k.edge_ws, d_x,
-                                                  ld_dx, addend, ld_add);
+    launch_pdl(agg_bwd_src_kernel<4>, dim3(grid), dim3(block), 0, st, k.N, k.plan.F, k.plan.chunks, k.out_ptr, k.out_slot, k.edge_ws, d_x, ld_dx, addend, ld_add);
   else if (vec == 2)
-    agg_bwd_src_kernel<2><<<grid, block, 0, st>>>(k.N, k.plan.F, k.plan.chunks, k.out_ptr, k.out_slot, k.edge_ws, d_x,
-                                                  ld_dx, addend, ld_add);
+    launch_pdl(agg_bwd_src_kernel<2>, dim3(grid), dim3(block), 0, st, k.N, k.plan.F, k.plan.chunks, k.out_ptr, k.out_slot, k.edge_ws, d_x, ld_dx, addend, ld_add);
   else
-    agg_bwd_src_kernel<1><<<grid, block, 0, st>>>(k.N, k.plan.F, k.plan.chunks, k.out_ptr, k.out_slot, k.edge_ws, d_x,
-                                                  ld_dx, addend, ld_add);
+    launch_pdl(agg_bwd_src_kernel<1>, dim3(grid), dim3(block), 0, st, k.N, k.plan.F, k.plan.chunks, k.out_ptr, k.out_slot, k.edge_ws, d_x, ld_dx, addend, ld_add);
   return cudaGetLastError() == cudaSuccess ? DGN_OK : DGN_ERR_CUDA;
 }
 

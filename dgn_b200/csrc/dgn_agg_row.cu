@@ -17,6 +17,7 @@
 // op table (isotropic first, then slot by slot) so that every accumulator keeps a static register name.
 #include <stdlib.h>
 
+#include "dgn_launch.cuh"
 #include "dgn_plan.cuh"
 
 extern thread_local cudaError_t g_dgn_last_cuda;
@@ -181,6 +182,7 @@ struct FieldArgs {
 };
 
 __global__ void __launch_bounds__(256) field_build_kernel(const __grid_constant__ FieldArgs k) {
+  pdl_prologue();
   const int ns = k.fp.n_slots, lanes = ns > 0 ? ns : 1, gstride = 1 + ns;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int v = (int)(t / lanes), s = (int)(t - (long long)v * lanes);
@@ -267,7 +269,8 @@ __device__ __forceinline__ float div_by(float x, float fD, float rD) {
 // Walks the in-edge groups of node v: the node-aligned first group, then its overflow groups.  fn(jg, m, wts) is
 // called for every real in-edge in mailbox order with its message (this thread's columns) and slot weights.
 // The message mode is a launch-uniform runtime branch: SOURCE is AFFINE with q = 0 (qv stays zero), DENSE reads R[eid].
-template <int VEC, int NS, typename Fn>
+// WIDE: all 4 gathers of a group in flight at once (latency-optimised variant for single-wave launches).
+template <int VEC, int NS, bool WIDE, typename Fn>
 __device__ __forceinline__ void walk_groups(const RowArgs& k, int v, int c, const Vec<VEC>& qv, int e0, int ovf0, int ovf1,
                                             Fn&& fn) {
   constexpr int NSA = NS > 0 ? NS : 1;
@@ -277,6 +280,42 @@ __device__ __forceinline__ void walk_groups(const RowArgs& k, int v, int c, cons
   while (true) {
     const float4* gp = k.groups + (size_t)g * k.gstride;
     const int4 su4 = __ldg(reinterpret_cast<const int4*>(gp));
+    if constexpr (WIDE) {
+      float4 wv[NSA];
+#pragma unroll
+      for (int s = 0; s < NS; ++s) wv[s] = (s < k.rp.n_slots) ? __ldg(gp + 1 + s) : make_float4(0.f, 0.f, 0.f, 0.f);
+      Vec<VEC> m[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int u = lane_of(su4, j);
+        if (dense) {
+          int id = e0 + jbase + j;
+          if (k.in_eid && u >= 0) id = __ldg(k.in_eid + id);
+          m[j] = vload<VEC>(k.r + (size_t)(u >= 0 ? id : 0) * k.ld_r + c);
+        } else {
+          m[j] = vload<VEC>(k.x + (size_t)max(u, 0) * k.ld_x + c);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (lane_of(su4, j) >= 0) {
+          Vec<VEC> mm = m[j];
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) mm.a[i] += qv.a[i];
+          if (edge_term) {
+            const int e = e0 + jbase + j;
+            const int id = k.in_eid ? __ldg(k.in_eid + e) : e;
+            const Vec<VEC> rv = vload<VEC>(k.r + (size_t)id * k.ld_r + c);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) mm.a[i] += rv.a[i];
+          }
+          float wj[NSA];
+#pragma unroll
+          for (int s = 0; s < NSA; ++s) wj[s] = lane_of(wv[s], j);
+          fn(jbase + j, mm, wj);
+        }
+      }
+    } else {
     // the group is consumed as two pairs of in-edge slots: half the staging registers of a 4-wide pass (occupancy is
     // what hides the gather latency), and no gathers at all for the padding pair of a degree <= 2 node
 #pragma unroll
@@ -318,6 +357,7 @@ __device__ __forceinline__ void walk_groups(const RowArgs& k, int v, int c, cons
           fn(jbase + 2 * h + j, mm, wj);
         }
       }
+    }
     }
     if (o >= ovf1) break;
     g = k.N + o;
@@ -472,8 +512,10 @@ __device__ __forceinline__ void fwd_epilogue(const RowPlan& P, const Acc<VEC, NS
   }
 }
 
-template <int VEC, int NS, bool ISO>
-__global__ void __launch_bounds__(ROW_THREADS, ROW_MINB_FWD) agg_fwd_row_kernel(const __grid_constant__ RowArgs k) {
+// LAT = latency-optimised variant for launches that fit in one wave: wide gathers, no register cap.
+template <int VEC, int NS, bool ISO, bool LAT>
+__global__ void __launch_bounds__(ROW_THREADS, LAT ? 4 : ROW_MINB_FWD) agg_fwd_row_kernel(const __grid_constant__ RowArgs k) {
+  pdl_prologue();
   constexpr int NSA = NS > 0 ? NS : 1;
   const RowPlan& P = k.rp;
   const int v = blockIdx.x * blockDim.y + threadIdx.y;
@@ -503,7 +545,7 @@ __global__ void __launch_bounds__(ROW_THREADS, ROW_MINB_FWD) agg_fwd_row_kernel(
   Acc<VEC, NS, ISO> R;
   acc_clear(R);
   int D = 0;
-  walk_groups<VEC, NS>(k, v, c, qv, e0, ovf0, ovf1, [&](int, const Vec<VEC>& m, const float* wj) {
+  walk_groups<VEC, NS, LAT>(k, v, c, qv, e0, ovf0, ovf1, [&](int, const Vec<VEC>& m, const float* wj) {
     ++D;
     acc_add<VEC, NS, ISO>(R, m, wj);
   });
@@ -619,8 +661,9 @@ __device__ __forceinline__ void bwd_fold(const RowPlan& P, const Acc<VEC, NS, IS
   }
 }
 
-template <int VEC, int NS, bool ISO, bool PIPE>
-__global__ void __launch_bounds__(ROW_THREADS, PIPE ? 4 : ROW_MINB_BWD) agg_bwd_row_kernel(const __grid_constant__ RowArgs k) {
+template <int VEC, int NS, bool ISO, bool LAT>
+__global__ void __launch_bounds__(ROW_THREADS, LAT ? 4 : ROW_MINB_BWD) agg_bwd_row_kernel(const __grid_constant__ RowArgs k) {
+  pdl_prologue();
   constexpr int NSA = NS > 0 ? NS : 1;
   const RowPlan& P = k.rp;
   const int v = blockIdx.x * blockDim.y + threadIdx.y;
@@ -663,7 +706,7 @@ __global__ void __launch_bounds__(ROW_THREADS, PIPE ? 4 : ROW_MINB_BWD) agg_bwd_
   Acc<VEC, NS, ISO> R;
   acc_clear(R);
   int D = 0;
-  walk_groups<VEC, NS>(k, v, c, qv, e0, ovf0, ovf1, [&](int, const Vec<VEC>& m, const float* wj) {
+  walk_groups<VEC, NS, LAT>(k, v, c, qv, e0, ovf0, ovf1, [&](int, const Vec<VEC>& m, const float* wj) {
     ++D;
     acc_add<VEC, NS, ISO>(R, m, wj);
   });
@@ -677,13 +720,13 @@ __global__ void __launch_bounds__(ROW_THREADS, PIPE ? 4 : ROW_MINB_BWD) agg_bwd_
     for (int s = 0; s < NSA; ++s) cs[s] = vfill<VEC>(0.f);
     const float* grow = k.g_out + (size_t)v * k.ld_out + (size_t)tower * k.out_gs + cg;
     asm volatile("" : "+l"(grow));                    // opaque base: slab addresses are base + 32-bit offset
-    if (P.S == 3) bwd_fold<VEC, NS, ISO, 3, PIPE>(P, R, hv, wsumv, D, ld, grow, c0, c1, gmx, gmn, cs, dh);
-    else if (P.S == 1) bwd_fold<VEC, NS, ISO, 1, PIPE>(P, R, hv, wsumv, D, ld, grow, c0, c1, gmx, gmn, cs, dh);
-    else bwd_fold<VEC, NS, ISO, 0, PIPE>(P, R, hv, wsumv, D, ld, grow, c0, c1, gmx, gmn, cs, dh);
+    if (P.S == 3) bwd_fold<VEC, NS, ISO, 3, LAT>(P, R, hv, wsumv, D, ld, grow, c0, c1, gmx, gmn, cs, dh);
+    else if (P.S == 1) bwd_fold<VEC, NS, ISO, 1, LAT>(P, R, hv, wsumv, D, ld, grow, c0, c1, gmx, gmn, cs, dh);
+    else bwd_fold<VEC, NS, ISO, 0, LAT>(P, R, hv, wsumv, D, ld, grow, c0, c1, gmx, gmn, cs, dh);
 
     // ---- pass 2: per-edge message gradients (rows and weights come back from L1 / L2) -------------------
     unsigned given = 0u;          // bit i: max gradient of column i already routed; bit VEC+i: min
-    walk_groups<VEC, NS>(k, v, c, qv, e0, ovf0, ovf1, [&](int jg, const Vec<VEC>& m, const float* wj) {
+    walk_groups<VEC, NS, LAT>(k, v, c, qv, e0, ovf0, ovf1, [&](int jg, const Vec<VEC>& m, const float* wj) {
       Vec<VEC> dm;
 #pragma unroll
       for (int i = 0; i < VEC; ++i) {
@@ -733,20 +776,26 @@ static int launch_row_iso(const RowArgs& k, cudaStream_t st) {
   const dim3 block((unsigned)chunks, (unsigned)(ROW_THREADS / chunks));
   const unsigned grid = (unsigned)((k.N + block.y - 1) / block.y);
   const bool iso = row_needs_iso(k.rp);
+  // A launch that fits in one wave at the lean kernels' occupancy is bound by the latency of one thread's dependent
+  // chain, not by occupancy: it takes the LAT variants (wide gathers, pipelined fold).  DGN_ROW_LAT=0/1 overrides.
+  static const int force_lat = [] { const char* e = getenv("DGN_ROW_LAT"); return e ? atoi(e) : -1; }();
+  const bool lat = force_lat >= 0 ? force_lat != 0 : grid <= 148u * 6u;
   if constexpr (BWD) {
-    // one wave at the lean kernel's occupancy (6 CTAs / SM): latency, not occupancy, is what is left -> pipelined fold
-    static const int force_pipe = [] { const char* e = getenv("DGN_ROW_PIPE"); return e ? atoi(e) : -1; }();
-    const bool pipe = force_pipe >= 0 ? force_pipe != 0 : grid <= 148u * 6u;
-    if (pipe) {
-      if (iso) agg_bwd_row_kernel<VEC, NS, true, true><<<grid, block, 0, st>>>(k);
-      else agg_bwd_row_kernel<VEC, NS, false, true><<<grid, block, 0, st>>>(k);
+    if (lat) {
+      if (iso) launch_pdl(agg_bwd_row_kernel<VEC, NS, true, true>, grid, block, 0, st, k);
+      else launch_pdl(agg_bwd_row_kernel<VEC, NS, false, true>, grid, block, 0, st, k);
     } else {
-      if (iso) agg_bwd_row_kernel<VEC, NS, true, false><<<grid, block, 0, st>>>(k);
-      else agg_bwd_row_kernel<VEC, NS, false, false><<<grid, block, 0, st>>>(k);
+      if (iso) launch_pdl(agg_bwd_row_kernel<VEC, NS, true, false>, grid, block, 0, st, k);
+      else launch_pdl(agg_bwd_row_kernel<VEC, NS, false, false>, grid, block, 0, st, k);
     }
   } else {
-    if (iso) agg_fwd_row_kernel<VEC, NS, true><<<grid, block, 0, st>>>(k);
-    else agg_fwd_row_kernel<VEC, NS, false><<<grid, block, 0, st>>>(k);
+    if (lat) {
+      if (iso) launch_pdl(agg_fwd_row_kernel<VEC, NS, true, true>, grid, block, 0, st, k);
+      else launch_pdl(agg_fwd_row_kernel<VEC, NS, false, true>, grid, block, 0, st, k);
+    } else {
+      if (iso) launch_pdl(agg_fwd_row_kernel<VEC, NS, true, false>, grid, block, 0, st, k);
+      else launch_pdl(agg_fwd_row_kernel<VEC, NS, false, false>, grid, block, 0, st, k);
+    }
   }
   return cudaGetLastError() == cudaSuccess ? DGN_OK : DGN_ERR_CUDA;
 }
@@ -841,7 +890,7 @@ extern "C" int dgn_field_build(const DgnGraph* g, const DgnAggSpec* spec, const 
   k.eig = eig; k.ld_eig = ld_eig; k.groups = f->groups; k.wsum = f->wsum;
   if (k.N == 0) return DGN_OK;
   const long long threads = (long long)k.N * (k.fp.n_slots > 0 ? k.fp.n_slots : 1);
-  field_build_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(k);
+  launch_pdl(field_build_kernel, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, k);
   if (cudaGetLastError() != cudaSuccess) { g_dgn_last_cuda = cudaPeekAtLastError(); return DGN_ERR_CUDA; }
   return DGN_OK;
 }

@@ -21,6 +21,7 @@
 #include <stdint.h>
 
 #include "../../include/dgn_b200.h"
+#include "dgn_launch.cuh"
 
 namespace dgn {
 
@@ -154,6 +155,7 @@ __device__ __forceinline__ void store_tile(const float4 (&vv)[ROWS * BK / 4 / kL
 
 template <bool A_K, bool B_K>
 __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tf32x3_kernel(const GemmArgs g) {
+  pdl_prologue();
   extern __shared__ unsigned char raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * STAGE_BYTES);
@@ -333,6 +335,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tf32x3_kernel(const Gemm
 // Sums the split-K partial tiles in split order (deterministic) and writes / accumulates C.
 // One thread per (row, 4-column chunk) of the M x N result.
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const GemmArgs g, int m_tiles, int n_tiles) {
+  pdl_prologue();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int n4 = (g.N + 3) / 4;
   if (idx >= (long long)g.M * n4) return;
@@ -412,7 +415,7 @@ extern "C" int dgn_gemm_tf32x3(int32_t M, int32_t N, int32_t K, const float* A, 
   do {                                                                                                           \
     static bool attr = false;                                                                                    \
     if (!attr) { e = cudaFuncSetAttribute(gemm_tf32x3_kernel<AK, BK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM); attr = true; } \
-    if (e == cudaSuccess) gemm_tf32x3_kernel<AK, BK_><<<grid, kGemmThreads, GEMM_SMEM, st>>>(g);                  \
+    if (e == cudaSuccess) launch_pdl(gemm_tf32x3_kernel<AK, BK_>, grid, dim3(kGemmThreads), GEMM_SMEM, st, g);                  \
   } while (0)
   if (a_kmajor && b_kmajor) LAUNCH(true, true);
   else if (a_kmajor && !b_kmajor) LAUNCH(true, false);
@@ -422,7 +425,7 @@ extern "C" int dgn_gemm_tf32x3(int32_t M, int32_t N, int32_t K, const float* A, 
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e == cudaSuccess && splits > 1) {
     const long long threads = (long long)M * ((N + 3) / 4);
-    splitk_reduce_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(g, mt, nt);
+    launch_pdl(splitk_reduce_kernel, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, st, g, mt, nt);
     e = cudaGetLastError();
   }
   if (e != cudaSuccess) { g_dgn_last_cuda = e; return DGN_ERR_CUDA; }

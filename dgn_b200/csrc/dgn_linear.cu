@@ -10,6 +10,7 @@
 #include <stdint.h>
 
 #include "../../include/dgn_b200.h"
+#include "dgn_launch.cuh"
 
 namespace dgn {
 
@@ -20,6 +21,7 @@ __global__ void __launch_bounds__(LT) pair_linear_fwd_kernel(int N, int Fi, int 
                                                              const float* __restrict__ W, int ld_w,
                                                              float* __restrict__ P, int ld_p, float* __restrict__ Q,
                                                              int ld_q) {
+  pdl_prologue();
   extern __shared__ __align__(16) float sm[];
   float* ht = sm;                              // [Fi][LR]   h tile, transposed
   float* wp = ht + Fi * LR;                    // [Fi][LC]   W_src block, transposed
@@ -67,6 +69,7 @@ __global__ void __launch_bounds__(LT) pair_linear_bwd_kernel(int N, int Fi, int 
                                                              const float* __restrict__ dQ, int ld_q,
                                                              const float* __restrict__ W, int ld_w,
                                                              float* __restrict__ d_h, int ld_dh) {
+  pdl_prologue();
   extern __shared__ __align__(16) float sm[];
   float* pt = sm;                              // [Fo][LR]  dP tile, transposed
   float* qt = pt + Fo * LR;                    // [Fo][LR]  dQ tile, transposed
@@ -138,8 +141,7 @@ extern "C" int dgn_pair_linear_forward(int32_t N, int32_t Fi, int32_t Fo, const 
   if (N == 0) return DGN_OK;
   const size_t smem = (size_t)(Fi * LR + 2 * Fi * LC) * sizeof(float);
   if (int rc = lin_attr(pair_linear_fwd_kernel, smem)) return rc;
-  pair_linear_fwd_kernel<<<dim3((N + LR - 1) / LR, (Fo + LC - 1) / LC), LT, smem, (cudaStream_t)stream>>>(
-      N, Fi, Fo, h, ld_h, W, ld_w, P, ld_p, Q, ld_q);
+  launch_pdl(pair_linear_fwd_kernel, dim3((N + LR - 1) / LR, (Fo + LC - 1) / LC), dim3(LT), smem, (cudaStream_t)stream, N, Fi, Fo, h, ld_h, W, ld_w, P, ld_p, Q, ld_q);
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { g_dgn_last_cuda = e; return DGN_ERR_CUDA; }
   return DGN_OK;
@@ -153,8 +155,7 @@ extern "C" int dgn_pair_linear_backward(int32_t N, int32_t Fi, int32_t Fo, const
   if (N == 0) return DGN_OK;
   const size_t smem = (size_t)(2 * Fo * LR + 2 * Fo * LC) * sizeof(float);
   if (int rc = lin_attr(pair_linear_bwd_kernel, smem)) return rc;
-  pair_linear_bwd_kernel<<<dim3((N + LR - 1) / LR, (Fi + LC - 1) / LC), LT, smem, (cudaStream_t)stream>>>(
-      N, Fi, Fo, dP, ld_p, dQ, ld_q, W, ld_w, d_h, ld_dh);
+  launch_pdl(pair_linear_bwd_kernel, dim3((N + LR - 1) / LR, (Fi + LC - 1) / LC), dim3(LT), smem, (cudaStream_t)stream, N, Fi, Fo, dP, ld_p, dQ, ld_q, W, ld_w, d_h, ld_dh);
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { g_dgn_last_cuda = e; return DGN_ERR_CUDA; }
   return DGN_OK;

@@ -14,6 +14,7 @@
 #include <stdint.h>
 
 #include "../../include/dgn_b200.h"
+#include "dgn_launch.cuh"
 
 namespace dgn {
 
@@ -40,6 +41,7 @@ __device__ __forceinline__ void welford_merge(float& n, float& mean, float& m2, 
 
 // partial statistics of z = y * snorm for one (row slab, 32-column tile)
 __global__ void __launch_bounds__(kTX * kTY) norm_stats_kernel(const DgnNormArgs a) {
+  pdl_prologue();
   const int n = rows_of(a);
   const int col = blockIdx.y * kTX + threadIdx.x;
   int r0, r1;
@@ -103,6 +105,7 @@ __device__ __forceinline__ void merged_stats(const DgnNormArgs& a, int n, int co
 }
 
 __global__ void __launch_bounds__(kTX * kTY) norm_apply_kernel(const DgnNormArgs a) {
+  pdl_prologue();
   const int n = rows_of(a);
   const int col = blockIdx.y * kTX + threadIdx.x;
   __shared__ float s_mean[kTX], s_rstd[kTX];
@@ -166,6 +169,7 @@ constexpr int kBwdSums = 5;   // sum g1, sum g1*xhat, sum s*g1, sum s, sum s*xha
 // The five column sums are accumulated and merged in fp64: d_bias (and to a lesser degree d_gamma / d_beta)
 // are small differences of large sums, and fp32 partial sums would leave ~1e-5 relative noise in them.
 __global__ void __launch_bounds__(kTX * kTY) norm_bwd_reduce_kernel(const DgnNormArgs a, const DgnNormGrad g) {
+  pdl_prologue();
   const int n = rows_of(a);
   const int col = blockIdx.y * kTX + threadIdx.x;
   int r0, r1;
@@ -202,6 +206,7 @@ __global__ void __launch_bounds__(kTX * kTY) norm_bwd_reduce_kernel(const DgnNor
 }
 
 __global__ void __launch_bounds__(kTX * kTY) norm_bwd_apply_kernel(const DgnNormArgs a, const DgnNormGrad g) {
+  pdl_prologue();
   const int n = rows_of(a);
   const int col = blockIdx.y * kTX + threadIdx.x;
   __shared__ float s_b[kTX], s_g[kTX];
@@ -285,6 +290,7 @@ __global__ void __launch_bounds__(kTX * kTY) embedding_bwd_kernel(int n_rows, in
                                                                   float* __restrict__ dw, int ld_w,
                                                                   const int32_t* __restrict__ n_rows_dev,
                                                                   float* __restrict__ ws, unsigned* __restrict__ counters) {
+  pdl_prologue();
   extern __shared__ float tile[];                      // [kTY][vocab][kTX]
   __shared__ bool is_last;
   const int n = n_rows_dev ? *n_rows_dev : n_rows;
@@ -328,6 +334,7 @@ __global__ void __launch_bounds__(kTX * kTY) embedding_bwd_kernel(int n_rows, in
 // ---- readout -------------------------------------------------------------------------------------
 __global__ void readout_fwd_kernel(int n_graphs, const int32_t* __restrict__ gp, int C, const float* __restrict__ h,
                                    int ld_h, int op, float* __restrict__ out, int ld_o) {
+  pdl_prologue();
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
   const int gi = blockIdx.y;
   if (col >= C || gi >= n_graphs) return;
@@ -346,6 +353,7 @@ __global__ void readout_bwd_kernel(int n_graphs, const int32_t* __restrict__ gp,
                                    int ld_h, const float* __restrict__ out, int ld_o, int op,
                                    const float* __restrict__ g_out, int ld_go, float* __restrict__ d_h, int ld_dh,
                                    int n_rows_total) {
+  pdl_prologue();
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
   const int gi = blockIdx.y;
   if (col >= C) return;
@@ -375,6 +383,7 @@ __global__ void readout_bwd_kernel(int n_graphs, const int32_t* __restrict__ gp,
 __global__ void __launch_bounds__(256) adam_kernel(long long n, float* __restrict__ p, const float* __restrict__ g,
                                                    float* __restrict__ m, float* __restrict__ v, float lr, float b1,
                                                    float b2, float eps, float wd, int* __restrict__ state) {
+  pdl_prologue();
   const int t = state[0] + 1;
   const float c1 = 1.f - powf(b1, (float)t), c2 = 1.f - powf(b2, (float)t);
   const float step_size = lr / c1, inv_sqrt_c2 = rsqrtf(c2);
@@ -439,10 +448,10 @@ extern "C" int dgn_norm_forward(const DgnNormArgs* a, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const dim3 block(kTX, kTY);
   if (a->gamma && a->training) {
-    norm_stats_kernel<<<dim3(kParts, (a->n_cols + kTX - 1) / kTX), block, 0, st>>>(*a);
+    launch_pdl(norm_stats_kernel, dim3(kParts, (a->n_cols + kTX - 1) / kTX), block, 0, st, *a);
     if (int rc = check_launch()) return rc;
   }
-  norm_apply_kernel<<<norm_grid_apply(a), block, 0, st>>>(*a);
+  launch_pdl(norm_apply_kernel, norm_grid_apply(a), block, 0, st, *a);
   return check_launch();
 }
 
@@ -452,9 +461,9 @@ extern "C" int dgn_norm_backward(const DgnNormArgs* a, const DgnNormGrad* g, voi
   if (a->n_rows == 0) return DGN_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const dim3 block(kTX, kTY);
-  norm_bwd_reduce_kernel<<<dim3(kParts, (a->n_cols + kTX - 1) / kTX), block, 0, st>>>(*a, *g);
+  launch_pdl(norm_bwd_reduce_kernel, dim3(kParts, (a->n_cols + kTX - 1) / kTX), block, 0, st, *a, *g);
   if (int rc = check_launch()) return rc;
-  norm_bwd_apply_kernel<<<norm_grid_apply(a), block, 0, st>>>(*a, *g);
+  launch_pdl(norm_bwd_apply_kernel, norm_grid_apply(a), block, 0, st, *a, *g);
   return check_launch();
 }
 
@@ -471,8 +480,7 @@ extern "C" int dgn_embedding_backward(int32_t n_rows, int32_t n_cols, int32_t vo
     attr_set = true;
   }
   unsigned* counters = reinterpret_cast<unsigned*>(ws + (size_t)kEmbSlabs * vocab * n_cols);
-  embedding_bwd_kernel<<<dim3((n_cols + kTX - 1) / kTX, kEmbSlabs), dim3(kTX, kTY), smem, (cudaStream_t)stream>>>(
-      n_rows, n_cols, vocab, reinterpret_cast<const long long*>(idx), g, ld_g, d_weight, ld_w, n_rows_dev, ws, counters);
+  launch_pdl(embedding_bwd_kernel, dim3((n_cols + kTX - 1) / kTX, kEmbSlabs), dim3(kTX, kTY), smem, (cudaStream_t)stream, n_rows, n_cols, vocab, reinterpret_cast<const long long*>(idx), g, ld_g, d_weight, ld_w, n_rows_dev, ws, counters);
   return check_launch();
 }
 
@@ -481,8 +489,7 @@ extern "C" int dgn_readout_forward(int32_t n_graphs, const int32_t* graph_ptr, i
   if (n_graphs < 0 || n_cols <= 0 || !graph_ptr || !h || !out || op < 0 || op > 2) return DGN_ERR_INVALID;
   if (n_graphs == 0) return DGN_OK;
   const int block = 64;
-  readout_fwd_kernel<<<dim3((n_cols + block - 1) / block, n_graphs), block, 0, (cudaStream_t)stream>>>(
-      n_graphs, graph_ptr, n_cols, h, ld_h, op, out, ld_o);
+  launch_pdl(readout_fwd_kernel, dim3((n_cols + block - 1) / block, n_graphs), block, 0, (cudaStream_t)stream, n_graphs, graph_ptr, n_cols, h, ld_h, op, out, ld_o);
   return check_launch();
 }
 
@@ -493,8 +500,7 @@ extern "C" int dgn_readout_backward(int32_t n_graphs, const int32_t* graph_ptr, 
   if (op == 2 && (!h || !out)) return DGN_ERR_INVALID;
   if (n_graphs == 0) return DGN_OK;
   const int block = 64;
-  readout_bwd_kernel<<<dim3((n_cols + block - 1) / block, n_graphs + 1), block, 0, (cudaStream_t)stream>>>(
-      n_graphs, graph_ptr, n_cols, h, ld_h, out, ld_o, op, g_out, ld_go, d_h, ld_dh, n_rows_total);
+  launch_pdl(readout_bwd_kernel, dim3((n_cols + block - 1) / block, n_graphs + 1), block, 0, (cudaStream_t)stream, n_graphs, graph_ptr, n_cols, h, ld_h, out, ld_o, op, g_out, ld_go, d_h, ld_dh, n_rows_total);
   return check_launch();
 }
 
@@ -506,7 +512,6 @@ extern "C" int dgn_adam_step(int64_t n, float* param, const float* grad, float* 
     return DGN_ERR_ALIGNMENT;
   if (n == 0) return DGN_OK;
   const long long threads = (n + 3) / 4;
-  adam_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, param, grad, exp_avg, exp_avg_sq, lr,
-                                                                                  beta1, beta2, eps, weight_decay, state);
+  launch_pdl(adam_kernel, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, n, param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, state);
   return check_launch();
 }
