@@ -12,7 +12,9 @@ L=4, hidden 64, 10 aggregators x 3 scalers, k=2 eigenvectors).  Prints ONE JSON 
              and a D2H read of the loss, inside the timed region
 * roofline   fused aggregation kernels (forward + backward of one layer of the workload) timed alone with CUDA
              events (CUDA graph of 8 launches over rotating operand sets > L2), algorithmic bytes of SURVEY.md 8(d) /
-             DESIGN.md over the measured HBM copy peak (MEASURED_PEAKS.json)
+             DESIGN.md over the measured HBM copy peak (MEASURED_PEAKS.json).  `at_scale` repeats the measurement on
+             the same workload replicated 16x (2048 graphs): at 128 graphs one launch is a single wave of ~6 us, i.e.
+             launch-latency bound, the 16x figure shows what the kernels reach once the launch is HBM bound
 * cpu_baseline / --impl reference   the oracle port of the reference's python path on the host cores
 """
 from __future__ import annotations
@@ -170,7 +172,7 @@ def agg_bytes(N, E, F, A, S, r_ops, k_used):
     return fwd, bwd
 
 
-def kernel_roofline(graph, avg_log, device, rot=8, replays=10):
+def kernel_roofline(graph, avg_log, device, rot=8, replays=10, n_real=None, e_real=None):
     """Times dgn_agg_forward / dgn_agg_backward alone on the layer operands of the bench workload.
 
     ``rot`` operand sets are rotated inside one captured CUDA graph so that every launch finds its
@@ -181,7 +183,8 @@ def kernel_roofline(graph, avg_log, device, rot=8, replays=10):
     from dgn_b200.nets.scalers import SCALERS as SC
     from dgn_b200.ops import AggSpec, agg_forward_raw, agg_backward_raw
     N, E, F = graph.number_of_nodes(), graph.number_of_edges(), HIDDEN
-    n_real, e_real = graph.n_real_nodes, graph.n_real_edges
+    n_real = graph.n_real_nodes if n_real is None else n_real
+    e_real = graph.n_real_edges if e_real is None else e_real
     aggs = [AGGREGATORS[a] for a in AGGS.split()]
     spec = AggSpec(aggs, [SC[s] for s in SCALERS.split()], avg_log, F, graph.ndata["eig"].shape[1])
     A, S = len(aggs), 3
@@ -378,14 +381,27 @@ def run_gpu_arm(args):
     if rank == 0:
         kr = kernel_roofline(step.g, avg_log, dev)
         peak, peak_src = measured_peak()
+        big, _ = collate(pools[0] * 16)                           # the same batch 16 x: 2048 graphs, ~98 k edges
+        big.to(dev)
+        ks = kernel_roofline(big, avg_log, dev, rot=2, replays=5)
+        del big
+        torch.cuda.empty_cache()
         roof = {"bound": "hbm", "achieved": kr["achieved_gbs"], "peak": peak, "unit": "GB/s",
                 "frac": kr["achieved_gbs"] / peak, "traffic": measured_traffic(), "peak_source": peak_src,
                 "traffic_note": "dram__bytes_read+write of one fwd+bwd launch, ncu --set full (profiles/r1_agg_traffic.json); "
                                 "output writes stay in the 126 MB L2 during the kernel, algorithmic bytes are bytes_fwd+bytes_bwd",
-                "kernel": "dgn agg_fwd_kernel + agg_bwd_dst_kernel + agg_bwd_src_kernel (one DGN layer of the bench "
-                          "workload, timed alone: CUDA graph of 8 launches on rotating operand sets > L2)",
+                "kernel": "dgn::agg_fwd_row_kernel + agg_bwd_row_kernel + agg_bwd_src_kernel = dgn_agg_forward + "
+                          "dgn_agg_backward of one DGN layer of the bench workload, timed alone: CUDA graph of 8 launches "
+                          "on rotating operand sets > L2; the per-batch dgn_field_build launch (shared by the 8 "
+                          "aggregation launches of a step) is not included",
                 "fwd_us": kr["fwd_us"], "bwd_us": kr["bwd_us"], "bytes_fwd": kr["bytes_fwd"],
-                "bytes_bwd": kr["bytes_bwd"], "fwd_gbs": kr["fwd_gbs"], "bwd_gbs": kr["bwd_gbs"]}
+                "bytes_bwd": kr["bytes_bwd"], "fwd_gbs": kr["fwd_gbs"], "bwd_gbs": kr["bwd_gbs"],
+                "fwd_frac": kr["fwd_gbs"] / peak, "bwd_frac": kr["bwd_gbs"] / peak,
+                "at_scale": {"workload": "same batch replicated 16x (2048 graphs) in one launch",
+                             "achieved": ks["achieved_gbs"], "frac": ks["achieved_gbs"] / peak,
+                             "fwd_us": ks["fwd_us"], "bwd_us": ks["bwd_us"], "fwd_frac": ks["fwd_gbs"] / peak,
+                             "bwd_frac": ks["bwd_gbs"] / peak, "bytes_fwd": ks["bytes_fwd"],
+                             "bytes_bwd": ks["bytes_bwd"]}}
         if world == 1 and not args.no_cpu:
             c = cpu_reference_time(steps=60, warmup=2, budget_s=20.0)
             cpu = {"value": c["value"], "unit": UNIT, "cores": c["cores"], "kind": "port",

@@ -782,8 +782,10 @@ static int launch_row_iso(const RowArgs& k, cudaStream_t st) {
   const bool lat = force_lat >= 0 ? force_lat != 0 : grid <= 148u * 6u;
   if constexpr (BWD) {
     if (lat) {
-      if (iso) launch_pdl(agg_bwd_row_kernel<VEC, NS, true, true>, grid, block, 0, st, k);
-      else launch_pdl(agg_bwd_row_kernel<VEC, NS, false, true>, grid, block, 0, st, k);
+      RowArgs kl = k;
+      kl.pf_bytes = 0;                 // single wave: the pipelined fold already overlaps the loads (prefetch measured slower)
+      if (iso) launch_pdl(agg_bwd_row_kernel<VEC, NS, true, true>, grid, block, 0, st, kl);
+      else launch_pdl(agg_bwd_row_kernel<VEC, NS, false, true>, grid, block, 0, st, kl);
     } else {
       if (iso) launch_pdl(agg_bwd_row_kernel<VEC, NS, true, false>, grid, block, 0, st, k);
       else launch_pdl(agg_bwd_row_kernel<VEC, NS, false, false>, grid, block, 0, st, k);
