@@ -238,7 +238,7 @@ def measured_traffic():
     """DRAM bytes of one forward + backward launch from the committed ncu capture (profiles/), or None."""
     try:
         t = json.load(open(os.path.join(REPO, "profiles", "r1_agg_traffic.json")))
-        return int(t["fwd_bytes"]) + int(t["bwd_bytes"])
+        return int(t["fwd_bytes"]) + int(t["bwd_bytes"])          # TypeError -> None while a leg is unmeasured
     except Exception:
         return None
 
@@ -388,8 +388,10 @@ def run_gpu_arm(args):
         torch.cuda.empty_cache()
         roof = {"bound": "hbm", "achieved": kr["achieved_gbs"], "peak": peak, "unit": "GB/s",
                 "frac": kr["achieved_gbs"] / peak, "traffic": measured_traffic(), "peak_source": peak_src,
-                "traffic_note": "dram__bytes_read+write of one fwd+bwd launch, ncu --set full (profiles/r1_agg_traffic.json); "
-                                "output writes stay in the 126 MB L2 during the kernel, algorithmic bytes are bytes_fwd+bytes_bwd",
+                "traffic_note": "dram__bytes_read+write of one fwd+bwd launch at this workload, ncu --set full "
+                                "(profiles/r1_agg_traffic.json); the 24 MB of output / gradient stay in the 126 MB L2 for the "
+                                "duration of one cold launch, so traffic < algorithmic bytes here; at 16x the batch the "
+                                "captures show 361 / 461 MB for 386 / 421 MB algorithmic (no wasted re-reads)",
                 "kernel": "dgn::agg_fwd_row_kernel + agg_bwd_row_kernel + agg_bwd_src_kernel = dgn_agg_forward + "
                           "dgn_agg_backward of one DGN layer of the bench workload, timed alone: CUDA graph of 8 launches "
                           "on rotating operand sets > L2; the per-batch dgn_field_build launch (shared by the 8 "
