@@ -573,8 +573,14 @@ __device__ __forceinline__ void load_slabs(const float* __restrict__ grow, int a
     if (s < (SS > 0 ? SS : S)) g[s] = vload_stream<VEC>(grow + (off + (unsigned)s * (unsigned)scaler_stride));
 }
 
-// PIPE: the slab loads of the next aggregator are in flight while this one is folded.  Costs 12 registers (occupancy),
-// so it is used for launches that fit in one wave anyway, where the serial load latency is what is left.
+// PIPE: the slab loads of the next kPipeDepth aggregators are in flight while this one is folded.  Costs
+// 12 registers per stage (occupancy), so it is used for launches that fit in one wave anyway, where the serial load
+// latency (one DRAM round trip per aggregator otherwise) is what is left.
+#ifndef ROW_PIPE_DEPTH
+#define ROW_PIPE_DEPTH 3
+#endif
+constexpr int kPipeDepth = ROW_PIPE_DEPTH;
+
 template <int VEC, int NS, bool ISO, int SS, bool PIPE>
 __device__ __forceinline__ void bwd_fold(const RowPlan& P, const Acc<VEC, NS, ISO>& R, const Vec<VEC>& hv, const float* wsumv,
                                          int D, float ld, const float* __restrict__ grow, Vec<VEC>& c0, Vec<VEC>& c1,
@@ -598,14 +604,24 @@ __device__ __forceinline__ void bwd_fold(const RowPlan& P, const Acc<VEC, NS, IS
       neg_m |= (sv < 0.f ? 1u : 0u) << (s * VEC + i);
     }
   }
-  Vec<VEC> gnext[DGN_MAX_SCALERS];
-  if constexpr (PIPE) load_slabs<VEC, SS>(grow, P.order[0], P.Fg, scaler_stride, S, gnext);
+  Vec<VEC> ring[PIPE ? kPipeDepth : 1][DGN_MAX_SCALERS];      // static indices only: stays in registers
+  if constexpr (PIPE) {
+#pragma unroll
+    for (int d = 0; d < kPipeDepth; ++d)
+      if (d < P.A) load_slabs<VEC, SS>(grow, P.order[d], P.Fg, scaler_stride, S, ring[d]);
+  }
   auto next_G = [&](int pos) {
     Vec<VEC> gcur[DGN_MAX_SCALERS];
     if constexpr (PIPE) {
 #pragma unroll
-      for (int s = 0; s < DGN_MAX_SCALERS; ++s) gcur[s] = gnext[s];
-      if (pos + 1 < P.A) load_slabs<VEC, SS>(grow, P.order[pos + 1], P.Fg, scaler_stride, S, gnext);
+      for (int s = 0; s < DGN_MAX_SCALERS; ++s) gcur[s] = ring[0][s];
+#pragma unroll
+      for (int d = 0; d + 1 < kPipeDepth; ++d) {
+#pragma unroll
+        for (int s = 0; s < DGN_MAX_SCALERS; ++s) ring[d][s] = ring[d + 1][s];
+      }
+      if (pos + kPipeDepth < P.A)
+        load_slabs<VEC, SS>(grow, P.order[pos + kPipeDepth], P.Fg, scaler_stride, S, ring[kPipeDepth - 1]);
     } else {
       load_slabs<VEC, SS>(grow, P.order[pos], P.Fg, scaler_stride, S, gcur);    // L2 hits: the row was prefetched
     }

@@ -27,15 +27,18 @@ __global__ void __launch_bounds__(LT) pair_linear_fwd_kernel(int N, int Fi, int 
   float* wp = ht + Fi * LR;                    // [Fi][LC]   W_src block, transposed
   float* wq = wp + Fi * LC;                    // [Fi][LC]   W_dst block, transposed
   const int t = threadIdx.x, r0 = blockIdx.x * LR, c0 = blockIdx.y * LC;
-  for (int idx = t; idx < LR * Fi; idx += LT) {          // coalesced along i
-    const int r = idx / Fi, i = idx - r * Fi;
-    ht[i * LR + r] = (r0 + r < N) ? __ldg(h + (size_t)(r0 + r) * ld_h + i) : 0.f;
+  // Staging transposes the tiles.  Consecutive threads take consecutive rows / output columns, so the shared-memory
+  // stores are conflict free (the other order - coalesced global reads, stride-LR stores - serialises every store
+  // instruction 32 ways and was most of this kernel's time); the strided global reads hit L1 / L2.
+  for (int idx = t; idx < LR * Fi; idx += LT) {
+    const int i = idx / LR, r = idx - i * LR;
+    ht[idx] = (r0 + r < N) ? __ldg(h + (size_t)(r0 + r) * ld_h + i) : 0.f;
   }
   for (int idx = t; idx < LC * Fi; idx += LT) {
-    const int o = idx / Fi, i = idx - o * Fi;
+    const int i = idx / LC, o = idx - i * LC;
     const bool ok = c0 + o < Fo;
-    wp[i * LC + o] = ok ? __ldg(W + (size_t)(c0 + o) * ld_w + i) : 0.f;
-    wq[i * LC + o] = ok ? __ldg(W + (size_t)(c0 + o) * ld_w + Fi + i) : 0.f;
+    wp[idx] = ok ? __ldg(W + (size_t)(c0 + o) * ld_w + i) : 0.f;
+    wq[idx] = ok ? __ldg(W + (size_t)(c0 + o) * ld_w + Fi + i) : 0.f;
   }
   __syncthreads();
   const int tx = t & 15, ty = t >> 4;          // 16 column groups x 8 row groups
@@ -76,11 +79,11 @@ __global__ void __launch_bounds__(LT) pair_linear_bwd_kernel(int N, int Fi, int 
   float* ws = qt + Fo * LR;                    // [Fo][LC]  W[:, c0:c0+LC]
   float* wd = ws + Fo * LC;                    // [Fo][LC]  W[:, Fi+c0 : Fi+c0+LC]
   const int t = threadIdx.x, r0 = blockIdx.x * LR, c0 = blockIdx.y * LC;
-  for (int idx = t; idx < LR * Fo; idx += LT) {
-    const int r = idx / Fo, o = idx - r * Fo;
+  for (int idx = t; idx < LR * Fo; idx += LT) {          // conflict-free transposing stores, see the forward
+    const int o = idx / LR, r = idx - o * LR;
     const bool ok = r0 + r < N;
-    pt[o * LR + r] = ok ? __ldg(dP + (size_t)(r0 + r) * ld_p + o) : 0.f;
-    qt[o * LR + r] = ok ? __ldg(dQ + (size_t)(r0 + r) * ld_q + o) : 0.f;
+    pt[idx] = ok ? __ldg(dP + (size_t)(r0 + r) * ld_p + o) : 0.f;
+    qt[idx] = ok ? __ldg(dQ + (size_t)(r0 + r) * ld_q + o) : 0.f;
   }
   for (int idx = t; idx < Fo * LC; idx += LT) {
     const int o = idx / LC, i = idx - o * LC;

@@ -80,7 +80,13 @@ class TrainStep:
         g = self.g
         g.invalidate_fields()                 # new batch in the static buffers: the eigen-field is rebuilt (1 launch)
         self.flat_g.zero_()
-        scores = self.net(g, g.ndata[self.node_key], g.edata[self.edge_key], g.snorm_n, None)
+        ops.BN_COUNTERS = []                  # BatchNorm batch counters: one multi-tensor bump instead of one per layer
+        try:
+            scores = self.net(g, g.ndata[self.node_key], g.edata[self.edge_key], g.snorm_n, None)
+            if ops.BN_COUNTERS:
+                torch._foreach_add_(ops.BN_COUNTERS, 1)
+        finally:
+            ops.BN_COUNTERS = None
         loss = self.net.loss(scores, self.targets)
         loss.backward()
         ops.side_join(self.dev)               # weight-gradient GEMMs forked onto the side stream are done

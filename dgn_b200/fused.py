@@ -21,7 +21,7 @@ from __future__ import annotations
 
 import torch
 
-from . import _lib
+from . import _lib, ops
 from .ops import (agg_backward_raw, agg_forward_raw, gemm, norm_backward_raw, norm_forward_raw, pair_linear_backward,
                   pair_linear_forward, side_queue, _f32c, _need_cuda)
 
@@ -70,8 +70,8 @@ class _FusedLayer(torch.autograd.Function):
         bn = cfg.bn
         use_batch = True
         if bn is not None:
-            if cfg.training and bn.track_running_stats and bn.num_batches_tracked is not None:
-                bn.num_batches_tracked += 1
+            if cfg.training:
+                ops.count_bn_batch(bn)
             use_batch = cfg.training or not bn.track_running_stats
         nargs = norm_forward_raw(
             y, out, stats, snorm=cfg.snorm, y_bias=b_post,

@@ -248,8 +248,11 @@ class BatchedGraph:
                                wsum.data_ptr() if ns > 0 else None)
             ent = {"c": cf, "groups": groups, "wsum": wsum, "stamp": None}
             self._fields[key] = ent
+        # (address, version) identifies the contents only while the tensor is alive: the entry keeps a reference so
+        # that the allocator cannot hand the same address to a different eig tensor behind our back
         stamp = (eig.data_ptr(), eig._version, eig.stride(0)) if eig is not None else (0, 0, 0)
         if ent["stamp"] != stamp:
+            ent["eig_ref"] = eig
             from . import ops
             _lib.check(_lib.lib.dgn_field_build(ctypes.byref(self.c_graph()), ctypes.byref(spec.c),
                                                 eig.data_ptr() if eig is not None else None,
@@ -264,6 +267,7 @@ class BatchedGraph:
         starts and must record the build launch); the device buffers are kept."""
         for ent in self._fields.values():
             ent["stamp"] = None
+            ent["eig_ref"] = None
 
     @property
     def max_in_degree(self):

@@ -267,14 +267,28 @@ class _NormAct(torch.autograd.Function):
         return d_y, None, d_gamma, d_beta, None, None, None, None, None, None, d_res, None
 
 
+# nn.BatchNorm1d counts its training batches in `num_batches_tracked`.  Incrementing it costs one tiny launch per
+# layer on the step's critical path; a step runner may collect the counters here instead (set BN_COUNTERS to a list)
+# and bump them all with ONE multi-tensor launch at the end of the forward pass (engine.TrainStep does).
+BN_COUNTERS = None
+
+
+def count_bn_batch(bn):
+    if bn.track_running_stats and bn.num_batches_tracked is not None:
+        if BN_COUNTERS is None:
+            bn.num_batches_tracked += 1
+        else:
+            BN_COUNTERS.append(bn.num_batches_tracked)
+
+
 def norm_act(y, snorm, bn, training, relu, residual, n_rows_dev=None):
     """Fused layer epilogue.  ``bn`` is an ``nn.BatchNorm1d`` (or None when batch_norm is off).
 
     ``n_rows_dev`` (device int32, optional) is the number of REAL rows of a padded batch: statistics
     run over those rows only and the padding rows of the output are written as zeros."""
     if bn is not None:
-        if training and bn.track_running_stats and bn.num_batches_tracked is not None:
-            bn.num_batches_tracked += 1
+        if training:
+            count_bn_batch(bn)
         use_batch = training or not bn.track_running_stats
         mom = 0.1 if bn.momentum is None else bn.momentum
         return _NormAct.apply(y, snorm, bn.weight, bn.bias, bn.running_mean, bn.running_var, mom, bn.eps,
