@@ -231,7 +231,8 @@ def kernel_roofline(graph, avg_log, device, rot=8, replays=10, n_real=None, e_re
     t_f, t_b = timed(fwd), timed(bwd)
     bf, bb = agg_bytes(n_real, e_real, F, A, S, 3, 2)
     return {"fwd_us": t_f * 1e6, "bwd_us": t_b * 1e6, "bytes_fwd": bf, "bytes_bwd": bb,
-            "achieved_gbs": (bf + bb) / (t_f + t_b) / 1e9, "fwd_gbs": bf / t_f / 1e9, "bwd_gbs": bb / t_b / 1e9}
+            "achieved_gbs": (bf + bb) / (t_f + t_b) / 1e9, "fwd_gbs": bf / t_f / 1e9, "bwd_gbs": bb / t_b / 1e9,
+            "medges_per_s": e_real / (t_f + t_b) / 1e6}          # edges / kernel time of one layer
 
 
 def measured_traffic():
@@ -399,11 +400,12 @@ def run_gpu_arm(args):
                 "fwd_us": kr["fwd_us"], "bwd_us": kr["bwd_us"], "bytes_fwd": kr["bytes_fwd"],
                 "bytes_bwd": kr["bytes_bwd"], "fwd_gbs": kr["fwd_gbs"], "bwd_gbs": kr["bwd_gbs"],
                 "fwd_frac": kr["fwd_gbs"] / peak, "bwd_frac": kr["bwd_gbs"] / peak,
+                "kernel_medges_per_s_per_layer": kr["medges_per_s"],
                 "at_scale": {"workload": "same batch replicated 16x (2048 graphs) in one launch",
                              "achieved": ks["achieved_gbs"], "frac": ks["achieved_gbs"] / peak,
                              "fwd_us": ks["fwd_us"], "bwd_us": ks["bwd_us"], "fwd_frac": ks["fwd_gbs"] / peak,
                              "bwd_frac": ks["bwd_gbs"] / peak, "bytes_fwd": ks["bytes_fwd"],
-                             "bytes_bwd": ks["bytes_bwd"]}}
+                             "bytes_bwd": ks["bytes_bwd"], "kernel_medges_per_s_per_layer": ks["medges_per_s"]}}
         if world == 1 and not args.no_cpu:
             c = cpu_reference_time(steps=60, warmup=2, budget_s=20.0)
             cpu = {"value": c["value"], "unit": UNIT, "cores": c["cores"], "kind": "port",

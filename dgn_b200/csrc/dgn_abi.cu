@@ -131,8 +131,9 @@ extern "C" int dgn_agg_forward(const DgnGraph* g, const DgnAggSpec* spec, const 
   if (int rc = fill_args(g, spec, io, k, vec)) return rc;
   vec = choose_vec(vec, k.N, k.plan.F, true);
   k.plan.chunks = k.plan.F / vec;
-  const int rc = io->field ? launch_forward_row(k, spec, io->field, vec, (cudaStream_t)stream)
-                           : launch_forward(k, vec, (cudaStream_t)stream);
+  int rc = io->field ? launch_forward_row(k, spec, io->field, vec, (cudaStream_t)stream) : DGN_ERR_UNSUPPORTED;
+  if (rc == DGN_ERR_UNSUPPORTED)           // no field, or a row wider than the row kernels' CTA: in-kernel weights
+    rc = launch_forward(k, vec, (cudaStream_t)stream);
   if (rc == DGN_ERR_CUDA) g_dgn_last_cuda = cudaPeekAtLastError();
   return rc;
 }
@@ -164,16 +165,16 @@ extern "C" int dgn_agg_backward(const DgnGraph* g, const DgnAggSpec* spec, const
   // the weights in the launch prefer 8 B lanes for small launches
   vec = choose_vec(vec, k.N, k.plan.F, io->field == nullptr);
   k.plan.chunks = k.plan.F / vec;
-  int rc;
+  int rc = DGN_ERR_UNSUPPORTED;
   if (io->field) {
     rc = launch_backward_row_dst(k, spec, io->field, vec, (cudaStream_t)stream);
     if (rc == DGN_OK && grad->d_x)
       rc = launch_backward_src(k, vec, grad->d_x, grad->ld_dx, grad->fold_h_in ? grad->d_h_in : nullptr, grad->ld_dh,
                                (cudaStream_t)stream);
-  } else {
+  }
+  if (rc == DGN_ERR_UNSUPPORTED)           // no field, or a row wider than the row kernels' CTA: in-kernel weights
     rc = launch_backward(k, vec, grad->d_x, grad->ld_dx, grad->fold_h_in ? grad->d_h_in : nullptr, grad->ld_dh,
                          (cudaStream_t)stream);
-  }
   if (rc == DGN_ERR_CUDA) g_dgn_last_cuda = cudaPeekAtLastError();
   return rc;
 }

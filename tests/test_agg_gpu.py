@@ -283,6 +283,26 @@ def test_in_kernel_weight_path_still_matches_oracle():
     assert out.returncode == 0, out.stdout[-3000:]
 
 
+def test_rows_wider_than_a_row_kernel_cta_fall_back():
+    """F / 4 > 128 column chunks do not fit the row kernels' 128-thread CTA: dgn_agg_forward / backward then run the
+    in-kernel-weight kernels even though a field was supplied."""
+    F = 640
+    g, samples, eig, h, P, Q, R, avg = _graph_case("zinc", 3, 11, F)
+    aggs = ["mean", "max", "dir1-dx", "dir2-av"]
+    src, dst = g.host("src").astype(np.int64), g.host("dst").astype(np.int64)
+    hl = h.clone().requires_grad_(True)
+    ref = oracle_aggregate(g.number_of_nodes(), src, dst, eig, hl, hl[src], aggs, S3, avg)
+    gy = torch.randn(ref.shape, generator=torch.Generator().manual_seed(0))
+    ref.backward(gy)
+    g.to(DEV)
+    spec = AggSpec([AGGREGATORS[a] for a in aggs], [SCALERS[s] for s in S3], avg, F, eig.shape[1])
+    hd = h.to(DEV).requires_grad_(True)
+    out = aggregate(g, spec, _lib.MSG_SOURCE, hd, eig.to(DEV), x=hd)
+    out.backward(gy.to(DEV))
+    assert_close(out, ref, what="out")
+    assert_close(hd.grad, hl.grad, what="dh")
+
+
 def test_field_is_rebuilt_when_eig_changes_in_place():
     """The eigen-field is cached per batch; an in-place change of eig (the sign-flip augmentation,
     rb/train/train_molecules_graph_regression.py:29-33) must invalidate it."""
