@@ -72,6 +72,19 @@ class DgnNormGrad(C.Structure):
                 ("d_bias", C.c_void_p), ("accumulate", C.c_int32), ("scratch", C.c_void_p)]
 
 
+class DgnHeadArgs(C.Structure):
+    _fields_ = [("n_rows", C.c_int32), ("d0", C.c_int32), ("d1", C.c_int32), ("d2", C.c_int32), ("d_out", C.c_int32),
+                ("x", C.c_void_p), ("ld_x", C.c_int32), ("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p),
+                ("b2", C.c_void_p), ("w3", C.c_void_p), ("b3", C.c_void_p), ("a1", C.c_void_p), ("a2", C.c_void_p),
+                ("y", C.c_void_p), ("ld_y", C.c_int32)]
+
+
+class DgnHeadGrad(C.Structure):
+    _fields_ = [("g_y", C.c_void_p), ("ld_gy", C.c_int32), ("d_x", C.c_void_p), ("ld_dx", C.c_int32),
+                ("d_w1", C.c_void_p), ("d_b1", C.c_void_p), ("d_w2", C.c_void_p), ("d_b2", C.c_void_p),
+                ("d_w3", C.c_void_p), ("d_b3", C.c_void_p), ("accumulate", C.c_int32)]
+
+
 # name -> (restype, argtypes); the CPU test-suite checks this table against include/dgn_b200.h
 SIGNATURES = {
     "dgn_abi_version": (C.c_int, []),
@@ -100,6 +113,10 @@ SIGNATURES = {
                                           C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
     "dgn_pair_linear_backward": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
                                            C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
+    "dgn_head_forward": (C.c_int, [C.POINTER(DgnHeadArgs), C.c_void_p]),
+    "dgn_head_backward": (C.c_int, [C.POINTER(DgnHeadArgs), C.POINTER(DgnHeadGrad), C.c_void_p]),
+    "dgn_l1_loss_forward": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dgn_l1_loss_backward": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dgn_readout_forward": (C.c_int, [C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
                                       C.c_void_p, C.c_int32, C.c_void_p]),
     "dgn_readout_backward": (C.c_int, [C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,

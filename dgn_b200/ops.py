@@ -514,3 +514,111 @@ def pair_linear_backward(d_P, d_Q, W, Fi, d_h):
     check(rc, "dgn_pair_linear_backward")
     _count(1)
     return d_h
+
+
+# ---------------------------------------------------------------------------------------------------------
+# graph-level prediction head (MLPReadout, L = 2) and L1 loss: one launch per direction each
+# ---------------------------------------------------------------------------------------------------------
+HEAD_ENABLED = os.environ.get("DGN_NO_HEAD", "0") != "1"
+
+
+def _head_args(x, w1, b1, w2, b2, w3, b3, a1, a2, y):
+    a = _lib.DgnHeadArgs()
+    a.n_rows, a.d0, a.d1, a.d2, a.d_out = x.shape[0], w1.shape[1], w1.shape[0], w2.shape[0], w3.shape[0]
+    a.x, a.ld_x = x.data_ptr(), x.stride(0)
+    a.w1, a.b1, a.w2, a.b2, a.w3, a.b3 = (t.data_ptr() for t in (w1, b1, w2, b2, w3, b3))
+    a.a1, a.a2, a.y, a.ld_y = a1.data_ptr(), a2.data_ptr(), y.data_ptr(), y.stride(0)
+    return a
+
+
+def head_supported(x, fcs) -> bool:
+    """Shapes dgn_head_forward takes: 3 Linear layers with bias on CUDA fp32, sizes within the kernel's limits."""
+    if not (HEAD_ENABLED and x.is_cuda and x.dim() == 2 and len(fcs) == 3 and x.dtype == torch.float32):
+        return False
+    if any(fc.bias is None or not fc.weight.is_contiguous() or fc.weight.dtype != torch.float32 for fc in fcs):
+        return False
+    d0, d1, d2, do = fcs[0].in_features, fcs[0].out_features, fcs[1].out_features, fcs[2].out_features
+    return (x.shape[0] <= 1024 and x.shape[1] == d0 and d1 * d0 <= 4096 and d2 * d1 <= 1024 and do * d2 <= 512 and
+            d1 + d2 + do <= 256 and (d1 * d0 + d2 * d1 + do * d2 + 32 * (d0 + 2 * d1 + 2 * d2 + do)) * 4 <= 150 * 1024)
+
+
+class _Head(torch.autograd.Function):
+    """y = W3 relu(W2 relu(W1 x + b1) + b2) + b3 (rb/nets/mlp_readout_layer.py:24-30) through dgn_head_forward /
+    dgn_head_backward.  With ``direct`` and existing ``.grad`` buffers the parameter gradients are accumulated in
+    place (no autograd accumulation kernels), like the fused layer."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, w3, b3, direct):
+        x = _f32c(x)
+        B = x.shape[0]
+        a1 = torch.empty((B, w1.shape[0]), device=x.device, dtype=torch.float32)
+        a2 = torch.empty((B, w2.shape[0]), device=x.device, dtype=torch.float32)
+        y = torch.empty((B, w3.shape[0]), device=x.device, dtype=torch.float32)
+        if B > 0:
+            check(lib.dgn_head_forward(C.byref(_head_args(x, w1, b1, w2, b2, w3, b3, a1, a2, y)), _stream(x)),
+                  "dgn_head_forward")
+            _count(1)
+        ctx.save_for_backward(x, w1, b1, w2, b2, w3, b3, a1, a2, y)
+        ctx.direct = direct
+        return y
+
+    @staticmethod
+    def backward(ctx, g_y):
+        x, w1, b1, w2, b2, w3, b3, a1, a2, y = ctx.saved_tensors
+        params = (w1, b1, w2, b2, w3, b3)
+        g_y = g_y.contiguous()
+        direct = ctx.direct and all(p.grad is not None and p.grad.is_contiguous() for p in params)
+        grads = [p.grad for p in params] if direct else [torch.empty_like(p) for p in params]
+        d_x = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        if x.shape[0] > 0:
+            g = _lib.DgnHeadGrad()
+            g.g_y, g.ld_gy = g_y.data_ptr(), g_y.stride(0)
+            if d_x is not None:
+                g.d_x, g.ld_dx = d_x.data_ptr(), d_x.stride(0)
+            g.d_w1, g.d_b1, g.d_w2, g.d_b2, g.d_w3, g.d_b3 = (t.data_ptr() for t in grads)
+            g.accumulate = int(direct)
+            check(lib.dgn_head_backward(C.byref(_head_args(x, w1, b1, w2, b2, w3, b3, a1, a2, y)), C.byref(g),
+                                        _stream(x)), "dgn_head_backward")
+            _count(1)
+        elif not direct:
+            grads = [torch.zeros_like(p) for p in params]
+        if direct:
+            return (d_x,) + (None,) * 7
+        return (d_x,) + tuple(grads) + (None,)
+
+
+def mlp_head(x, fcs, direct_grads=True):
+    """MLPReadout forward over its three ``nn.Linear`` layers in one launch (one more for the backward)."""
+    return _Head.apply(x, fcs[0].weight, fcs[0].bias, fcs[1].weight, fcs[1].bias, fcs[2].weight, fcs[2].bias,
+                       direct_grads)
+
+
+class _L1Loss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y, target):
+        y, target = y.contiguous(), target.contiguous()
+        loss = torch.empty((), device=y.device, dtype=torch.float32)
+        check(lib.dgn_l1_loss_forward(y.numel(), y.data_ptr(), target.data_ptr(), loss.data_ptr(), _stream(y)),
+              "dgn_l1_loss_forward")
+        _count(1)
+        ctx.save_for_backward(y, target)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        y, target = ctx.saved_tensors
+        g = g.contiguous().float()
+        d_y = torch.empty_like(y)
+        check(lib.dgn_l1_loss_backward(y.numel(), y.data_ptr(), target.data_ptr(), g.data_ptr(), d_y.data_ptr(),
+                                       _stream(y)), "dgn_l1_loss_backward")
+        _count(1)
+        return d_y, None
+
+
+def l1_loss(scores, targets):
+    """``nn.L1Loss()(scores, targets)`` (rb/nets/molecules_graph_regression/dgn_net.py:90-92): one launch per direction
+    on CUDA fp32 tensors of equal shape; anything else goes through torch."""
+    if (HEAD_ENABLED and scores.is_cuda and scores.dtype == torch.float32 and targets.dtype == torch.float32 and
+            scores.shape == targets.shape and scores.numel() > 0 and not targets.requires_grad):
+        return _L1Loss.apply(scores, targets)
+    return torch.nn.functional.l1_loss(scores, targets)

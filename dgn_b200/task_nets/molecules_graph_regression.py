@@ -6,7 +6,7 @@ runs unmodified on top of ``nets.dgn_layer`` from this package, see INTEGRATION.
 """
 import torch.nn as nn
 
-from dgn_b200.ops import embedding
+from dgn_b200.ops import embedding, l1_loss
 from dgn_b200.task_nets._common import build_layers, graph_readout
 from dgn_b200.nets.mlp_readout_layer import MLPReadout
 
@@ -38,4 +38,4 @@ class DGNNet(nn.Module):
         return self.MLP_layer(graph_readout(g, h, self.readout))
 
     def loss(self, scores, targets):
-        return nn.L1Loss()(scores, targets)
+        return l1_loss(scores, targets)          # nn.L1Loss()(scores, targets), one launch per direction on CUDA

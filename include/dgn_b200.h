@@ -21,6 +21,8 @@
  *   dgn_readout_*     - dgl.{mean,sum,max}_nodes at rb/nets/molecules_graph_regression/dgn_net.py:71-86.
  *   dgn_gemm_tf32x3   - the Linear layers of pretrans / posttrans (FCLayer, rb/nets/layers.py:76-100) in fp32
  *                       accuracy on the tcgen05 tensor cores.
+ *   dgn_head_*        - the graph-level prediction head MLPReadout (rb/nets/mlp_readout_layer.py:11-30) in one launch
+ *                       per direction; dgn_l1_loss_* - nn.L1Loss of rb/nets/molecules_graph_regression/dgn_net.py:90-92.
  *   dgn_embedding_backward, dgn_adam_step - the two remaining per-step pieces of the training loop that sit
  *                       between launches of the path (rb/nets/molecules_graph_regression/dgn_net.py:58,
  *                       rb/main_molecules.py:82).
@@ -289,6 +291,43 @@ int dgn_pair_linear_forward(int32_t N, int32_t Fi, int32_t Fo, const float* h, i
                             float* P, int32_t ld_p, float* Q, int32_t ld_q, void* stream);
 int dgn_pair_linear_backward(int32_t N, int32_t Fi, int32_t Fo, const float* dP, int32_t ld_p, const float* dQ,
                              int32_t ld_q, const float* W, int32_t ld_w, float* d_h, int32_t ld_dh, void* stream);
+
+/* MLPReadout with L = 2 hidden layers (rb/nets/mlp_readout_layer.py:11-30):
+ *   y = W3 relu(W2 relu(W1 x + b1) + b2) + b3      x [n_rows, d0], W1 [d1, d0], W2 [d2, d1], W3 [d_out, d2]
+ * in ONE launch (one CTA, weights resident in shared memory).  Weights are contiguous row-major ([out][in], the
+ * nn.Linear layout).  a1 [n_rows, d1] and a2 [n_rows, d2] receive the post-ReLU activations the backward needs.
+ * Limits (else DGN_ERR_UNSUPPORTED, callers use the library): n_rows <= DGN_HEAD_MAX_ROWS, d1*d0 <= 4096,
+ * d2*d1 <= 1024, d_out*d2 <= 512, d1 + d2 + d_out <= 256. */
+#define DGN_HEAD_MAX_ROWS 1024
+typedef struct {
+  int32_t n_rows, d0, d1, d2, d_out;
+  const float* x;  int32_t ld_x;
+  const float* w1; const float* b1;
+  const float* w2; const float* b2;
+  const float* w3; const float* b3;
+  float* a1;       /* [n_rows, d1] contiguous */
+  float* a2;       /* [n_rows, d2] contiguous */
+  float* y;        int32_t ld_y;
+} DgnHeadArgs;
+
+/* Gradients of dgn_head_forward given g_y [n_rows, d_out]; any output may be NULL.  accumulate = 1 adds into the
+ * weight / bias gradient buffers (d_x is always overwritten).  Deterministic: fixed owner thread per entry, rows in order. */
+typedef struct {
+  const float* g_y; int32_t ld_gy;
+  float* d_x;       int32_t ld_dx;
+  float* d_w1; float* d_b1;
+  float* d_w2; float* d_b2;
+  float* d_w3; float* d_b3;
+  int32_t accumulate;
+} DgnHeadGrad;
+
+int dgn_head_forward(const DgnHeadArgs* a, void* stream);
+int dgn_head_backward(const DgnHeadArgs* a, const DgnHeadGrad* g, void* stream);
+
+/* loss[0] = mean |y[i] - target[i]| over n contiguous elements (nn.L1Loss, reduction = mean), one launch, fixed
+ * summation order; backward: d_y[i] = g_loss[0] * sign(y[i] - target[i]) / n with sign(0) = 0. */
+int dgn_l1_loss_forward(int32_t n, const float* y, const float* target, float* loss, void* stream);
+int dgn_l1_loss_backward(int32_t n, const float* y, const float* target, const float* g_loss, float* d_y, void* stream);
 
 int dgn_readout_forward(int32_t n_graphs, const int32_t* graph_ptr, int32_t n_cols, const float* h, int32_t ld_h,
                         int32_t op, float* out, int32_t ld_o, void* stream);
