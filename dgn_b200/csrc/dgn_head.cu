@@ -18,11 +18,14 @@ extern thread_local cudaError_t g_dgn_last_cuda;
 
 namespace dgn {
 
-constexpr int HT = 256;        // threads of the single CTA
+// 1024 threads: the inner products are chains of dependent shared-memory loads + FMAs, so a single CTA is latency
+// bound and the number of resident warps is its throughput (256 threads measured 3-4x slower than the ~32 library
+// launches this replaces; profiles/README.md).
+constexpr int HT = 1024;       // threads of the single CTA
 constexpr int HR = 32;         // rows per tile
-constexpr int HE1 = 16;        // weight-gradient entries per thread: d1*d0 <= HT*HE1, d2*d1 <= HT*HE2, ...
-constexpr int HE2 = 4;
-constexpr int HE3 = 2;
+constexpr int HE1 = 4;         // weight-gradient entries per thread: d1*d0 <= HT*HE1, d2*d1 <= HT*HE2, ...
+constexpr int HE2 = 1;
+constexpr int HE3 = 1;
 
 struct HeadSmem {
   float *w1t, *w2t, *w3t, *b1, *b2, *b3, *xs, *a1s, *a2s, *ys, *red;

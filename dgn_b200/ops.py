@@ -538,8 +538,8 @@ def head_supported(x, fcs) -> bool:
     if any(fc.bias is None or not fc.weight.is_contiguous() or fc.weight.dtype != torch.float32 for fc in fcs):
         return False
     d0, d1, d2, do = fcs[0].in_features, fcs[0].out_features, fcs[1].out_features, fcs[2].out_features
-    return (x.shape[0] <= 1024 and x.shape[1] == d0 and d1 * d0 <= 4096 and d2 * d1 <= 1024 and do * d2 <= 512 and
-            d1 + d2 + do <= 256 and (d1 * d0 + d2 * d1 + do * d2 + 32 * (d0 + 2 * d1 + 2 * d2 + do)) * 4 <= 150 * 1024)
+    return (x.shape[0] <= 1024 and x.shape[1] == d0 and d1 * d0 <= 4096 and d2 * d1 <= 1024 and do * d2 <= 1024 and
+            d1 + d2 + do <= 1024 and (d1 * d0 + d2 * d1 + do * d2 + 32 * (d0 + 2 * d1 + 2 * d2 + do)) * 4 <= 150 * 1024)
 
 
 class _Head(torch.autograd.Function):

@@ -297,7 +297,7 @@ int dgn_pair_linear_backward(int32_t N, int32_t Fi, int32_t Fo, const float* dP,
  * in ONE launch (one CTA, weights resident in shared memory).  Weights are contiguous row-major ([out][in], the
  * nn.Linear layout).  a1 [n_rows, d1] and a2 [n_rows, d2] receive the post-ReLU activations the backward needs.
  * Limits (else DGN_ERR_UNSUPPORTED, callers use the library): n_rows <= DGN_HEAD_MAX_ROWS, d1*d0 <= 4096,
- * d2*d1 <= 1024, d_out*d2 <= 512, d1 + d2 + d_out <= 256. */
+ * d2*d1 <= 1024, d_out*d2 <= 1024, d1 + d2 + d_out <= 1024. */
 #define DGN_HEAD_MAX_ROWS 1024
 typedef struct {
   int32_t n_rows, d0, d1, d2, d_out;

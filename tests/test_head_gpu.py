@@ -17,7 +17,7 @@ def _torch_head(head, x):
     return head.FC_layers[-1](x)
 
 
-@pytest.mark.parametrize("B,d0,dout", [(128, 64, 1), (77, 64, 1), (1, 64, 1), (300, 128, 10), (40, 36, 3), (1024, 64, 2)])
+@pytest.mark.parametrize("B,d0,dout", [(128, 64, 1), (77, 64, 1), (1, 64, 1), (300, 64, 10), (40, 36, 3), (1024, 64, 2)])
 def test_head_matches_torch(B, d0, dout):
     torch.manual_seed(B + d0)
     head = MLPReadout(d0, dout).to(DEV)
