@@ -4,15 +4,19 @@
 // vectors of a batch, and nn.L1Loss (rb/nets/molecules_graph_regression/dgn_net.py:90-92).  Through the library
 // this head is ~32 launches per step (3 GEMMs + epilogues + activations forward; sign / scale / 3 x (2 GEMMs + bias
 // reduction) + gradient accumulation adds backward) for ~1 MFLOP of work - at the headline batch (128 graphs) that
-// is a quarter of all launches of the step.  Here ONE CTA walks the batch in tiles of 32 rows with all three weight
-// matrices resident in shared memory; the backward keeps every weight-gradient entry in a register of a fixed
-// owner thread and adds the rows in a fixed order (deterministic), writing or accumulating into the gradient
-// buffers directly.
+// is a quarter of all launches of the step.  Here the batch is cut into tiles of 32 rows, every CTA keeps all three
+// weight matrices in shared memory.  Forward: one CTA per tile.  Backward: a thread-block CLUSTER of 4 CTAs shares the
+// tiles; every weight-gradient entry lives in a register of a fixed owner thread, rows are added in order, and the
+// four partial sums meet in distributed shared memory: rank 0 reads its peers' partials (DSMEM) in rank order and
+// writes or accumulates into the gradient buffers - deterministic, no atomics, no workspace, no second launch.
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include "../../include/dgn_b200.h"
 #include "dgn_launch.cuh"
+
+namespace cg = cooperative_groups;
 
 extern thread_local cudaError_t g_dgn_last_cuda;
 
@@ -21,8 +25,10 @@ namespace dgn {
 // 1024 threads: the inner products are chains of dependent shared-memory loads + FMAs, so a single CTA is latency
 // bound and the number of resident warps is its throughput (256 threads measured 3-4x slower than the ~32 library
 // launches this replaces; profiles/README.md).
-constexpr int HT = 1024;       // threads of the single CTA
+constexpr int HT = 1024;       // threads per CTA
 constexpr int HR = 32;         // rows per tile
+constexpr int HC = 4;          // CTAs of the backward's cluster
+constexpr int HF = 32;         // at most this many CTAs in the forward
 constexpr int HE1 = 4;         // weight-gradient entries per thread: d1*d0 <= HT*HE1, d2*d1 <= HT*HE2, ...
 constexpr int HE2 = 1;
 constexpr int HE3 = 1;
@@ -93,7 +99,7 @@ __global__ void __launch_bounds__(HT) head_fwd_kernel(const DgnHeadArgs a) {
   extern __shared__ __align__(16) float hsm[];
   const HeadSmem s = head_carve(hsm, a.d0, a.d1, a.d2, a.d_out);
   head_load_weights(a, s);
-  for (int r0 = 0; r0 < a.n_rows; r0 += HR) {
+  for (int r0 = blockIdx.x * HR; r0 < a.n_rows; r0 += gridDim.x * HR) {
     const int nr = min(HR, a.n_rows - r0);
     __syncthreads();                                    // weights staged / previous tile consumed
     for (int i = threadIdx.x; i < nr * a.d0; i += HT) {
@@ -137,9 +143,11 @@ __global__ void __launch_bounds__(HT) l1_bwd_kernel(int n, const float* __restri
   d_y[i] = d > 0.f ? g : (d < 0.f ? -g : 0.f);
 }
 
-__global__ void __launch_bounds__(HT) head_bwd_kernel(const DgnHeadArgs a, const DgnHeadGrad g) {
+__global__ void __cluster_dims__(HC, 1, 1) __launch_bounds__(HT) head_bwd_kernel(const DgnHeadArgs a, const DgnHeadGrad g) {
   pdl_prologue();
   extern __shared__ __align__(16) float hsm[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
   const int d0 = a.d0, d1 = a.d1, d2 = a.d2, dout = a.d_out, t = threadIdx.x;
   // shared memory: weights in their natural [out][in] layout (the backward multiplies by W, not W^T), the tile's
   // x / a1 / a2 and the three gradient tiles
@@ -152,6 +160,7 @@ __global__ void __launch_bounds__(HT) head_bwd_kernel(const DgnHeadArgs a, const
   float* dys = a2s + HR * d2;      // [HR][dout]
   float* dz2 = dys + HR * dout;    // [HR][d2]
   float* dz1 = dz2 + HR * d2;      // [HR][d1]
+  float* part = dz1 + HR * d1;     // [d1*d0 + d2*d1 + dout*d2 + d1 + d2 + dout] this CTA's partial gradients
   for (int i = t; i < d1 * d0; i += HT) w1[i] = __ldg(a.w1 + i);
   for (int i = t; i < d2 * d1; i += HT) w2[i] = __ldg(a.w2 + i);
   for (int i = t; i < dout * d2; i += HT) w3[i] = __ldg(a.w3 + i);
@@ -163,7 +172,7 @@ __global__ void __launch_bounds__(HT) head_bwd_kernel(const DgnHeadArgs a, const
 #pragma unroll
   for (int q = 0; q < HE3; ++q) gw3[q] = 0.f;
 
-  for (int r0 = 0; r0 < a.n_rows; r0 += HR) {
+  for (int r0 = rank * HR; r0 < a.n_rows; r0 += HC * HR) {    // this CTA's tiles (possibly none: it still joins the syncs)
     const int nr = min(HR, a.n_rows - r0);
     __syncthreads();
     for (int i = t; i < nr * d0; i += HT) { const int r = i / d0, k = i - r * d0; xs[i] = __ldg(a.x + (size_t)(r0 + r) * a.ld_x + k); }
@@ -233,20 +242,39 @@ __global__ void __launch_bounds__(HT) head_bwd_kernel(const DgnHeadArgs a, const
     else if (t < d1 + d2) { for (int r = 0; r < nr; ++r) gb += dz2[r * d2 + (t - d1)]; }
     else if (t < d1 + d2 + dout) { for (int r = 0; r < nr; ++r) gb += dys[r * dout + (t - d1 - d2)]; }
   }
-  auto put = [&](float* dst, float v) { *dst = g.accumulate ? *dst + v : v; };
+  // partial gradients -> this CTA's shared memory, then rank 0 adds the cluster's partials in rank order (DSMEM)
+  const int o2 = d1 * d0, o3 = o2 + d2 * d1, ob = o3 + dout * d2, n_par = ob + d1 + d2 + dout;
 #pragma unroll
-  for (int q = 0; q < HE1; ++q) { const int e = t + q * HT; if (e < d1 * d0 && g.d_w1) put(g.d_w1 + e, gw1[q]); }
+  for (int q = 0; q < HE1; ++q) { const int e = t + q * HT; if (e < d1 * d0) part[e] = gw1[q]; }
 #pragma unroll
-  for (int q = 0; q < HE2; ++q) { const int e = t + q * HT; if (e < d2 * d1 && g.d_w2) put(g.d_w2 + e, gw2[q]); }
+  for (int q = 0; q < HE2; ++q) { const int e = t + q * HT; if (e < d2 * d1) part[o2 + e] = gw2[q]; }
 #pragma unroll
-  for (int q = 0; q < HE3; ++q) { const int e = t + q * HT; if (e < dout * d2 && g.d_w3) put(g.d_w3 + e, gw3[q]); }
-  if (t < d1) { if (g.d_b1) put(g.d_b1 + t, gb); }
-  else if (t < d1 + d2) { if (g.d_b2) put(g.d_b2 + (t - d1), gb); }
-  else if (t < d1 + d2 + dout) { if (g.d_b3) put(g.d_b3 + (t - d1 - d2), gb); }
+  for (int q = 0; q < HE3; ++q) { const int e = t + q * HT; if (e < dout * d2) part[o3 + e] = gw3[q]; }
+  if (t < d1 + d2 + dout) part[ob + t] = gb;
+  cluster.sync();
+  if (rank == 0) {
+    const float* peer[HC];
+#pragma unroll
+    for (int r = 0; r < HC; ++r) peer[r] = cluster.map_shared_rank(part, r);
+    for (int e = t; e < n_par; e += HT) {
+      float v = 0.f;
+#pragma unroll
+      for (int r = 0; r < HC; ++r) v += peer[r][e];
+      float* dst;
+      if (e < o2) dst = g.d_w1 ? g.d_w1 + e : nullptr;
+      else if (e < o3) dst = g.d_w2 ? g.d_w2 + (e - o2) : nullptr;
+      else if (e < ob) dst = g.d_w3 ? g.d_w3 + (e - o3) : nullptr;
+      else if (e < ob + d1) dst = g.d_b1 ? g.d_b1 + (e - ob) : nullptr;
+      else if (e < ob + d1 + d2) dst = g.d_b2 ? g.d_b2 + (e - ob - d1) : nullptr;
+      else dst = g.d_b3 ? g.d_b3 + (e - ob - d1 - d2) : nullptr;
+      if (dst) *dst = g.accumulate ? *dst + v : v;
+    }
+  }
+  cluster.sync();                                     // peers keep their shared memory alive until rank 0 has read it
 }
 
 static inline size_t head_bwd_smem_bytes(int d0, int d1, int d2, int dout) {
-  return sizeof(float) * ((size_t)d1 * d0 + (size_t)d2 * d1 + (size_t)dout * d2 +
+  return sizeof(float) * (2 * ((size_t)d1 * d0 + (size_t)d2 * d1 + (size_t)dout * d2) + d1 + d2 + dout +
                           (size_t)HR * (d0 + 2 * d1 + 2 * d2 + dout) + 4);
 }
 
@@ -280,7 +308,8 @@ extern "C" int dgn_head_forward(const DgnHeadArgs* a, void* stream) {
   if (smem > 48 * 1024 &&
       cudaFuncSetAttribute(head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) != cudaSuccess)
     return DGN_ERR_CUDA;
-  launch_pdl(head_fwd_kernel, dim3(1), dim3(HT), smem, (cudaStream_t)stream, *a);
+  const int tiles = (a->n_rows + HR - 1) / HR;
+  launch_pdl(head_fwd_kernel, dim3((unsigned)(tiles < HF ? tiles : HF)), dim3(HT), smem, (cudaStream_t)stream, *a);
   return head_done();
 }
 
@@ -292,7 +321,7 @@ extern "C" int dgn_head_backward(const DgnHeadArgs* a, const DgnHeadGrad* g, voi
   if (smem > 48 * 1024 &&
       cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) != cudaSuccess)
     return DGN_ERR_CUDA;
-  launch_pdl(head_bwd_kernel, dim3(1), dim3(HT), smem, (cudaStream_t)stream, *a, *g);
+  launch_pdl(head_bwd_kernel, dim3(HC), dim3(HT), smem, (cudaStream_t)stream, *a, *g);      // one cluster
   return head_done();
 }
 
