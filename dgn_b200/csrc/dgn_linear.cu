@@ -16,6 +16,14 @@ namespace dgn {
 
 constexpr int LR = 32, LC = 64, LT = 128;     // rows / columns per block, threads
 
+// Asynchronous 4-byte global -> shared copies (LDGSTS): the staging loops issue all their copies back to back instead
+// of 80 dependent load -> store round trips per thread - with 4 warps per CTA nothing else hides that latency.
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // P[n,o] = sum_i h[n,i] W[o,i] ;  Q[n,o] = sum_i h[n,i] W[o,Fi+i]
 __global__ void __launch_bounds__(LT) pair_linear_fwd_kernel(int N, int Fi, int Fo, const float* __restrict__ h, int ld_h,
                                                              const float* __restrict__ W, int ld_w,
@@ -32,14 +40,20 @@ __global__ void __launch_bounds__(LT) pair_linear_fwd_kernel(int N, int Fi, int 
   // instruction 32 ways and was most of this kernel's time); the strided global reads hit L1 / L2.
   for (int idx = t; idx < LR * Fi; idx += LT) {
     const int i = idx / LR, r = idx - i * LR;
-    ht[idx] = (r0 + r < N) ? __ldg(h + (size_t)(r0 + r) * ld_h + i) : 0.f;
+    if (r0 + r < N) cp_async4(ht + idx, h + (size_t)(r0 + r) * ld_h + i);
+    else ht[idx] = 0.f;
   }
   for (int idx = t; idx < LC * Fi; idx += LT) {
     const int i = idx / LC, o = idx - i * LC;
-    const bool ok = c0 + o < Fo;
-    wp[idx] = ok ? __ldg(W + (size_t)(c0 + o) * ld_w + i) : 0.f;
-    wq[idx] = ok ? __ldg(W + (size_t)(c0 + o) * ld_w + Fi + i) : 0.f;
+    if (c0 + o < Fo) {
+      cp_async4(wp + idx, W + (size_t)(c0 + o) * ld_w + i);
+      cp_async4(wq + idx, W + (size_t)(c0 + o) * ld_w + Fi + i);
+    } else {
+      wp[idx] = 0.f;
+      wq[idx] = 0.f;
+    }
   }
+  cp_async_wait_all();
   __syncthreads();
   const int tx = t & 15, ty = t >> 4;          // 16 column groups x 8 row groups
   float ap[4][4] = {}, aq[4][4] = {};
@@ -81,16 +95,25 @@ __global__ void __launch_bounds__(LT) pair_linear_bwd_kernel(int N, int Fi, int 
   const int t = threadIdx.x, r0 = blockIdx.x * LR, c0 = blockIdx.y * LC;
   for (int idx = t; idx < LR * Fo; idx += LT) {          // conflict-free transposing stores, see the forward
     const int o = idx / LR, r = idx - o * LR;
-    const bool ok = r0 + r < N;
-    pt[idx] = ok ? __ldg(dP + (size_t)(r0 + r) * ld_p + o) : 0.f;
-    qt[idx] = ok ? __ldg(dQ + (size_t)(r0 + r) * ld_q + o) : 0.f;
+    if (r0 + r < N) {
+      cp_async4(pt + idx, dP + (size_t)(r0 + r) * ld_p + o);
+      cp_async4(qt + idx, dQ + (size_t)(r0 + r) * ld_q + o);
+    } else {
+      pt[idx] = 0.f;
+      qt[idx] = 0.f;
+    }
   }
   for (int idx = t; idx < Fo * LC; idx += LT) {
     const int o = idx / LC, i = idx - o * LC;
-    const bool ok = c0 + i < Fi;
-    ws[o * LC + i] = ok ? __ldg(W + (size_t)o * ld_w + c0 + i) : 0.f;
-    wd[o * LC + i] = ok ? __ldg(W + (size_t)o * ld_w + Fi + c0 + i) : 0.f;
+    if (c0 + i < Fi) {
+      cp_async4(ws + idx, W + (size_t)o * ld_w + c0 + i);
+      cp_async4(wd + idx, W + (size_t)o * ld_w + Fi + c0 + i);
+    } else {
+      ws[idx] = 0.f;
+      wd[idx] = 0.f;
+    }
   }
+  cp_async_wait_all();
   __syncthreads();
   const int tx = t & 15, ty = t >> 4;
   float acc[4][4] = {};
