@@ -64,7 +64,24 @@ def test_group_builder_and_field_slots():
     assert slots("mean dir1-dx dir1-dx-no-abs") == 1
     assert slots("dir1-dx dir2-dx dir1-dx-no-abs dir2-dx-no-abs dir1-av dir2-av") == 4
     assert slots("dir1-dx-balanced dir1-0.1 dir1-neg-0.1 dir1-av") == 4
+    assert slots("dir1-dx dir1-dx dir1-dx-no-abs") == 2        # a repeated aggregator opens a slot of its own
     assert _lib.lib.dgn_field_slots(None) == -1
+
+
+@pytest.mark.parametrize("kind,kw", [("zinc", {}), ("cifar", dict(n_min=20, n_max=40)), ("pattern", dict(n_min=20, n_max=40))])
+def test_batched_graph_carries_the_field_group_layout(kind, kw):
+    """ovf_ptr travels in the packed buffer and the eigen-field capacity covers every batch of a padded layout."""
+    samples = make_samples(kind, 4, seed=5, **kw)
+    g, _ = collate(samples)
+    deg = np.diff(g.host("in_ptr"))
+    want = np.maximum(0, -(-(deg - 4) // 4))
+    assert np.array_equal(g.host("ovf_ptr"), np.concatenate([[0], np.cumsum(want)]))
+    assert g.n_groups == g.number_of_nodes() + int(want.sum())
+    cap = (g.number_of_nodes() + 17, g.number_of_edges() + 33)
+    gp, _ = collate(samples, capacity=cap)
+    ovf = gp.host("ovf_ptr")
+    assert ovf.shape[0] == cap[0] + 1 and ovf[-1] == want.sum() and np.all(np.diff(ovf[g.number_of_nodes():]) == 0)
+    assert gp.n_groups >= cap[0] + int(want.sum())               # fixed capacity: N_cap + E_cap / 4 + 1 groups
 
 
 def test_null_arguments_are_rejected_without_a_gpu():
