@@ -382,8 +382,13 @@ __global__ void readout_bwd_kernel(int n_graphs, const int32_t* __restrict__ gp,
 // entry, the last block to finish increments it.
 __global__ void __launch_bounds__(256) adam_kernel(long long n, float* __restrict__ p, const float* __restrict__ g,
                                                    float* __restrict__ m, float* __restrict__ v, float lr, float b1,
-                                                   float b2, float eps, float wd, int* __restrict__ state) {
+                                                   float b2, float eps, float wd, const float* __restrict__ hyper,
+                                                   int* __restrict__ state) {
   pdl_prologue();
+  // hyper (device, optional) = {lr, weight_decay, grad_scale}: a captured CUDA graph freezes by-value arguments, so a
+  // scheduler (ReduceLROnPlateau, rb/main_molecules.py:89-130) changes the step size by writing device memory
+  float gs = 1.f;
+  if (hyper) { lr = hyper[0]; wd = hyper[1]; gs = hyper[2]; }
   const int t = state[0] + 1;
   const float c1 = 1.f - powf(b1, (float)t), c2 = 1.f - powf(b2, (float)t);
   const float step_size = lr / c1, inv_sqrt_c2 = rsqrtf(c2);
@@ -395,7 +400,7 @@ __global__ void __launch_bounds__(256) adam_kernel(long long n, float* __restric
     float* pa = &pp.x; float* ma = &mm.x; float* va = &vv.x; const float* ga = &gg.x;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float gr = fmaf(wd, pa[j], ga[j]);
+      const float gr = fmaf(wd, pa[j], gs * ga[j]);
       ma[j] = fmaf(b1, ma[j], (1.f - b1) * gr);
       va[j] = fmaf(b2, va[j], (1.f - b2) * gr * gr);
       pa[j] -= step_size * ma[j] / (sqrtf(va[j]) * inv_sqrt_c2 + eps);
@@ -405,7 +410,7 @@ __global__ void __launch_bounds__(256) adam_kernel(long long n, float* __restric
     *reinterpret_cast<float4*>(v + i4) = vv;
   } else {
     for (long long i = i4; i < n; ++i) {
-      const float gr = fmaf(wd, p[i], g[i]);
+      const float gr = fmaf(wd, p[i], gs * g[i]);
       m[i] = fmaf(b1, m[i], (1.f - b1) * gr);
       v[i] = fmaf(b2, v[i], (1.f - b2) * gr * gr);
       p[i] -= step_size * m[i] / (sqrtf(v[i]) * inv_sqrt_c2 + eps);
@@ -505,13 +510,14 @@ extern "C" int dgn_readout_backward(int32_t n_graphs, const int32_t* graph_ptr, 
 }
 
 extern "C" int dgn_adam_step(int64_t n, float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float lr,
-                             float beta1, float beta2, float eps, float weight_decay, int32_t* state, void* stream) {
+                             float beta1, float beta2, float eps, float weight_decay, const float* hyper,
+                             int32_t* state, void* stream) {
   if (n < 0 || !param || !grad || !exp_avg || !exp_avg_sq || !state) return DGN_ERR_INVALID;
   if ((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(exp_avg) |
        reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15u)
     return DGN_ERR_ALIGNMENT;
   if (n == 0) return DGN_OK;
   const long long threads = (n + 3) / 4;
-  launch_pdl(adam_kernel, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, n, param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, state);
+  launch_pdl(adam_kernel, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, n, param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, hyper, state);
   return check_launch();
 }

@@ -30,17 +30,38 @@ class FlatAdam:
     (the step counter lives on the device).  Same update rule as ``torch.optim.Adam(lr, betas, eps, weight_decay)``
     (rb/main_molecules.py:82)."""
 
-    def __init__(self, flat_p, flat_g, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+    def __init__(self, flat_p, flat_g, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, grad_scale=1.0):
         self.p, self.g = flat_p, flat_g
-        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.betas, self.eps = betas, eps
         self.exp_avg = torch.zeros_like(flat_g)
         self.exp_avg_sq = torch.zeros_like(flat_g)
         self.state = torch.zeros(2, dtype=torch.int32, device=flat_g.device)
+        # {lr, weight_decay, grad_scale} live in DEVICE memory: by-value kernel arguments are frozen into a captured
+        # CUDA graph, these are read by every replay (ReduceLROnPlateau / min_lr stop, rb/main_molecules.py:89-130)
+        self._hyper_host = [float(lr), float(weight_decay), float(grad_scale)]
+        self.hyper = torch.tensor(self._hyper_host, dtype=torch.float32, device=flat_g.device)
+
+    lr = property(lambda self: self._hyper_host[0], lambda self, v: self.set_lr(v))
+    weight_decay = property(lambda self: self._hyper_host[1], lambda self, v: self._set(1, v))
+    grad_scale = property(lambda self: self._hyper_host[2], lambda self, v: self._set(2, v))
+
+    def _set(self, i, v):
+        self._hyper_host[i] = float(v)
+        self.hyper.copy_(torch.tensor(self._hyper_host, dtype=torch.float32), non_blocking=False)
+
+    def set_lr(self, lr):
+        """Takes effect on the next step, captured or not (one 12-byte H2D copy, stream ordered)."""
+        self._set(0, lr)
+
+    @property
+    def param_groups(self):
+        """Just enough of the torch.optim surface for ``lr_scheduler.ReduceLROnPlateau``-style loops to read the lr."""
+        return [{"lr": self.lr, "weight_decay": self.weight_decay}]
 
     def step(self):
         _lib.check(_lib.lib.dgn_adam_step(self.p.numel(), self.p.data_ptr(), self.g.data_ptr(), self.exp_avg.data_ptr(),
-                                          self.exp_avg_sq.data_ptr(), self.lr, self.betas[0], self.betas[1], self.eps,
-                                          self.weight_decay, self.state.data_ptr(),
+                                          self.exp_avg_sq.data_ptr(), self._hyper_host[0], self.betas[0], self.betas[1],
+                                          self.eps, self._hyper_host[1], self.hyper.data_ptr(), self.state.data_ptr(),
                                           torch.cuda.current_stream(self.p.device).cuda_stream), "dgn_adam_step")
         ops._count(1)
 
@@ -54,7 +75,6 @@ class TrainStep:
         self.graphed = graphed
         self.node_key, self.edge_key = node_key, edge_key
         self.flat_p, self.flat_g = flatten_parameters(net)
-        ops.SIDE_STREAM_ENABLED = True         # weight-gradient GEMMs become a parallel branch of the step
         self.opt = FlatAdam(self.flat_p, self.flat_g, lr=lr, weight_decay=weight_decay)
         if graphed and not template_graph.padded:
             raise ValueError("graphed=True needs batches padded to a fixed capacity (BatchedGraph(capacity=...))")
@@ -80,16 +100,13 @@ class TrainStep:
         g = self.g
         g.invalidate_fields()                 # new batch in the static buffers: the eigen-field is rebuilt (1 launch)
         self.flat_g.zero_()
-        ops.BN_COUNTERS = []                  # BatchNorm batch counters: one multi-tensor bump instead of one per layer
-        try:
+        # for THIS step only: in-place parameter gradients, weight-gradient GEMMs as a parallel branch, one
+        # multi-tensor BatchNorm-counter bump instead of one per layer; the scope joins the side stream on exit
+        with ops.step_scope(self.dev) as scope:
             scores = self.net(g, g.ndata[self.node_key], g.edata[self.edge_key], g.snorm_n, None)
-            if ops.BN_COUNTERS:
-                torch._foreach_add_(ops.BN_COUNTERS, 1)
-        finally:
-            ops.BN_COUNTERS = None
-        loss = self.net.loss(scores, self.targets)
-        loss.backward()
-        ops.side_join(self.dev)               # weight-gradient GEMMs forked onto the side stream are done
+            scope.flush_bn_counters()
+            loss = self.net.loss(scores, self.targets)
+            loss.backward()
         return loss
 
     def _reduce_and_update(self):

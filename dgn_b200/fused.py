@@ -133,7 +133,9 @@ class _FusedLayer(torch.autograd.Function):
             d_P = torch.empty((N, Fi), device=dev, dtype=torch.float32)
             d_Q = torch.empty((N, Fi), device=dev, dtype=torch.float32)
             if R is not None:
-                d_R = torch.empty((max(E, 1), Fi), device=dev, dtype=torch.float32)[:E]
+                # zeros: only rows of real edges are written; the padding rows of a fixed-capacity batch flow into
+                # dW_e = d_R^T @ e (and the pretrans MLP backward) and must not carry allocator garbage
+                d_R = torch.zeros((max(E, 1), Fi), device=dev, dtype=torch.float32)[:E]
             agg_backward_raw(g, spec, _lib.MSG_AFFINE, P, Q, R, h, cfg.eig, d_cat, True, d_x=d_P, d_q=d_Q, d_r=d_R,
                              d_h=d_h, edge_ws=ws, q_bias=b_pre, d_h_addend=resid)
             pair_linear_backward(d_P, d_Q, W_pre, Fi, d_h)                                   # += d_P W_src + d_Q W_dst
@@ -145,7 +147,9 @@ class _FusedLayer(torch.autograd.Function):
                     gemm(d_P, h, a_kmajor=False, b_kmajor=False, out=gW[:, :Fi], accumulate=True)          # += d_P^T @ h
                     gemm(d_Q, h, a_kmajor=False, b_kmajor=False, out=gW[:, Fi:2 * Fi], accumulate=True)    # += d_Q^T @ h
                     pb_pre.grad.addmv_(d_Q.t(), ones)
-                if side is not None:
+                # with edge features autograd itself accumulates into W_pre.grad on the main stream (backward of
+                # R = e @ W_pre[:, 2F:]^T, a read-modify-write of the whole tensor): keep these on the main stream too
+                if side is not None and R is None:
                     side.run(_dw_pre, keep=(d_P, d_Q, h))
                 else:
                     _dw_pre()
@@ -166,10 +170,13 @@ class _FusedLayer(torch.autograd.Function):
 
 
 def fused_layer(graph, spec, eig, h, R, pretrans_lin, posttrans_lin, bn, snorm, training, relu, residual, in_dim,
-                direct_grads=True):
+                direct_grads=None):
     """One DGN layer (complex / tower when ``pretrans_lin`` is given, simple otherwise) as a single autograd node.
 
-    ``direct_grads``: accumulate parameter gradients in place when every parameter already has ``.grad``."""
+    ``direct_grads``: accumulate parameter gradients in place when every parameter already has ``.grad``; defaults
+    to the enclosing ``ops.step_scope`` (off for plain autograd use, where autograd receives ordinary gradients)."""
+    if direct_grads is None:
+        direct_grads = ops.DIRECT_GRADS
     has_pre = pretrans_lin is not None
     W_pre = pretrans_lin.weight if has_pre else None
     b_pre = pretrans_lin.bias if has_pre else None
@@ -178,7 +185,10 @@ def fused_layer(graph, spec, eig, h, R, pretrans_lin, posttrans_lin, bn, snorm, 
     params = (W_pre, b_pre, posttrans_lin.weight, posttrans_lin.bias, gamma, beta)
     if snorm is not None:
         snorm = snorm.reshape(-1)
+        if snorm.dtype != torch.float32:
+            snorm = snorm.float()
         if not snorm.is_contiguous():
             snorm = snorm.contiguous()
+    eig = _f32c(eig)
     cfg = LayerConfig(graph, spec, eig, snorm, bn, training, relu, residual, direct_grads, in_dim, has_pre, params)
     return _FusedLayer.apply(cfg, h, R, W_pre, b_pre, posttrans_lin.weight, posttrans_lin.bias, gamma, beta)

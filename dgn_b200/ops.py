@@ -173,7 +173,9 @@ class _Aggregate(torch.autograd.Function):
         if q is not None and need[5]:
             d_q = torch.empty((N, F), device=dev, dtype=torch.float32)
         if r is not None and need[6]:
-            d_r = torch.empty((max(E, 1), F), device=dev, dtype=torch.float32)[:E]
+            # zeros: the kernels write the rows of REAL edges only; padding rows of a fixed-capacity batch must not
+            # carry allocator garbage into the caller's weight gradient (d_r^T @ e)
+            d_r = torch.zeros((max(E, 1), F), device=dev, dtype=torch.float32)[:E]
         if need[7] or fold:
             d_h = torch.empty((N, F), device=dev, dtype=torch.float32)
         agg_backward_raw(graph, spec, mode, x, q, r, h_in, eig, g_out, ctx.cat_input, d_x, d_q, d_r, d_h, ws,
@@ -368,15 +370,20 @@ class _Embedding(torch.autograd.Function):
         return (None if direct else dw), None, None, None
 
 
-def embedding(weight, idx, n_rows_dev=None, direct_grad=False):
+def embedding(weight, idx, n_rows_dev=None, direct_grad=None):
     """``weight[idx]`` (rb/nets/molecules_graph_regression/dgn_net.py:58) with a deterministic backward.
 
     ``direct_grad=True`` accumulates straight into ``weight.grad`` (which must already exist) instead of
     returning a gradient tensor - the engine's flat gradient buffer makes autograd's extra add redundant.
     Falls back to torch's own embedding when the vocabulary does not fit the kernel's shared-memory tile."""
     _need_cuda(weight, idx)
-    if weight.shape[0] > 200:            # tile would not fit in shared memory: library op (still on the GPU)
-        return torch.nn.functional.embedding(idx, weight)
+    if direct_grad is None:
+        direct_grad = DIRECT_GRADS
+    # the kernel reads idx as a contiguous 1-D int64 array and weight as contiguous fp32
+    if weight.shape[0] > 200 or idx.dim() != 1 or weight.dtype != torch.float32 or not weight.is_contiguous():
+        return torch.nn.functional.embedding(idx, weight)      # library op (still on the GPU)
+    if idx.dtype != torch.int64 or not idx.is_contiguous():
+        idx = idx.long().contiguous()
     return _Embedding.apply(weight, idx, n_rows_dev, direct_grad)
 
 
@@ -462,7 +469,37 @@ class _SideQueue:
 
 
 _SIDE = {}
-SIDE_STREAM_ENABLED = False      # engine.TrainStep switches it on; plain autograd use stays single-stream
+SIDE_STREAM_ENABLED = False      # only inside step_scope(): plain autograd use stays single-stream
+DIRECT_GRADS = False             # only inside step_scope(): parameter gradients accumulate straight into .grad
+
+
+class step_scope:
+    """What a step runner (engine.TrainStep) switches on for the duration of ITS OWN forward + backward, and nothing
+    else: in-place accumulation of parameter gradients into existing ``.grad`` buffers (autograd receives None for
+    them - that breaks ``torch.autograd.grad``, hooks and DDP, so it is opt-in), the forked stream for
+    weight-gradient GEMMs, and the collected BatchNorm batch counters.  Leaving the scope joins the side stream and
+    restores every switch, so a later ``backward()`` outside the runner is plain single-stream autograd again."""
+
+    def __init__(self, device, direct_grads=True, side_stream=True):
+        self.device, self.direct, self.side = device, direct_grads, side_stream
+
+    def __enter__(self):
+        global SIDE_STREAM_ENABLED, DIRECT_GRADS, BN_COUNTERS
+        self._saved = (SIDE_STREAM_ENABLED, DIRECT_GRADS, BN_COUNTERS)
+        SIDE_STREAM_ENABLED, DIRECT_GRADS, BN_COUNTERS = self.side, self.direct, []
+        return self
+
+    def flush_bn_counters(self):
+        global BN_COUNTERS
+        if BN_COUNTERS:
+            torch._foreach_add_(BN_COUNTERS, 1)
+        BN_COUNTERS = []
+
+    def __exit__(self, *exc):
+        global SIDE_STREAM_ENABLED, DIRECT_GRADS, BN_COUNTERS
+        side_join(self.device)
+        SIDE_STREAM_ENABLED, DIRECT_GRADS, BN_COUNTERS = self._saved
+        return False
 
 
 def side_queue(device):
@@ -587,8 +624,11 @@ class _Head(torch.autograd.Function):
         return (d_x,) + tuple(grads) + (None,)
 
 
-def mlp_head(x, fcs, direct_grads=True):
-    """MLPReadout forward over its three ``nn.Linear`` layers in one launch (one more for the backward)."""
+def mlp_head(x, fcs, direct_grads=None):
+    """MLPReadout forward over its three ``nn.Linear`` layers in one launch (one more for the backward).
+    ``direct_grads`` defaults to the enclosing ``step_scope`` (off for plain autograd use)."""
+    if direct_grads is None:
+        direct_grads = DIRECT_GRADS
     return _Head.apply(x, fcs[0].weight, fcs[0].bias, fcs[1].weight, fcs[1].bias, fcs[2].weight, fcs[2].bias,
                        direct_grads)
 

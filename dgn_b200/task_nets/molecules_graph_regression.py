@@ -28,7 +28,7 @@ class DGNNet(nn.Module):
         self.MLP_layer = MLPReadout((2 if wide else 1) * p["out_dim"], 1)
 
     def forward(self, g, h, e, snorm_n, snorm_e):
-        h = self.in_feat_dropout(embedding(self.embedding_h.weight, h, getattr(g, "n_rows_dev", None), True))
+        h = self.in_feat_dropout(embedding(self.embedding_h.weight, h, getattr(g, "n_rows_dev", None)))
         if self.pos_enc_dim > 0:
             h = h + self.embedding_pos_enc(g.ndata["pos_enc"].to(h.device))
         if self.edge_feat:

@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define DGN_ABI_VERSION 3
+#define DGN_ABI_VERSION 4
 #define DGN_MAX_AGG 32      /* aggregators per layer (the reference registry has 24)        */
 #define DGN_MAX_SCALERS 4   /* scalers per layer (the reference registry has 3)             */
 #define DGN_MAX_SLOTS 8     /* distinct eigen-weighted feature sums one launch can carry    */
@@ -264,9 +264,12 @@ int dgn_embedding_backward(int32_t n_rows, int32_t n_cols, int32_t vocab, const 
 
 /* One Adam update of a flat fp32 parameter buffer (torch.optim.Adam as used at rb/main_molecules.py:82:
  * weight decay added to the gradient, bias-corrected moments).  state: 2 device int32, zero-initialised:
- * state[0] = steps taken so far (incremented by the kernel), state[1] = internal.  All pointers 16 B aligned. */
+ * state[0] = steps taken so far (incremented by the kernel), state[1] = internal.  All pointers 16 B aligned.
+ * hyper (optional, DEVICE, 3 floats {lr, weight_decay, grad_scale}): when given it overrides the by-value lr /
+ * weight_decay and multiplies the gradient by grad_scale (1 / world size after a sum all-reduce), so a launch that
+ * was captured into a CUDA graph follows a learning-rate scheduler (ReduceLROnPlateau, rb/main_molecules.py:89-130). */
 int dgn_adam_step(int64_t n, float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float lr, float beta1,
-                  float beta2, float eps, float weight_decay, int32_t* state, void* stream);
+                  float beta2, float eps, float weight_decay, const float* hyper, int32_t* state, void* stream);
 
 /* C (+)= op(A) * op(B) in fp32 accuracy on the tcgen05 tensor cores (3xTF32 split, fp32 accumulation in tensor
  * memory).  Replaces the library GEMMs of the pre/post-transform MLPs (FCLayer, rb/nets/layers.py:76-100).
