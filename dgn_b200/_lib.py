@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DGN_LIB_PATH") or os.path.join(_HERE, "libdgn_b200.so")
 
 MAX_AGG, MAX_SCALERS, MAX_SLOTS = 32, 4, 8
-ABI_VERSION = 4
+ABI_VERSION = 6
 NORM_WS_PER_COL = 640
 
 # DgnAggKind / DgnScalerKind / DgnMsgMode
@@ -63,7 +63,7 @@ class DgnNormArgs(C.Structure):
                 ("y_bias", C.c_void_p), ("snorm", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("running_mean", C.c_void_p),
                 ("running_var", C.c_void_p), ("momentum", C.c_float), ("eps", C.c_float), ("training", C.c_int32),
                 ("relu", C.c_int32), ("residual", C.c_void_p), ("ld_res", C.c_int32), ("out", C.c_void_p),
-                ("ld_o", C.c_int32), ("stats", C.c_void_p), ("n_rows_dev", C.c_void_p)]
+                ("ld_o", C.c_int32), ("stats", C.c_void_p), ("n_rows_dev", C.c_void_p), ("stat_parts", C.c_int32)]
 
 
 class DgnNormGrad(C.Structure):
@@ -77,6 +77,17 @@ class DgnHeadArgs(C.Structure):
                 ("x", C.c_void_p), ("ld_x", C.c_int32), ("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p),
                 ("b2", C.c_void_p), ("w3", C.c_void_p), ("b3", C.c_void_p), ("a1", C.c_void_p), ("a2", C.c_void_p),
                 ("y", C.c_void_p), ("ld_y", C.c_int32)]
+
+
+class DgnPostArgs(C.Structure):
+    _fields_ = [("n_rows", C.c_int32), ("n_lead", C.c_int32), ("n_agg", C.c_int32), ("n_out", C.c_int32),
+                ("n_scalers", C.c_int32), ("scaler_kind", C.c_uint8 * MAX_SCALERS), ("avg_log", C.c_float),
+                ("log_deg", C.c_void_p), ("cat", C.c_void_p), ("ld_cat", C.c_int32), ("w", C.c_void_p),
+                ("ld_w", C.c_int32)]
+
+
+class DgnPostStats(C.Structure):
+    _fields_ = [("stats", C.c_void_p), ("y_bias", C.c_void_p), ("snorm", C.c_void_p), ("n_rows_dev", C.c_void_p)]
 
 
 class DgnHeadGrad(C.Structure):
@@ -109,6 +120,13 @@ SIGNATURES = {
     "dgn_gemm_tf32x3": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                   C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                   C.c_void_p]),
+    "dgn_post_forward": (C.c_int, [C.POINTER(DgnPostArgs), C.c_void_p, C.c_int32, C.POINTER(DgnPostStats),
+                                   C.POINTER(C.c_int32), C.c_void_p]),
+    "dgn_post_backward": (C.c_int, [C.POINTER(DgnPostArgs), C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
+    "dgn_post_wgrad": (C.c_int, [C.POINTER(DgnPostArgs), C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
+                                 C.c_void_p]),
+    "dgn_pre_wgrad": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
+                                C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
     "dgn_pair_linear_forward": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
                                           C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
     "dgn_pair_linear_backward": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,

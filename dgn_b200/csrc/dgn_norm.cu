@@ -79,20 +79,38 @@ __device__ __forceinline__ void merged_stats(const DgnNormArgs& a, int n, int co
                                              float (&s_mu)[kTY][kTX], float (&s_m2)[kTY][kTX], float& mean,
                                              float& var) {
   constexpr int PER = kParts / kTY;
-  float pm[PER], p2[PER], pn[PER];
-#pragma unroll
-  for (int j = 0; j < PER; ++j) {
-    const int p = threadIdx.y + j * kTY;
-    int r0, r1;
-    slab(n, p, r0, r1);
-    const float* part = a.stats + 2 * a.n_cols + (size_t)p * 2 * a.n_cols;
-    pn[j] = (float)(r1 - r0);
-    pm[j] = (col < a.n_cols) ? part[col] : 0.f;
-    p2[j] = (col < a.n_cols) ? part[a.n_cols + col] : 0.f;
-  }
   float cnt = 0.f, mu = 0.f, m2 = 0.f;
+  if (a.stat_parts > 0) {
+    // slabs written by dgn_post_forward (explicit counts): [cnt | mean | M2][C] each, merged in slab order
+    for (int p0 = threadIdx.y; p0 < a.stat_parts; p0 += 4 * kTY) {
+      float pn[4], pm[4], p2[4];
 #pragma unroll
-  for (int j = 0; j < PER; ++j) welford_merge(cnt, mu, m2, pn[j], pm[j], p2[j]);
+      for (int j = 0; j < 4; ++j) {                    // independent loads, issued together
+        const int p = p0 + j * kTY;
+        const bool ok = p < a.stat_parts && col < a.n_cols;
+        const float* part = a.stats + 2 * a.n_cols + (size_t)p * 3 * a.n_cols;
+        pn[j] = ok ? part[col] : 0.f;
+        pm[j] = ok ? part[a.n_cols + col] : 0.f;
+        p2[j] = ok ? part[2 * a.n_cols + col] : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) welford_merge(cnt, mu, m2, pn[j], pm[j], p2[j]);
+    }
+  } else {
+    float pm[PER], p2[PER], pn[PER];
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      const int p = threadIdx.y + j * kTY;
+      int r0, r1;
+      slab(n, p, r0, r1);
+      const float* part = a.stats + 2 * a.n_cols + (size_t)p * 2 * a.n_cols;
+      pn[j] = (float)(r1 - r0);
+      pm[j] = (col < a.n_cols) ? part[col] : 0.f;
+      p2[j] = (col < a.n_cols) ? part[a.n_cols + col] : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < PER; ++j) welford_merge(cnt, mu, m2, pn[j], pm[j], p2[j]);
+  }
   s_cnt[threadIdx.y][threadIdx.x] = cnt;
   s_mu[threadIdx.y][threadIdx.x] = mu;
   s_m2[threadIdx.y][threadIdx.x] = m2;
@@ -452,7 +470,7 @@ extern "C" int dgn_norm_forward(const DgnNormArgs* a, void* stream) {
   if (a->n_rows == 0) return DGN_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const dim3 block(kTX, kTY);
-  if (a->gamma && a->training) {
+  if (a->gamma && a->training && a->stat_parts <= 0) {
     launch_pdl(norm_stats_kernel, dim3(kParts, (a->n_cols + kTX - 1) / kTX), block, 0, st, *a);
     if (int rc = check_launch()) return rc;
   }

@@ -4,9 +4,14 @@
 layer a fixed chain
 
     P = h W_src^T, Q = h W_dst^T                         1 launch (node level), dgn_pair_linear_forward
-    cat = [h | scalers(aggregators(P[u] + Q[v] + b))]    dgn_agg_forward      (b fused as q_bias)
-    y = cat W_post^T                                     1 GEMM (dgn_gemm_tf32x3)
+    cat = [h | aggregators(P[u] + Q[v] + b)]             dgn_agg_forward      (b fused as q_bias; RAW aggregates)
+    y = h W_h^T + sum_s c_s(v) (agg W_s^T)               dgn_post_forward     (scalers folded into the GEMM epilogue:
+                                                                               the [N, S*A*F] concatenation of
+                                                                               rb/nets/dgn_layer.py:94-96 never exists)
     out = relu(BN((y + b_post) * snorm_n)) + h           dgn_norm_forward     (b_post fused as y_bias)
+
+(shapes the folded kernels do not take - widths that are not multiples of 4, towers in one launch - fall back to the
+scaled ``[N, (1 + S*A) F]`` concatenation and the generic ``dgn_gemm_tf32x3``.)
 
 Running that chain through generic autograd costs ~50 kernels per layer and direction in glue: slice
 backward, gradient accumulation adds, bias-gradient reductions, fills.  This node owns the whole chain
@@ -23,7 +28,7 @@ import torch
 
 from . import _lib, ops
 from .ops import (agg_backward_raw, agg_forward_raw, gemm, norm_backward_raw, norm_forward_raw, pair_linear_backward,
-                  pair_linear_forward, side_queue, _f32c, _need_cuda)
+                  pair_linear_forward, post_backward, post_forward, post_wgrad, pre_wgrad, side_queue, _f32c, _need_cuda)
 
 _ONES = {}
 
@@ -40,12 +45,16 @@ def _ones(n, device):
 class LayerConfig:
     """Non-tensor state of one fused layer call."""
     __slots__ = ("graph", "spec", "eig", "snorm", "bn", "training", "relu", "residual", "direct", "in_dim",
-                 "has_pretrans", "params")
+                 "has_pretrans", "params", "aspec", "post")
 
-    def __init__(self, graph, spec, eig, snorm, bn, training, relu, residual, direct, in_dim, has_pretrans, params):
+    def __init__(self, graph, spec, eig, snorm, bn, training, relu, residual, direct, in_dim, has_pretrans, params,
+                 spec_raw=None, post=None):
         self.graph, self.spec, self.eig, self.snorm, self.bn = graph, spec, eig, snorm, bn
         self.training, self.relu, self.residual, self.direct = training, relu, residual, direct
         self.in_dim, self.has_pretrans, self.params = in_dim, has_pretrans, params
+        # folded path: the aggregation runs with the single-scaler spec (raw aggregates), `post` folds the scalers
+        self.post = post if (post is not None and spec_raw is not None) else None
+        self.aspec = spec_raw if self.post is not None else spec
 
 
 class _FusedLayer(torch.autograd.Function):
@@ -53,7 +62,7 @@ class _FusedLayer(torch.autograd.Function):
     def forward(ctx, cfg, h, R, W_pre, b_pre, W_post, b_post, gamma, beta):
         _need_cuda(h)
         h = _f32c(h)
-        g, spec, Fi = cfg.graph, cfg.spec, cfg.in_dim
+        g, spec, Fi = cfg.graph, cfg.aspec, cfg.in_dim
         N, dev = h.shape[0], h.device
         P = Q = None
         if cfg.has_pretrans:
@@ -63,8 +72,7 @@ class _FusedLayer(torch.autograd.Function):
         else:                                            # simple layer: message = h[src], no h block
             cat = torch.empty((N, spec.out_width), device=dev, dtype=torch.float32)
             agg_forward_raw(g, spec, _lib.MSG_SOURCE, h, None, None, h, cfg.eig, cat, False)
-        y = gemm(cat, W_post)                            # cat @ W_post^T
-        Co = y.shape[1]
+        Co = W_post.shape[0]
         out = torch.empty((N, Co), device=dev, dtype=torch.float32)
         stats = torch.empty(_lib.NORM_WS_PER_COL * Co, device=dev, dtype=torch.float32)
         bn = cfg.bn
@@ -73,6 +81,15 @@ class _FusedLayer(torch.autograd.Function):
             if cfg.training:
                 ops.count_bn_batch(bn)
             use_batch = cfg.training or not bn.track_running_stats
+        stat_parts = 0
+        if cfg.post is not None:                         # h W_h^T + sum_s c_s (agg W_s^T): scalers folded in the epilogue
+            y = torch.empty((N, Co), device=dev, dtype=torch.float32)
+            if N > 0:
+                want_stats = bn is not None and use_batch      # BatchNorm partial statistics as a by-product
+                stat_parts = post_forward(cfg.post, g, cat, W_post, y, stats if want_stats else None, b_post, cfg.snorm,
+                                          getattr(g, "n_rows_dev", None))
+        else:
+            y = gemm(cat, W_post)                        # cat @ W_post^T
         nargs = norm_forward_raw(
             y, out, stats, snorm=cfg.snorm, y_bias=b_post,
             gamma=gamma if bn is not None else None, beta=beta if bn is not None else None,
@@ -80,7 +97,7 @@ class _FusedLayer(torch.autograd.Function):
             running_var=bn.running_var if bn is not None else None,
             momentum=(0.1 if bn is None or bn.momentum is None else bn.momentum),
             eps=(1e-5 if bn is None else bn.eps), training=use_batch, relu=cfg.relu,
-            residual=h if cfg.residual else None, n_rows_dev=getattr(g, "n_rows_dev", None))
+            residual=h if cfg.residual else None, n_rows_dev=getattr(g, "n_rows_dev", None), stat_parts=stat_parts)
         ctx.cfg, ctx.nargs = cfg, nargs
         ctx.save_for_backward(h, R, P, Q, cat, y, stats, W_pre, b_pre, W_post, b_post, gamma, beta)
         return out
@@ -89,7 +106,7 @@ class _FusedLayer(torch.autograd.Function):
     def backward(ctx, g_out):
         cfg = ctx.cfg
         h, R, P, Q, cat, y, stats, W_pre, b_pre, W_post, b_post, gamma, beta = ctx.saved_tensors
-        g, spec, Fi = cfg.graph, cfg.spec, cfg.in_dim
+        g, spec, Fi = cfg.graph, cfg.aspec, cfg.in_dim
         N, E, dev = h.shape[0], g.number_of_edges(), h.device
         g_out = g_out.contiguous()
         Co = y.shape[1]
@@ -109,18 +126,29 @@ class _FusedLayer(torch.autograd.Function):
         norm_backward_raw(ctx.nargs, g_out, d_y, scratch, d_gamma, d_beta, d_bpost, accumulate=direct)
 
         # ---- posttrans GEMM --------------------------------------------------------------------------------------------
-        d_cat = gemm(d_y, W_post, b_kmajor=False)        # d_y @ W_post
+        fold = cfg.post is not None and N > 0
+        if fold:
+            d_cat = torch.empty_like(cat)                # [d_y W_h | sum_s c_s (d_y W_s)]: gradient of [h | raw aggregates]
+            post_backward(cfg.post, g, cat, W_post, d_y, d_cat)
+        else:
+            d_cat = gemm(d_y, W_post, b_kmajor=False)    # d_y @ W_post
         # dW_post = d_y^T @ cat, computed as (cat^T @ d_y)^T so the 128-row tile dimension is the wide one.
         # Weight gradients are off the critical path: with direct accumulation they run on the side stream.
         side = side_queue(dev) if direct else None
         if direct:
             def _dw_post():
-                gemm(cat, d_y, a_kmajor=False, b_kmajor=False, out=pW_post.grad, accumulate=True, c_transposed=True)
+                if fold:
+                    post_wgrad(cfg.post, g, cat, W_post, d_y, pW_post.grad, True)
+                else:
+                    gemm(cat, d_y, a_kmajor=False, b_kmajor=False, out=pW_post.grad, accumulate=True, c_transposed=True)
             if side is not None:
                 side.run(_dw_post, keep=(cat, d_y))
             else:
                 _dw_post()
             d_Wpost = None
+        elif fold:
+            d_Wpost = torch.empty_like(W_post)
+            post_wgrad(cfg.post, g, cat, W_post, d_y, d_Wpost, False)
         else:
             d_Wpost = gemm(cat, d_y, a_kmajor=False, b_kmajor=False, c_transposed=True)
 
@@ -144,6 +172,8 @@ class _FusedLayer(torch.autograd.Function):
                 ones = _ones(N, dev)
 
                 def _dw_pre():
+                    if ops.FOLD_ENABLED and pre_wgrad(h, d_P, d_Q, gW, pb_pre.grad, True):   # one launch: both halves + bias
+                        return
                     gemm(d_P, h, a_kmajor=False, b_kmajor=False, out=gW[:, :Fi], accumulate=True)          # += d_P^T @ h
                     gemm(d_Q, h, a_kmajor=False, b_kmajor=False, out=gW[:, Fi:2 * Fi], accumulate=True)    # += d_Q^T @ h
                     pb_pre.grad.addmv_(d_Q.t(), ones)
@@ -155,9 +185,11 @@ class _FusedLayer(torch.autograd.Function):
                     _dw_pre()
             else:
                 d_Wpre = torch.zeros_like(W_pre)          # columns past 2F (edge features) get theirs via R
-                gemm(d_P, h, a_kmajor=False, b_kmajor=False, out=d_Wpre[:, :Fi])
-                gemm(d_Q, h, a_kmajor=False, b_kmajor=False, out=d_Wpre[:, Fi:2 * Fi])
-                d_bpre = torch.mv(d_Q.t(), _ones(N, dev))
+                d_bpre = torch.empty_like(b_pre)
+                if not (ops.FOLD_ENABLED and N > 0 and pre_wgrad(h, d_P, d_Q, d_Wpre, d_bpre, False)):
+                    gemm(d_P, h, a_kmajor=False, b_kmajor=False, out=d_Wpre[:, :Fi])
+                    gemm(d_Q, h, a_kmajor=False, b_kmajor=False, out=d_Wpre[:, Fi:2 * Fi])
+                    d_bpre = torch.mv(d_Q.t(), _ones(N, dev))
         else:
             # x and h_in are the same tensor: the kernel folds d_h_in (+ residual) into the scattered gradient
             d_x = torch.empty((N, Fi), device=dev, dtype=torch.float32)
@@ -170,7 +202,7 @@ class _FusedLayer(torch.autograd.Function):
 
 
 def fused_layer(graph, spec, eig, h, R, pretrans_lin, posttrans_lin, bn, snorm, training, relu, residual, in_dim,
-                direct_grads=None):
+                direct_grads=None, spec_raw=None, post=None):
     """One DGN layer (complex / tower when ``pretrans_lin`` is given, simple otherwise) as a single autograd node.
 
     ``direct_grads``: accumulate parameter gradients in place when every parameter already has ``.grad``; defaults
@@ -190,5 +222,6 @@ def fused_layer(graph, spec, eig, h, R, pretrans_lin, posttrans_lin, bn, snorm, 
         if not snorm.is_contiguous():
             snorm = snorm.contiguous()
     eig = _f32c(eig)
-    cfg = LayerConfig(graph, spec, eig, snorm, bn, training, relu, residual, direct_grads, in_dim, has_pre, params)
+    cfg = LayerConfig(graph, spec, eig, snorm, bn, training, relu, residual, direct_grads, in_dim, has_pre, params,
+                      spec_raw, post)
     return _FusedLayer.apply(cfg, h, R, W_pre, b_pre, posttrans_lin.weight, posttrans_lin.bias, gamma, beta)

@@ -24,7 +24,7 @@ import torch.nn.functional as F
 
 from dgn_b200 import _lib
 from dgn_b200.fused import fused_layer
-from dgn_b200.ops import AggSpec, aggregate, norm_act, readout
+from dgn_b200.ops import AggSpec, PostSpec, aggregate, norm_act, readout
 
 from .aggregators import AGGREGATORS
 from .layers import MLP, FCLayer
@@ -54,6 +54,21 @@ class _FusedConv(nn.Module):
             self._specs[n_eig] = sp
         return sp
 
+    def _folded(self, n_eig, lead, n_out):
+        """(raw-aggregate spec, PostSpec) of the scaler-folded path, or (None, None) when the shapes are outside it."""
+        key = ("fold", n_eig, lead, n_out)
+        ent = self._specs.get(key)
+        if ent is None:
+            spec = self._spec(n_eig)
+            post = PostSpec(spec, lead, n_out)
+            if post.supported(spec):
+                raw = AggSpec(self.aggregators, [SCALERS["identity"]], spec.avg_log, self.in_dim, n_eig)
+                ent = (raw, post)
+            else:
+                ent = (None, None)
+            self._specs[key] = ent
+        return ent
+
     @staticmethod
     def _eig(g, like):
         eig = g.ndata["eig"]
@@ -78,9 +93,12 @@ class _FusedConv(nn.Module):
         R = None
         if pre is not None and self.edge_features:
             R = F.linear(e, pre.weight[:, 2 * self.in_dim:])            # per-edge term W_e ef, edge-id order
+        spec_raw, pspec = self._folded(eig.shape[1], self.in_dim if pre is not None else 0, post.out_features)
+        if pspec is not None and post.in_features != pspec.w_cols:
+            spec_raw = pspec = None
         out = fused_layer(g, self._spec(eig.shape[1]), eig, h, R, pre, post,
                           self.batchnorm_h if self.batch_norm else None, snorm_n if self.graph_norm else None,
-                          self.training, relu, residual, self.in_dim)
+                          self.training, relu, residual, self.in_dim, spec_raw=spec_raw, post=pspec)
         if self.dropout and self.training:
             out = F.dropout(out, self.dropout, training=True)
         return out

@@ -193,7 +193,7 @@ def aggregate(graph, spec: AggSpec, mode: int, h_in, eig, x=None, q=None, r=None
 
 def norm_forward_raw(y, out, stats, snorm=None, y_bias=None, gamma=None, beta=None, running_mean=None,
                      running_var=None, momentum=0.1, eps=1e-5, training=True, relu=True, residual=None,
-                     n_rows_dev=None):
+                     n_rows_dev=None, stat_parts=0):
     """dgn_norm_forward on pre-allocated tensors; returns the filled DgnNormArgs (needed by the backward)."""
     N, Cn = y.shape
     a = _lib.DgnNormArgs()
@@ -212,8 +212,9 @@ def norm_forward_raw(y, out, stats, snorm=None, y_bias=None, gamma=None, beta=No
     a.out, a.ld_o, a.stats = out.data_ptr(), out.stride(0), stats.data_ptr()
     if n_rows_dev is not None:
         a.n_rows_dev = n_rows_dev.data_ptr()
+    a.stat_parts = int(stat_parts)
     check(lib.dgn_norm_forward(C.byref(a), _stream(y)), "dgn_norm_forward")
-    _count(2 if (gamma is not None and training) else 1)
+    _count(2 if (gamma is not None and training and not stat_parts) else 1)
     return a
 
 
@@ -439,6 +440,77 @@ def gemm(a, b, a_kmajor=True, b_kmajor=True, out=None, accumulate=False, c_trans
     else:
         torch.mm(A, Bm, out=out)
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# scaler-folded posttrans products (dgn_post_*): the [N, S*A*F] concatenation never exists
+# ---------------------------------------------------------------------------------------------------------
+FOLD_ENABLED = os.environ.get("DGN_NO_FOLD", "0") != "1"
+
+
+class PostSpec:
+    """Shapes / scalers of one layer's posttrans for ``dgn_post_*``: ``cat = [h (lead columns) | raw aggregates]``."""
+
+    def __init__(self, spec: AggSpec, lead: int, n_out: int):
+        self.lead, self.n_agg, self.n_out = int(lead), spec.A * spec.F, int(n_out)
+        self.S_decl, self.S = spec.S_decl, spec.S
+        self.kinds = [sc.kind for sc in spec.scalers]
+        self.avg_log = spec.avg_log
+        self.w_cols = self.lead + self.S * self.n_agg
+
+    def supported(self, spec: AggSpec) -> bool:
+        return (FOLD_ENABLED and spec.Fg == spec.F and self.lead % 4 == 0 and self.n_agg % 4 == 0 and
+                self.n_out % 4 == 0 and self.w_cols % 4 == 0)
+
+    def args(self, graph, cat, W):
+        a = _lib.DgnPostArgs()
+        a.n_rows, a.n_lead, a.n_agg, a.n_out, a.n_scalers = cat.shape[0], self.lead, self.n_agg, self.n_out, self.S_decl
+        for i, k in enumerate(self.kinds):
+            a.scaler_kind[i] = k
+        a.avg_log = self.avg_log
+        a.log_deg = graph.log_deg.data_ptr()
+        a.cat, a.ld_cat, a.w, a.ld_w = cat.data_ptr(), cat.stride(0), W.data_ptr(), W.stride(0)
+        return a
+
+
+def post_forward(ps: PostSpec, graph, cat, W, y, stats=None, y_bias=None, snorm=None, n_rows_dev=None):
+    """``y = h W_h^T + sum_s c_s (agg W_s^T)``.  With ``stats`` (the workspace of the norm call that follows) the kernel
+    also leaves partial batch statistics of ``(y + y_bias) * snorm`` there; returns their number (0 = not written)."""
+    st, parts = None, C.c_int32(0)
+    if stats is not None:
+        st = _lib.DgnPostStats(stats.data_ptr(), y_bias.data_ptr() if y_bias is not None else None,
+                               snorm.data_ptr() if snorm is not None else None,
+                               n_rows_dev.data_ptr() if n_rows_dev is not None else None)
+    check(lib.dgn_post_forward(C.byref(ps.args(graph, cat, W)), y.data_ptr(), y.stride(0),
+                               C.byref(st) if st is not None else None, C.byref(parts), _stream(cat)),
+          "dgn_post_forward")
+    _count(1)
+    return int(parts.value)
+
+
+def post_backward(ps: PostSpec, graph, cat, W, d_y, d_cat):
+    check(lib.dgn_post_backward(C.byref(ps.args(graph, cat, W)), d_y.data_ptr(), d_y.stride(0), d_cat.data_ptr(),
+                                d_cat.stride(0), _stream(cat)), "dgn_post_backward")
+    _count(1)
+
+
+def post_wgrad(ps: PostSpec, graph, cat, W, d_y, d_w, accumulate):
+    check(lib.dgn_post_wgrad(C.byref(ps.args(graph, cat, W)), d_y.data_ptr(), d_y.stride(0), d_w.data_ptr(),
+                             d_w.stride(0), int(accumulate), _stream(cat)), "dgn_post_wgrad")
+    _count(1)
+
+
+def pre_wgrad(h, d_P, d_Q, d_w, d_b, accumulate):
+    """``d_w[:, :Fi] (+)= d_P^T h ; d_w[:, Fi:2Fi] (+)= d_Q^T h ; d_b (+)= sum_rows d_Q`` in one launch; returns False
+    when the shapes are outside the kernel's range (callers then use the generic GEMMs)."""
+    rc = lib.dgn_pre_wgrad(h.shape[0], h.shape[1], d_P.shape[1], h.data_ptr(), h.stride(0), d_P.data_ptr(),
+                           d_P.stride(0), d_Q.data_ptr(), d_Q.stride(0), d_w.data_ptr(), d_w.stride(0),
+                           d_b.data_ptr() if d_b is not None else None, int(accumulate), _stream(h))
+    if rc == -2:
+        return False
+    check(rc, "dgn_pre_wgrad")
+    _count(1)
+    return True
 
 
 # ---------------------------------------------------------------------------------------------------------

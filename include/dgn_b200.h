@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define DGN_ABI_VERSION 4
+#define DGN_ABI_VERSION 6
 #define DGN_MAX_AGG 32      /* aggregators per layer (the reference registry has 24)        */
 #define DGN_MAX_SCALERS 4   /* scalers per layer (the reference registry has 3)             */
 #define DGN_MAX_SLOTS 8     /* distinct eigen-weighted feature sums one launch can carry    */
@@ -231,6 +231,8 @@ typedef struct {
   float* out;              int32_t ld_o;
   float* stats;            /* [DGN_NORM_WS_FLOATS(C)] workspace, see above                              */
   const int32_t* n_rows_dev;
+  int32_t stat_parts;      /* > 0: `stats` already holds that many partial batch statistics written by
+                              dgn_post_forward (DgnPostStats): the statistics pass is skipped (one launch)      */
 } DgnNormArgs;
 
 int dgn_norm_forward(const DgnNormArgs* a, void* stream);
@@ -283,6 +285,57 @@ int64_t dgn_gemm_ws_floats(void);
 int dgn_gemm_tf32x3(int32_t M, int32_t N, int32_t K, const float* A, int32_t lda, int32_t a_kmajor, const float* B,
                     int32_t ldb, int32_t b_kmajor, float* C, int32_t ldc, int32_t accumulate, int32_t c_transposed,
                     float* ws, void* stream);
+
+/* Scaler-folded posttrans of one DGN layer.  The reference concatenates the aggregates once per scaler,
+ * cat = [h | c_0 agg | ... | c_{S-1} agg] (rb/nets/dgn_layer.py:94-96, :116) and applies posttrans to it (:119).  c_s is a
+ * per-node factor (rb/nets/scalers.py:7-21), so with W = [W_h | W_0 | ... | W_{S-1}]
+ *     y[v] = h[v] W_h^T + sum_s c_s(v) (agg[v] W_s^T)
+ * and the [N, S*A*F] tensor never has to exist: `cat` here is [h | agg] with the RAW aggregates (dgn_agg_forward with a
+ * single scaler), one fp32 accumulator per scaler lives in tensor memory and the epilogue folds them with c_s(v).
+ *   dgn_post_forward   y = the expression above (no bias; dgn_norm_forward adds it as y_bias)
+ *   dgn_post_backward  d_cat[:, :F] = d_y W_h ; d_cat[:, F + c] = sum_s c_s(v) (d_y W_s)[c]   (gradient of `cat`)
+ *   dgn_post_wgrad     d_w (+)= [ d_y^T h | (c_0 d_y)^T agg | ... ]                             (gradient of `w`)
+ * tcgen05 3xTF32 like dgn_gemm_tf32x3; split-K partial tiles are reduced across a thread-block cluster through
+ * distributed shared memory (deterministic, no workspace).  All widths / leading dimensions multiples of 4 floats,
+ * pointers 16 B aligned, else DGN_ERR_UNSUPPORTED. */
+typedef struct {
+  int32_t n_rows;          /* N (row capacity of a padded batch)                                               */
+  int32_t n_lead;          /* F: leading columns of cat that no scaler touches (the copy of h; 0 = none)        */
+  int32_t n_agg;           /* A*F: columns of raw aggregates                                                    */
+  int32_t n_out;           /* F_out                                                                             */
+  int32_t n_scalers;       /* S as declared; like rb/nets/dgn_layer.py:95 the scalers are applied only if S > 1 */
+  uint8_t scaler_kind[DGN_MAX_SCALERS];
+  float avg_log;           /* avg_d["log"]                                                                      */
+  const float* log_deg;    /* [N] log(in_degree + 1) (DgnGraph.log_deg)                                         */
+  const float* cat;        /* [N, n_lead + n_agg]                                                               */
+  int32_t ld_cat;
+  const float* w;          /* [n_out, n_lead + S*n_agg]  posttrans weight (nn.Linear layout)                    */
+  int32_t ld_w;
+} DgnPostArgs;
+
+/* Optional by-product of dgn_post_forward: partial batch statistics (count, mean, M2 per column and per row slab) of
+ * z = (y + y_bias) * snorm, i.e. of what BatchNorm1d normalises at rb/nets/dgn_layer.py:122-126, written into the
+ * workspace of the dgn_norm_forward call that follows.  *stat_parts receives the number of slabs (pass it on as
+ * DgnNormArgs.stat_parts), 0 when the layout does not fit the workspace (then run the norm's own statistics pass). */
+typedef struct {
+  float* stats;              /* DgnNormArgs.stats of the following dgn_norm_forward, [DGN_NORM_WS_FLOATS(n_out)] */
+  const float* y_bias;       /* [n_out] or NULL                                                                */
+  const float* snorm;        /* [N] or NULL                                                                    */
+  const int32_t* n_rows_dev; /* device int32: real row count of a padded batch, or NULL                        */
+} DgnPostStats;
+
+int dgn_post_forward(const DgnPostArgs* a, float* y, int32_t ld_y, const DgnPostStats* st, int32_t* stat_parts,
+                     void* stream);
+int dgn_post_backward(const DgnPostArgs* a, const float* d_y, int32_t ld_dy, float* d_cat, int32_t ld_dcat, void* stream);
+int dgn_post_wgrad(const DgnPostArgs* a, const float* d_y, int32_t ld_dy, float* d_w, int32_t ld_dw, int32_t accumulate,
+                   void* stream);
+
+/* Weight / bias gradient of the 1-layer pretrans split per node (rb/nets/dgn_layer.py:75-80), one launch:
+ *   d_w[:, :Fi] (+)= d_P^T h ;  d_w[:, Fi:2Fi] (+)= d_Q^T h ;  d_b (+)= column sums of d_Q   (d_b may be NULL)
+ * h [N, Fi], d_P / d_Q [N, Fo] with one common leading dimension, d_w [Fo, >= 2 Fi]. */
+int dgn_pre_wgrad(int32_t n_rows, int32_t f_in, int32_t f_out, const float* h, int32_t ld_h, const float* d_p,
+                  int32_t ld_dp, const float* d_q, int32_t ld_dq, float* d_w, int32_t ld_dw, float* d_b,
+                  int32_t accumulate, void* stream);
 
 /* Node-level halves of the 1-layer pretrans (rb/nets/dgn_layer.py:75-80) in one launch each, straight from the
  * parameter W = [W_src | W_dst | ...] of shape [Fo, ld_w >= 2*Fi]:

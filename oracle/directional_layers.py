@@ -7,6 +7,7 @@ TEST INFRASTRUCTURE (see oracle/__init__.py).  Follows realworld_benchmark/nets/
 * ``TowerConv``    = DGNTower         :205-276   (no ReLU, no residual)
 * ``TowerStack``   = DGNLayerTower    :279-325
 * ``DGNLayer``     = factory          :328-352   (callers use ``.model``)
+* ``VirtualNode``  = VirtualNode      :12-49     (PCBA net only)
 
 It runs the same execution structure as the reference - ``apply_edges`` with a pretrans UDF,
 then ``update_all`` whose reduce UDF is called once per distinct in-degree - which is why it
@@ -168,3 +169,33 @@ class DGNLayer(nn.Module):
             self.model = TowerStack(in_dim, out_dim, aggs, scs, avg_d, dropout, graph_norm, batch_norm, towers,
                                     pretrans_layers, posttrans_layers, divide_input, residual, edge_features,
                                     edge_dim)
+
+
+class VirtualNode(nn.Module):
+    """realworld_benchmark/nets/dgn_layer.py:12-49: per-graph pooled feature pushed through an FCLayer and added back
+    to every node of its graph."""
+
+    def __init__(self, dim, dropout, batch_norm=False, bias=True, residual=True, vn_type="mean"):
+        super().__init__()
+        self.vn_type = vn_type.lower()
+        self.fc_layer = FCLayer(in_size=dim, out_size=dim, activation="relu", dropout=dropout, b_norm=batch_norm,
+                                bias=bias)
+        self.residual = residual
+
+    def forward(self, g, h, vn_h):
+        from . import use_standin_dgl
+        dgl = use_standin_dgl()
+        g.ndata["h"] = h
+        if self.vn_type == "mean":                                        # :25-33
+            pool = dgl.mean_nodes(g, "h")
+        elif self.vn_type == "sum":
+            pool = dgl.sum_nodes(g, "h")
+        elif self.vn_type == "logsum":
+            lognum = torch.log(torch.tensor(g.batch_num_nodes, dtype=h.dtype, device=h.device))
+            pool = dgl.mean_nodes(g, "h") * lognum.unsqueeze(-1)
+        else:
+            raise ValueError("Undefined input %r. Accepted values are sum, mean, logsum" % self.vn_type)
+        vn_new = self.fc_layer(vn_h + pool)                               # :37-41
+        vn_h = vn_h + vn_new if self.residual else vn_new
+        spread = torch.cat([vn_h[i:i + 1].repeat(n, 1) for i, n in enumerate(g.batch_num_nodes)], dim=0)   # :44-46
+        return vn_h, h + spread

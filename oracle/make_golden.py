@@ -119,11 +119,11 @@ def layer_case(rl, samples, type_net, F, aggs, scalers, towers, edge_dim, avg_lo
     return out
 
 
-def net_case(DGNNet, samples, avg_log, seed, type_net="complex", aggs="mean dir1-dx", edge_feat=False):
+def net_case(DGNNet, samples, avg_log, seed, type_net="complex", aggs="mean dir1-dx", edge_feat=False, readout="mean"):
     from oracle.graphs import collate_standin
     g, labels, snorm_n, snorm_e = collate_standin(samples)
     params = dict(num_atom_type=28, num_bond_type=4, hidden_dim=16, out_dim=16, in_feat_dropout=0.0, dropout=0.0,
-                  L=3, type_net=type_net, pos_enc_dim=0, readout="mean", graph_norm=True, batch_norm=True,
+                  L=3, type_net=type_net, pos_enc_dim=0, readout=readout, graph_norm=True, batch_norm=True,
                   aggregators=aggs, scalers=SCALERS3, avg_d={"log": torch.tensor(avg_log, dtype=torch.float32)},
                   residual=True, edge_feat=edge_feat, edge_dim=8 if edge_feat else 0, pretrans_layers=1,
                   posttrans_layers=1, device="cpu")
@@ -139,14 +139,57 @@ def net_case(DGNNet, samples, avg_log, seed, type_net="complex", aggs="mean dir1
            "loss": _np(loss), "snorm_n": _np(snorm_n), "eig": _np(g.ndata["eig"]), "avg_log": np.float32(avg_log),
            "src": _np(g.edges()[0]).astype(np.int32), "dst": _np(g.edges()[1]).astype(np.int32),
            "batch_num_nodes": np.array(g.batch_num_nodes, dtype=np.int64), "type_net": np.array(type_net),
-           "aggregators": np.array(aggs), "edge_feat_flag": np.int64(edge_feat), "seed": np.int64(seed)}
+           "aggregators": np.array(aggs), "edge_feat_flag": np.int64(edge_feat), "seed": np.int64(seed),
+           "readout": np.array(readout)}
     out.update(_flat_state(net))
     for k, p in net.named_parameters():
         out["grad/" + k] = _np(p.grad) if p.grad is not None else np.zeros(tuple(p.shape), np.float32)
     return out
 
 
-def main():
+def mol_net_case(kind, samples, avg_log, seed, **over):
+    """HIV / PCBA DGNNet of the unmodified reference (on the ogb stand-in) - scores, loss, all parameter gradients."""
+    from oracle.graphs import collate_standin
+    if kind == "hiv":
+        from nets.HIV_graph_classification.dgn_net import DGNNet
+    else:
+        from nets.PCBA_graph_classification.dgn_net import DGNNet
+    g, labels, snorm_n, snorm_e = collate_standin(samples)
+    params = dict(hidden_dim=20, out_dim=20, in_feat_dropout=0.0, dropout=0.0, L=3, type_net="towers", pos_enc_dim=0,
+                  readout="mean", graph_norm=True, batch_norm=True,
+                  aggregators="mean max min dir1-dx dir2-dx dir1-av dir2-av", scalers="identity",
+                  avg_d={"log": torch.tensor(avg_log, dtype=torch.float32)}, residual=True, edge_feat=False, edge_dim=0,
+                  pretrans_layers=1, posttrans_layers=1, device="cpu", towers=5, decreasing_dim=True,
+                  virtual_node="none")
+    params.update(over)
+    torch.manual_seed(seed)
+    net = DGNNet(params)
+    net.train()
+    x, e = g.ndata["feat"], g.edata["feat"]
+    scores = net.forward(g, x, e, snorm_n, snorm_e)
+    if kind == "hiv":          # the reference's loss moves the labels to 'cuda' unconditionally (dgn_net.py:88)
+        targets = labels.float()
+        loss = torch.nn.BCEWithLogitsLoss()(scores, targets.unsqueeze(-1))
+    else:
+        rng = np.random.default_rng(seed)
+        targets = torch.tensor((rng.random((len(samples), 128)) < 0.3).astype(np.float32))
+        loss = net.loss(scores, targets)
+    loss.backward()
+    out = {"node_feat": _np(x), "edge_feat": _np(e), "targets": _np(targets), "scores": _np(scores), "loss": _np(loss),
+           "snorm_n": _np(snorm_n), "eig": _np(g.ndata["eig"]), "avg_log": np.float32(avg_log),
+           "src": _np(g.edges()[0]).astype(np.int32), "dst": _np(g.edges()[1]).astype(np.int32),
+           "batch_num_nodes": np.array(g.batch_num_nodes, dtype=np.int64), "seed": np.int64(seed),
+           "kind": np.array(kind)}
+    for k, v in params.items():
+        if isinstance(v, (int, float, bool, str)):
+            out["p/" + k] = np.array(v)
+    out.update(_flat_state(net))
+    for k, p in net.named_parameters():
+        out["grad/" + k] = _np(p.grad) if p.grad is not None else np.zeros(tuple(p.shape), np.float32)
+    return out
+
+
+def main(only_new=False):
     sys.path.insert(0, REPO)
     from dgn_b200.data.synthetic import make_samples, avg_log_degree
     ra, rs, rl, DGNNet = _import_reference()
@@ -154,8 +197,9 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     rng = np.random.default_rng(2020)
 
-    np.savez_compressed(os.path.join(OUT, "aggregators.npz"), **aggregator_cases(ra, rng))
-    np.savez_compressed(os.path.join(OUT, "scalers.npz"), **scaler_cases(rs, rng))
+    if not only_new:
+        np.savez_compressed(os.path.join(OUT, "aggregators.npz"), **aggregator_cases(ra, rng))
+        np.savez_compressed(os.path.join(OUT, "scalers.npz"), **scaler_cases(rs, rng))
 
     zinc = make_samples("zinc", 6, seed=7)
     cifar = make_samples("cifar", 2, seed=8, n_min=20, n_max=30)     # directed kNN, in-degree 0 possible
@@ -177,6 +221,22 @@ def main():
         "net_zinc_simple": net_case(DGNNet, zinc, avg_z, 41, "simple", "mean max dir1-dx dir1-av"),
         "net_zinc_edge": net_case(DGNNet, zinc, avg_z, 41, "complex", "mean dir1-dx dir2-av", edge_feat=True),
     }
+    if only_new:
+        cases = {}
+    # round 2: the remaining task nets (OGB encoders, towers through the net, virtual node) and the directional readouts
+    hiv = make_samples("molhiv", 5, seed=21)
+    avg_h = avg_log_degree(hiv)
+    cases.update({
+        "net_hiv_towers": mol_net_case("hiv", hiv, avg_h, 41),                          # 5 towers (the layer default)
+        "net_hiv_edge": mol_net_case("hiv", hiv, avg_h, 42, type_net="complex", edge_feat=True, edge_dim=8,
+                                     aggregators="mean dir1-dx dir1-av", scalers=SCALERS3),
+        "net_pcba_vn": mol_net_case("pcba", hiv, avg_h, 43, towers=4, virtual_node="mean"),
+        "net_pcba_logsum": mol_net_case("pcba", hiv, avg_h, 44, towers=2, virtual_node="logsum", decreasing_dim=False,
+                                        residual=False, hidden_dim=16, out_dim=16),
+        "net_zinc_directional": net_case(DGNNet, zinc, avg_z, 45, "simple", "mean dir1-dx dir1-av", readout="directional"),
+        "net_zinc_directional_abs": net_case(DGNNet, zinc, avg_z, 46, "complex", "mean max dir2-dx",
+                                             readout="directional_abs"),
+    })
     for name, payload in cases.items():
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **payload)
     for f in sorted(os.listdir(OUT)):
@@ -184,4 +244,4 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    main(only_new="--only-new" in sys.argv)

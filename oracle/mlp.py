@@ -70,9 +70,9 @@ class MLP(nn.Module):
 class MLPReadout(nn.Module):
     """realworld_benchmark/nets/mlp_readout_layer.py:11-30: L halving Linear+ReLU, then Linear."""
 
-    def __init__(self, input_dim, output_dim, L=2):
+    def __init__(self, input_dim, output_dim, L=2, decreasing_dim=True):
         super().__init__()
-        dims = [input_dim // 2 ** l for l in range(L + 1)]
+        dims = [input_dim // 2 ** l if decreasing_dim else input_dim for l in range(L + 1)]     # :13-18
         self.FC_layers = nn.ModuleList(
             [nn.Linear(dims[l], dims[l + 1], bias=True) for l in range(L)] + [nn.Linear(dims[L], output_dim, bias=True)])
         self.L = L

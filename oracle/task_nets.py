@@ -3,6 +3,8 @@
 * ``ZincNet``        realworld_benchmark/nets/molecules_graph_regression/dgn_net.py:8-92
 * ``PatternNet``     realworld_benchmark/nets/SBMs_node_classification/dgn_net.py:8-81
 * ``SuperpixelNet``  realworld_benchmark/nets/superpixels_graph_classification/dgn_net.py:7-78
+* ``HivNet``         realworld_benchmark/nets/HIV_graph_classification/dgn_net.py:13-88
+* ``PcbaNet``        realworld_benchmark/nets/PCBA_graph_classification/dgn_net.py:9-102
 
 Parameter names (``embedding_h``, ``layers.{i}.*``, ``MLP_layer.FC_layers.{l}``) and module
 construction order follow the reference so seeds and state_dicts interchange.
@@ -12,7 +14,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from .directional_layers import DGNLayer
+from .directional_layers import DGNLayer, VirtualNode
 from .mlp import MLPReadout
 from . import use_standin_dgl
 
@@ -124,3 +126,71 @@ class SuperpixelNet(nn.Module):
 
     def loss(self, pred, label):                            # :75-78
         return nn.CrossEntropyLoss()(pred, label)
+
+
+def _mol_encoders():
+    use_standin_dgl()                       # puts oracle/standin (dgl AND the ogb stand-in) on sys.path
+    from ogb.graphproppred.mol_encoder import AtomEncoder, BondEncoder
+    return AtomEncoder, BondEncoder
+
+
+class HivNet(nn.Module):
+    def __init__(self, net_params):
+        super().__init__()
+        p = net_params
+        AtomEncoder, BondEncoder = _mol_encoders()
+        self.pos_enc_dim, self.readout, self.edge_feat = p["pos_enc_dim"], p["readout"], p["edge_feat"]
+        if self.pos_enc_dim > 0:
+            self.embedding_pos_enc = nn.Linear(self.pos_enc_dim, p["hidden_dim"])
+        self.in_feat_dropout = nn.Dropout(p["in_feat_dropout"])
+        self.embedding_h = AtomEncoder(emb_dim=p["hidden_dim"])
+        if self.edge_feat:
+            self.embedding_e = BondEncoder(emb_dim=p["edge_dim"])
+        self.layers = _conv_stack(p)         # the reference does not forward `towers` here (layer default: 5)
+        self.MLP_layer = MLPReadout(p["out_dim"], 1)
+
+    def forward(self, g, h, e, snorm_n, snorm_e):           # HIV dgn_net.py:62-84
+        h = self.in_feat_dropout(self.embedding_h(h))
+        if self.pos_enc_dim > 0:
+            h = h + self.embedding_pos_enc(g.ndata["pos_enc"])
+        if self.edge_feat:
+            e = self.embedding_e(e)
+        for conv in self.layers:
+            h = conv(g, h, e, snorm_n)
+        return self.MLP_layer(_graph_readout(g, h, self.readout if self.readout in ("sum", "max") else "mean"))
+
+    def loss(self, scores, labels):                         # :86-88 (minus the hard-coded .to('cuda'))
+        return nn.BCEWithLogitsLoss()(scores, labels.float().unsqueeze(-1))
+
+
+class PcbaNet(nn.Module):
+    def __init__(self, net_params):
+        super().__init__()
+        p = net_params
+        AtomEncoder, BondEncoder = _mol_encoders()
+        self.readout, self.edge_feat, self.virtual_node = p["readout"], p["edge_feat"], p["virtual_node"]
+        self.in_feat_dropout = nn.Dropout(p["in_feat_dropout"])
+        self.embedding_h = AtomEncoder(emb_dim=p["hidden_dim"])
+        if self.edge_feat:
+            self.embedding_e = BondEncoder(emb_dim=p["edge_dim"])
+        self.layers = _conv_stack(dict(p, layer_kwargs={"towers": p["towers"]}))
+        self.MLP_layer = MLPReadout(p["out_dim"], 128, decreasing_dim=p["decreasing_dim"])
+        self.virtual_node_layers = None
+        if self.virtual_node is not None and self.virtual_node.lower() != "none":       # :60-66
+            self.virtual_node_layers = nn.ModuleList(
+                VirtualNode(dim=p["hidden_dim"], dropout=p["dropout"], batch_norm=p["batch_norm"], bias=True,
+                            vn_type=self.virtual_node, residual=p["residual"]) for _ in range(p["L"] - 1))
+
+    def forward(self, g, h, e, snorm_n, snorm_e):           # PCBA dgn_net.py:68-97
+        h = self.in_feat_dropout(self.embedding_h(h))
+        if self.edge_feat:
+            e = self.embedding_e(e)
+        vn_h = 0
+        for i, conv in enumerate(self.layers):
+            h = conv(g, h, e, snorm_n)
+            if self.virtual_node_layers is not None and i < len(self.virtual_node_layers):
+                vn_h, h = self.virtual_node_layers[i](g, h, vn_h)
+        return self.MLP_layer(_graph_readout(g, h, self.readout if self.readout in ("sum", "max") else "mean"))
+
+    def loss(self, scores, labels):                         # :99-102
+        return nn.BCEWithLogitsLoss()(scores, labels)
