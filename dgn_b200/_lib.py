@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DGN_LIB_PATH") or os.path.join(_HERE, "libdgn_b200.so")
 
 MAX_AGG, MAX_SCALERS, MAX_SLOTS = 32, 4, 8
-ABI_VERSION = 6
+ABI_VERSION = 8
 NORM_WS_PER_COL = 640
 
 # DgnAggKind / DgnScalerKind / DgnMsgMode
@@ -69,7 +69,7 @@ class DgnNormArgs(C.Structure):
 class DgnNormGrad(C.Structure):
     _fields_ = [("g_out", C.c_void_p), ("ld_go", C.c_int32), ("d_y", C.c_void_p), ("ld_dy", C.c_int32),
                 ("d_residual", C.c_void_p), ("ld_dres", C.c_int32), ("d_gamma", C.c_void_p), ("d_beta", C.c_void_p),
-                ("d_bias", C.c_void_p), ("accumulate", C.c_int32), ("scratch", C.c_void_p)]
+                ("d_bias", C.c_void_p), ("accumulate", C.c_int32), ("scratch", C.c_void_p), ("counter", C.c_void_p)]
 
 
 class DgnHeadArgs(C.Structure):
@@ -111,6 +111,8 @@ SIGNATURES = {
     "dgn_field_build": (C.c_int, [C.POINTER(DgnGraph), C.POINTER(DgnAggSpec), C.c_void_p, C.c_int32,
                                   C.POINTER(DgnField), C.c_void_p]),
     "dgn_norm_forward": (C.c_int, [C.POINTER(DgnNormArgs), C.c_void_p]),
+    "dgn_norm_pair_forward": (C.c_int, [C.POINTER(DgnNormArgs), C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
+                                        C.c_void_p, C.c_int32, C.c_void_p]),
     "dgn_norm_backward": (C.c_int, [C.POINTER(DgnNormArgs), C.POINTER(DgnNormGrad), C.c_void_p]),
     "dgn_embedding_backward": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                                          C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -123,6 +125,8 @@ SIGNATURES = {
     "dgn_post_forward": (C.c_int, [C.POINTER(DgnPostArgs), C.c_void_p, C.c_int32, C.POINTER(DgnPostStats),
                                    C.POINTER(C.c_int32), C.c_void_p]),
     "dgn_post_backward": (C.c_int, [C.POINTER(DgnPostArgs), C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
+    "dgn_post_backward_norm": (C.c_int, [C.POINTER(DgnPostArgs), C.POINTER(DgnNormArgs), C.POINTER(DgnNormGrad), C.c_void_p,
+                                         C.c_int32, C.c_void_p]),
     "dgn_post_wgrad": (C.c_int, [C.POINTER(DgnPostArgs), C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
                                  C.c_void_p]),
     "dgn_pre_wgrad": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
@@ -131,6 +135,9 @@ SIGNATURES = {
                                           C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
     "dgn_pair_linear_backward": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
                                            C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
+    "dgn_pair_gather_backward": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                           C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
+                                           C.c_void_p, C.c_int32, C.c_void_p]),
     "dgn_head_forward": (C.c_int, [C.POINTER(DgnHeadArgs), C.c_void_p]),
     "dgn_head_backward": (C.c_int, [C.POINTER(DgnHeadArgs), C.POINTER(DgnHeadGrad), C.c_void_p]),
     "dgn_l1_loss_forward": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -150,7 +150,7 @@ extern "C" int dgn_agg_backward(const DgnGraph* g, const DgnAggSpec* spec, const
   k.d_r = grad->d_r; k.ld_dr = grad->ld_dr;
   k.d_h = grad->d_h_in; k.ld_dh = grad->ld_dh;
   k.d_h_add = grad->d_h_in ? grad->d_h_addend : nullptr; k.ld_dha = grad->ld_dha;
-  k.edge_ws = grad->d_x ? grad->edge_ws : nullptr;
+  k.edge_ws = grad->edge_ws;               // with d_x == NULL: spill only, the caller reduces over the out-edges
   if (grad->d_x && (!grad->edge_ws || !g->out_ptr || (g->n_edges > 0 && !g->out_slot))) return DGN_ERR_INVALID;
   if (grad->fold_h_in && (!grad->d_x || !grad->d_h_in)) return DGN_ERR_INVALID;
   if (k.g_hcopy && !k.h_copy) { k.ld_hc = io->ld_hcopy; k.hc_gs = io->hcopy_group_stride; }
@@ -160,7 +160,8 @@ extern "C" int dgn_agg_backward(const DgnGraph* g, const DgnAggSpec* spec, const
   if (k.d_r) vec = imin(vec, imin(vwp(k.d_r), vw(k.ld_dr)));
   if (k.d_h) vec = imin(vec, imin(vwp(k.d_h), vw(k.ld_dh)));
   if (k.d_h_add) vec = imin(vec, imin(vwp(k.d_h_add), vw(k.ld_dha)));
-  if (grad->d_x) vec = imin(vec, imin(imin(vwp(grad->d_x), vw(grad->ld_dx)), vwp(grad->edge_ws)));
+  if (grad->d_x) vec = imin(vec, imin(vwp(grad->d_x), vw(grad->ld_dx)));
+  if (grad->edge_ws) vec = imin(vec, vwp(grad->edge_ws));
   // measured (profiles/README.md): the row backward is fastest with 16 B lanes at every size; the kernels that derive
   // the weights in the launch prefer 8 B lanes for small launches
   vec = choose_vec(vec, k.N, k.plan.F, io->field == nullptr);

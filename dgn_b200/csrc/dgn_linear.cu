@@ -81,6 +81,162 @@ __global__ void __launch_bounds__(LT) pair_linear_fwd_kernel(int N, int Fi, int 
   }
 }
 
+// Layer epilogue of layer l fused with the node-level pretrans halves of layer l+1 (one launch instead of
+// norm_apply_kernel + pair_linear_fwd_kernel):
+//   out = relu(BN((y + b) * snorm)) + residual      rb/nets/dgn_layer.py:122-130, statistics final in a.stats
+//   P = out W_src^T, Q = out W_dst^T                rb/nets/dgn_layer.py:75-80 of the next layer
+// The row tile is produced with coalesced 128-bit accesses (16 threads per row), written to `out` and kept in shared
+// memory for the two products.
+constexpr int HS_LD_PAD = 1;
+__global__ void __launch_bounds__(LT) norm_pair_fwd_kernel(const DgnNormArgs a, int Fo, const float* __restrict__ W, int ld_w,
+                                                           float* __restrict__ P, int ld_p, float* __restrict__ Q,
+                                                           int ld_q) {
+  pdl_prologue();
+  extern __shared__ __align__(16) float sm[];
+  const int Fi = a.n_cols, hld = Fi + HS_LD_PAD;
+  float* hs = sm;                              // [LR][Fi + 1]  epilogue output tile, row-major
+  float* wp = hs + LR * hld;                   // [Fi][LC]      W_src block, transposed
+  float* wq = wp + Fi * LC;                    // [Fi][LC]      W_dst block, transposed
+  float* cst = wq + Fi * LC;                   // [5][Fi]       mean, rstd, gamma, beta, bias
+  const int t = threadIdx.x, r0 = blockIdx.x * LR, c0 = blockIdx.y * LC;
+  const int n = a.n_rows_dev ? *a.n_rows_dev : a.n_rows;
+  for (int idx = t; idx < LC * Fi; idx += LT) {
+    const int i = idx / LC, o = idx - i * LC;
+    if (c0 + o < Fo) {
+      cp_async4(wp + idx, W + (size_t)(c0 + o) * ld_w + i);
+      cp_async4(wq + idx, W + (size_t)(c0 + o) * ld_w + Fi + i);
+    } else {
+      wp[idx] = 0.f;
+      wq[idx] = 0.f;
+    }
+  }
+  // per-column constants; training-mode BatchNorm: merge the statistics slabs dgn_post_forward left in a.stats (slab
+  // order -> every CTA gets the same bits), block (0, 0) also updates the running statistics and the [mean | rstd] header
+  const bool bn = a.gamma != nullptr, merge = bn && a.training;
+  if (merge) {
+    const int nsub = (Fi <= LT) ? ((LT / Fi) < 4 ? (LT / Fi) : 4) : 1;   // threads per column (Fi = 64: 2)
+    float* part = hs;                                           // [nsub][3][Fi] scratch (the tile is not built yet)
+    for (int c0 = 0; c0 < Fi; c0 += LT) {
+      const int col = c0 + t % (Fi < LT ? Fi : LT), sub = (Fi < LT) ? t / Fi : 0;
+      float cnt = 0.f, mu = 0.f, m2 = 0.f;
+      if (col < Fi && sub < nsub) {
+        for (int p0 = sub; p0 < a.stat_parts; p0 += 8 * nsub) {
+          float pn[8], pm[8], p2[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {                          // independent loads first
+            const int p = p0 + j * nsub;
+            const float* sl = a.stats + 2 * Fi + (size_t)p * 3 * Fi;
+            const bool ok = p < a.stat_parts;
+            pn[j] = ok ? sl[col] : 0.f;
+            pm[j] = ok ? sl[Fi + col] : 0.f;
+            p2[j] = ok ? sl[2 * Fi + col] : 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (pn[j] > 0.f) {
+              const float nt = cnt + pn[j], d = pm[j] - mu;
+              mu += d * (pn[j] / nt);
+              m2 += p2[j] + d * d * (cnt * pn[j] / nt);
+              cnt = nt;
+            }
+          }
+        }
+        part[(sub * 3 + 0) * Fi + col] = cnt;
+        part[(sub * 3 + 1) * Fi + col] = mu;
+        part[(sub * 3 + 2) * Fi + col] = m2;
+      }
+      __syncthreads();
+      if (col < Fi && sub == 0) {
+        for (int j = 1; j < nsub; ++j) {
+          const float nb = part[(j * 3 + 0) * Fi + col], mb = part[(j * 3 + 1) * Fi + col], m2b = part[(j * 3 + 2) * Fi + col];
+          if (nb > 0.f) {
+            const float nt = cnt + nb, d = mb - mu;
+            mu += d * (nb / nt);
+            m2 += m2b + d * d * (cnt * nb / nt);
+            cnt = nt;
+          }
+        }
+        const float var = cnt > 0.f ? m2 / cnt : 0.f, rstd = 1.f / sqrtf(var + a.eps);
+        cst[col] = mu;
+        cst[Fi + col] = rstd;
+        if (blockIdx.x == 0 && blockIdx.y == 0) {
+          a.stats[col] = mu;                                    // the backward reads the header
+          a.stats[Fi + col] = rstd;
+          if (a.running_mean) {                                 // nn.BatchNorm1d: unbiased variance in the running estimate
+            const float unb = cnt > 1.f ? var * (cnt / (cnt - 1.f)) : var;
+            a.running_mean[col] = (1.f - a.momentum) * a.running_mean[col] + a.momentum * mu;
+            a.running_var[col] = (1.f - a.momentum) * a.running_var[col] + a.momentum * unb;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = t; i < Fi; i += LT) {
+    if (!merge) {
+      cst[i] = bn ? a.running_mean[i] : 0.f;
+      cst[Fi + i] = bn ? 1.f / sqrtf(a.running_var[i] + a.eps) : 1.f;
+    }
+    cst[2 * Fi + i] = bn ? a.gamma[i] : 1.f;
+    cst[3 * Fi + i] = bn ? a.beta[i] : 0.f;
+    cst[4 * Fi + i] = a.y_bias ? a.y_bias[i] : 0.f;
+  }
+  __syncthreads();
+  const int q4 = Fi / 4;
+  for (int idx = t; idx < LR * q4; idx += LT) {
+    const int r = idx / q4, i = (idx - r * q4) * 4, row = r0 + r;
+    float o[4] = {0.f, 0.f, 0.f, 0.f};
+    if (row < n) {
+      const float4 yv = *reinterpret_cast<const float4*>(a.y + (size_t)row * a.ld_y + i);
+      const float sn = a.snorm ? a.snorm[row] : 1.f;
+      const float yy[4] = {yv.x, yv.y, yv.z, yv.w};
+      float rs[4] = {0.f, 0.f, 0.f, 0.f};
+      if (a.residual) {
+        const float4 rv = *reinterpret_cast<const float4*>(a.residual + (size_t)row * a.ld_res + i);
+        rs[0] = rv.x; rs[1] = rv.y; rs[2] = rv.z; rs[3] = rv.w;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float z = (yy[j] + cst[4 * Fi + i + j]) * sn;
+        float v = (z - cst[i + j]) * cst[Fi + i + j] * cst[2 * Fi + i + j] + cst[3 * Fi + i + j];
+        if (a.relu) v = fmaxf(v, 0.f);
+        o[j] = v + rs[j];
+      }
+    }
+    if (row < a.n_rows && blockIdx.y == 0)
+      *reinterpret_cast<float4*>(a.out + (size_t)row * a.ld_o + i) = make_float4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) hs[r * hld + i + j] = o[j];
+  }
+  cp_async_wait_all();
+  __syncthreads();
+  const int tx = t & 15, ty = t >> 4;          // 16 column groups x 8 row groups
+  float ap[4][4] = {}, aq[4][4] = {};
+#pragma unroll 4
+  for (int i = 0; i < Fi; ++i) {
+    const float hr[4] = {hs[(ty * 4 + 0) * hld + i], hs[(ty * 4 + 1) * hld + i], hs[(ty * 4 + 2) * hld + i],
+                         hs[(ty * 4 + 3) * hld + i]};
+    const float4 pv = *reinterpret_cast<const float4*>(wp + i * LC + tx * 4);
+    const float4 qv = *reinterpret_cast<const float4*>(wq + i * LC + tx * 4);
+    const float pw[4] = {pv.x, pv.y, pv.z, pv.w}, qw[4] = {qv.x, qv.y, qv.z, qv.w};
+#pragma unroll
+    for (int a_ = 0; a_ < 4; ++a_)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        ap[a_][b] = fmaf(hr[a_], pw[b], ap[a_][b]);
+        aq[a_][b] = fmaf(hr[a_], qw[b], aq[a_][b]);
+      }
+  }
+#pragma unroll
+  for (int a_ = 0; a_ < 4; ++a_) {
+    const int r = r0 + ty * 4 + a_, c = c0 + tx * 4;
+    if (r < a.n_rows && c < Fo) {
+      *reinterpret_cast<float4*>(P + (size_t)r * ld_p + c) = make_float4(ap[a_][0], ap[a_][1], ap[a_][2], ap[a_][3]);
+      *reinterpret_cast<float4*>(Q + (size_t)r * ld_q + c) = make_float4(aq[a_][0], aq[a_][1], aq[a_][2], aq[a_][3]);
+    }
+  }
+}
+
 // d_h[n,i] += sum_o dP[n,o] W[o,i] + dQ[n,o] W[o,Fi+i]
 __global__ void __launch_bounds__(LT) pair_linear_bwd_kernel(int N, int Fi, int Fo, const float* __restrict__ dP, int ld_p,
                                                              const float* __restrict__ dQ, int ld_q,
@@ -142,6 +298,90 @@ __global__ void __launch_bounds__(LT) pair_linear_bwd_kernel(int N, int Fi, int 
   }
 }
 
+// pair_linear_bwd with the source-side reduction of the aggregation backward folded in (one launch instead of
+// agg_bwd_src_kernel + pair_linear_bwd_kernel):
+//   d_P[u]  = sum over the out-edges j of u of ws[out_slot[j]]      (deterministic gather, edge-slot order)
+//   d_h[u] += d_P[u] W_src + d_Q[u] W_dst                           and d_P is written out for the weight gradient
+// The row tile is produced with 128-bit accesses (16 threads per row) and kept row-major in shared memory.
+__global__ void __launch_bounds__(LT) pair_gather_bwd_kernel(int N, int Fi, int Fo, const int32_t* __restrict__ out_ptr,
+                                                             const int32_t* __restrict__ out_slot,
+                                                             const float* __restrict__ ws, int ld_ws,
+                                                             const float* __restrict__ dQ, int ld_q,
+                                                             const float* __restrict__ W, int ld_w,
+                                                             float* __restrict__ d_h, int ld_dh,
+                                                             float* __restrict__ dP, int ld_p) {
+  pdl_prologue();
+  extern __shared__ __align__(16) float sm[];
+  const int pld = Fo + 1;
+  float* ps = sm;                              // [LR][Fo + 1]  gathered dP tile, row-major
+  float* qs = ps + LR * pld;                   // [LR][Fo + 1]  dQ tile
+  float* wsr = qs + LR * pld;                  // [Fo][LC]      W[:, c0:c0+LC]
+  float* wds = wsr + Fo * LC;                  // [Fo][LC]      W[:, Fi+c0 : Fi+c0+LC]
+  const int t = threadIdx.x, r0 = blockIdx.x * LR, c0 = blockIdx.y * LC;
+  for (int idx = t; idx < Fo * LC; idx += LT) {
+    const int o = idx / LC, i = idx - o * LC;
+    if (c0 + i < Fi) {
+      cp_async4(wsr + idx, W + (size_t)o * ld_w + c0 + i);
+      cp_async4(wds + idx, W + (size_t)o * ld_w + Fi + c0 + i);
+    } else {
+      wsr[idx] = 0.f;
+      wds[idx] = 0.f;
+    }
+  }
+  const int q4 = Fo / 4;
+  for (int idx = t; idx < LR * q4; idx += LT) {
+    const int r = idx / q4, o = (idx - r * q4) * 4, u = r0 + r;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), qv = acc;
+    if (u < N) {
+      const int j0 = __ldg(out_ptr + u), j1 = __ldg(out_ptr + u + 1);
+      for (int j = j0; j < j1; j += 4) {                         // up to 4 edge rows in flight
+        float4 v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          v[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (j + e < j1) v[e] = __ldcs(reinterpret_cast<const float4*>(ws + (size_t)__ldg(out_slot + j + e) * ld_ws + o));
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { acc.x += v[e].x; acc.y += v[e].y; acc.z += v[e].z; acc.w += v[e].w; }
+      }
+      qv = *reinterpret_cast<const float4*>(dQ + (size_t)u * ld_q + o);
+      if (blockIdx.y == 0) *reinterpret_cast<float4*>(dP + (size_t)u * ld_p + o) = acc;
+    }
+    float* pp = ps + r * pld + o;
+    float* qq = qs + r * pld + o;
+    pp[0] = acc.x; pp[1] = acc.y; pp[2] = acc.z; pp[3] = acc.w;
+    qq[0] = qv.x; qq[1] = qv.y; qq[2] = qv.z; qq[3] = qv.w;
+  }
+  cp_async_wait_all();
+  __syncthreads();
+  const int tx = t & 15, ty = t >> 4;
+  float acc[4][4] = {};
+#pragma unroll 4
+  for (int o = 0; o < Fo; ++o) {
+    const float pr[4] = {ps[(ty * 4 + 0) * pld + o], ps[(ty * 4 + 1) * pld + o], ps[(ty * 4 + 2) * pld + o],
+                         ps[(ty * 4 + 3) * pld + o]};
+    const float qr[4] = {qs[(ty * 4 + 0) * pld + o], qs[(ty * 4 + 1) * pld + o], qs[(ty * 4 + 2) * pld + o],
+                         qs[(ty * 4 + 3) * pld + o]};
+    const float4 sv = *reinterpret_cast<const float4*>(wsr + o * LC + tx * 4);
+    const float4 dv = *reinterpret_cast<const float4*>(wds + o * LC + tx * 4);
+    const float sw[4] = {sv.x, sv.y, sv.z, sv.w}, dw[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(pr[a], sw[b], fmaf(qr[a], dw[b], acc[a][b]));
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int r = r0 + ty * 4 + a, c = c0 + tx * 4;
+    if (r < N && c < Fi) {
+      float4* dst = reinterpret_cast<float4*>(d_h + (size_t)r * ld_dh + c);
+      float4 v = *dst;
+      v.x += acc[a][0]; v.y += acc[a][1]; v.z += acc[a][2]; v.w += acc[a][3];
+      *dst = v;
+    }
+  }
+}
+
 }  // namespace dgn
 
 using namespace dgn;
@@ -173,6 +413,27 @@ extern "C" int dgn_pair_linear_forward(int32_t N, int32_t Fi, int32_t Fo, const 
   return DGN_OK;
 }
 
+extern "C" int dgn_norm_pair_forward(const DgnNormArgs* a, int32_t f_out, const float* w, int32_t ld_w, float* p,
+                                     int32_t ld_p, float* q, int32_t ld_q, void* stream) {
+  if (!a || !a->y || !a->out || !w || !p || !q || a->n_rows < 0 || a->n_cols <= 0) return DGN_ERR_INVALID;
+  if (a->gamma && (!a->beta || !a->stats)) return DGN_ERR_INVALID;
+  if (a->gamma && a->training && a->stat_parts <= 0) return DGN_ERR_INVALID;          // needs the statistics slabs
+  if (a->gamma && !a->training && (!a->running_mean || !a->running_var)) return DGN_ERR_INVALID;
+  auto al = [](const void* x) { return (reinterpret_cast<uintptr_t>(x) & 15u) == 0; };
+  if (!lin_ok(a->n_cols, f_out, p, q, ld_p, ld_q) || !al(a->y) || !al(a->out) || a->ld_y % 4 || a->ld_o % 4 ||
+      (a->residual && (!al(a->residual) || a->ld_res % 4)))
+    return DGN_ERR_UNSUPPORTED;
+  if (a->n_rows == 0) return DGN_OK;
+  const int Fi = a->n_cols;
+  const size_t smem = (size_t)(LR * (Fi + HS_LD_PAD) + 2 * Fi * LC + 5 * Fi) * sizeof(float);
+  if (int rc = lin_attr(norm_pair_fwd_kernel, smem)) return rc;
+  launch_pdl(norm_pair_fwd_kernel, dim3((a->n_rows + LR - 1) / LR, (f_out + LC - 1) / LC), dim3(LT), smem,
+             (cudaStream_t)stream, *a, f_out, w, ld_w, p, ld_p, q, ld_q);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { g_dgn_last_cuda = e; return DGN_ERR_CUDA; }
+  return DGN_OK;
+}
+
 extern "C" int dgn_pair_linear_backward(int32_t N, int32_t Fi, int32_t Fo, const float* dP, int32_t ld_p, const float* dQ,
                                         int32_t ld_q, const float* W, int32_t ld_w, float* d_h, int32_t ld_dh,
                                         void* stream) {
@@ -182,6 +443,22 @@ extern "C" int dgn_pair_linear_backward(int32_t N, int32_t Fi, int32_t Fo, const
   const size_t smem = (size_t)(2 * Fo * LR + 2 * Fo * LC) * sizeof(float);
   if (int rc = lin_attr(pair_linear_bwd_kernel, smem)) return rc;
   launch_pdl(pair_linear_bwd_kernel, dim3((N + LR - 1) / LR, (Fi + LC - 1) / LC), dim3(LT), smem, (cudaStream_t)stream, N, Fi, Fo, dP, ld_p, dQ, ld_q, W, ld_w, d_h, ld_dh);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { g_dgn_last_cuda = e; return DGN_ERR_CUDA; }
+  return DGN_OK;
+}
+
+extern "C" int dgn_pair_gather_backward(int32_t N, int32_t Fi, int32_t Fo, const int32_t* out_ptr, const int32_t* out_slot,
+                                        const float* edge_ws, int32_t ld_ws, const float* dQ, int32_t ld_q, const float* W,
+                                        int32_t ld_w, float* d_h, int32_t ld_dh, float* dP, int32_t ld_p, void* stream) {
+  if (N < 0 || !out_ptr || !edge_ws || !dQ || !W || !d_h || !dP) return DGN_ERR_INVALID;
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  if (!lin_ok(Fi, Fo, d_h, dP, ld_dh, ld_p) || !al(edge_ws) || !al(dQ) || ld_ws % 4 || ld_q % 4) return DGN_ERR_UNSUPPORTED;
+  if (N == 0) return DGN_OK;
+  const size_t smem = (size_t)(2 * LR * (Fo + 1) + 2 * Fo * LC) * sizeof(float);
+  if (int rc = lin_attr(pair_gather_bwd_kernel, smem)) return rc;
+  launch_pdl(pair_gather_bwd_kernel, dim3((N + LR - 1) / LR, (Fi + LC - 1) / LC), dim3(LT), smem, (cudaStream_t)stream, N, Fi,
+             Fo, out_ptr, out_slot, edge_ws, ld_ws, dQ, ld_q, W, ld_w, d_h, ld_dh, dP, ld_p);
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { g_dgn_last_cuda = e; return DGN_ERR_CUDA; }
   return DGN_OK;

@@ -61,9 +61,23 @@ struct PostK {
   int ksplit, n_lead_kb, n_agg_kb;
   int kb_start[kMaxSplit + 1];
   int n_lead_tiles, n_agg_tiles;
-  // optional BatchNorm partial statistics of z = (y + y_bias) * snorm per (row tile, rank) slab: [cnt | mean | M2][Fo]
+  // optional BatchNorm partial statistics of z = (y + y_bias) * snorm, one slab per row tile: [cnt | mean | M2][Fo]
   float* stat_parts; const float* y_bias; const float* snorm; const int* n_rows_dev;
+  // optional fused prologue of the backward: d_y = d(epilogue)/dy evaluated by the operand loader (dy == nullptr then)
+  const float* f_gout; int f_ld_go; const float* f_y; int f_ld_y; const float* f_ybias; const float* f_snorm;
+  const float* f_gamma; const float* f_beta; const float* f_stats; int f_training, f_relu;
+  float* f_dy; int f_ld_dy; const int* f_nrows_dev;
+  unsigned long long* dbg;                 // optional [n_ctas][8] %globaltimer stamps of the forward kernel's phases (tools/)
 };
+
+__device__ __forceinline__ void stamp(const PostK& g, int slot) {
+  if (g.dbg) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    const int cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    g.dbg[(size_t)cta * 8 + slot] = t;
+  }
+}
 
 struct Smem {
   unsigned char* base;
@@ -113,7 +127,9 @@ __global__ void __launch_bounds__(kPostThreads, 1) post_fwd_kernel(const __grid_
   const int rank = g.ksplit > 1 ? (int)cluster_ctarank() : 0;
   const int kb0 = g.kb_start[rank], kb1 = g.kb_start[rank + 1], nkb = kb1 - kb0;
   const int tmem_cols = (g.S + 1) * PN;
+  if (tid == 0) stamp(g, 0);
   const uint32_t tmem_d = prologue(sm, tmem_cols);
+  if (tid == 0) stamp(g, 1);
 
   if (warp < kLoad / 32) {
     // ------------------------------ loaders ------------------------------
@@ -131,33 +147,37 @@ __global__ void __launch_bounds__(kPostThreads, 1) post_fwd_kernel(const __grid_
           if (t < g.S) fetch_k<PN, kLoad>(g.W + g.F + (size_t)t * g.Ka, g.ld_w, n0, g.Fo, kcol, g.Ka, b[t], tid);
       }
     };
-    if (nkb > 0) fetch(kb0, va, vb);
-    for (int i = 0; i < nkb; ++i) {
+    // Two register sets in ping-pong (no copies: a copy would wait for the loads it copies): block i+1 is in flight
+    // while block i is split and stored.
+    float4 wa[PM * 8 / kLoad], wb[kMaxTerms][PN * 8 / kLoad];
+    auto step = [&](int i, float4 (&ca)[PM * 8 / kLoad], float4 (&cb)[kMaxTerms][PN * 8 / kLoad],
+                    float4 (&xa)[PM * 8 / kLoad], float4 (&xb)[kMaxTerms][PN * 8 / kLoad]) {
       const int s = i & 1;
-      float4 na[PM * 8 / kLoad], nb[kMaxTerms][PN * 8 / kLoad];
-      if (i + 1 < nkb) fetch(kb0 + i + 1, na, nb);                   // next k-block in flight during this one's stores
+      if (i + 1 < nkb) fetch(kb0 + i + 1, xa, xb);
       if (i >= 2) mb_wait(&sm.empty[s], ((i >> 1) - 1) & 1);
       unsigned char* st = sm.stage(s);
       const bool lead = (kb0 + i) < g.n_lead_kb;
-      store_k<PM, kLoad>(va, st, st + A_BYTES, tid);
+      store_k<PM, kLoad>(ca, st, st + A_BYTES, tid);
 #pragma unroll
       for (int t = 0; t < kMaxTerms; ++t)
         if (t < (lead ? 1 : g.S))
-          store_k<PN, kLoad>(vb[t], st + 2 * A_BYTES + t * 2 * B_BYTES, st + 2 * A_BYTES + t * 2 * B_BYTES + B_BYTES, tid);
+          store_k<PN, kLoad>(cb[t], st + 2 * A_BYTES + t * B_BYTES, st + 2 * A_BYTES + (g.S + t) * B_BYTES, tid);
       fence_async_smem();
       mb_arrive(&sm.full[s]);
-      if (i + 1 < nkb) {
-#pragma unroll
-        for (int q = 0; q < PM * 8 / kLoad; ++q) va[q] = na[q];
-#pragma unroll
-        for (int t = 0; t < kMaxTerms; ++t)
-#pragma unroll
-          for (int q = 0; q < PN * 8 / kLoad; ++q) vb[t][q] = nb[t][q];
-      }
+    };
+    if (nkb > 0) fetch(kb0, va, vb);
+    for (int i = 0; i < nkb; i += 2) {
+      step(i, va, vb, wa, wb);
+      if (i + 1 < nkb) step(i + 1, wa, wb, va, vb);
     }
+    if (tid == 0) stamp(g, 2);
   } else if (lane == 0) {
     // ------------------------------ MMA issuer ------------------------------
-    constexpr uint32_t idesc = instr_desc_tf32(PM, PN, false, false);
+    // The S scaler terms of an aggregate k-block are ONE wide operand (their B tiles are stacked along N): one
+    // N = 64 S instruction per k-step and split term instead of S narrow ones (which re-read A from shared memory
+    // S times and are bound by that).  The lead block goes to its own 64 accumulator columns.
+    constexpr uint32_t idesc_lead = instr_desc_tf32(PM, PN, false, false);
+    const uint32_t idesc_agg = instr_desc_tf32(PM, g.S * PN, false, false);
     uint32_t used = 0;
     for (int i = 0; i < nkb; ++i) {
       const int s = i & 1;
@@ -165,17 +185,14 @@ __global__ void __launch_bounds__(kPostThreads, 1) post_fwd_kernel(const __grid_
       tc_fence_after();
       const uint32_t a_hi = s32(sm.stage(s)), a_lo = a_hi + A_BYTES;
       const bool lead = (kb0 + i) < g.n_lead_kb;
-      const int nt = lead ? 1 : g.S;
-      for (int t = 0; t < nt; ++t) {
-        const int acc = lead ? g.S : t;
-        const uint32_t b_hi = a_hi + 2 * A_BYTES + t * 2 * B_BYTES, b_lo = b_hi + B_BYTES;
+      const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + g.S * B_BYTES;
+      const uint32_t dcol = lead ? g.S * PN : 0, bit = lead ? 2u : 1u;
 #pragma unroll
-        for (int kk = 0; kk < BK / 8; ++kk)
-          umma_tf32x3(tmem_d + acc * PN, tile_desc<PM, true>(a_hi, kk), tile_desc<PM, true>(a_lo, kk),
-                      tile_desc<PN, true>(b_hi, kk), tile_desc<PN, true>(b_lo, kk), idesc,
-                      (((used >> acc) & 1u) | (kk > 0 ? 1u : 0u)));
-        used |= 1u << acc;
-      }
+      for (int kk = 0; kk < BK / 8; ++kk)
+        umma_tf32x3(tmem_d + dcol, tile_desc<PM, true>(a_hi, kk), tile_desc<PM, true>(a_lo, kk),
+                    tile_desc<PN, true>(b_hi, kk), tile_desc<PN, true>(b_lo, kk), lead ? idesc_lead : idesc_agg,
+                    (((used & bit) ? 1u : 0u) | (kk > 0 ? 1u : 0u)));
+      used |= bit;
       umma_commit(&sm.empty[s]);
     }
     umma_commit(sm.accum_full);
@@ -186,6 +203,7 @@ __global__ void __launch_bounds__(kPostThreads, 1) post_fwd_kernel(const __grid_
   if (warp < kLoad / 32) {
     mb_wait(sm.accum_full, 0);
     tc_fence_after();
+    if (tid == 0) stamp(g, 3);
     const int q = warp & 3, hf = warp >> 2, row = q * 32 + lane, gm = m0 + row;
     const bool has_lead = nkb > 0 && kb0 < g.n_lead_kb, has_agg = nkb > 0 && kb1 > g.n_lead_kb;
     const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + hf * 32;
@@ -213,6 +231,7 @@ __global__ void __launch_bounds__(kPostThreads, 1) post_fwd_kernel(const __grid_
   }
   tc_fence_before();
   if (g.ksplit > 1) cluster_sync_all(); else __syncthreads();
+  if (tid == 0) stamp(g, 4);
   if (warp < kLoad / 32) {
     // Every thread's elements share one column (c = tid % PN) and step 4 rows: it keeps the running batch statistics
     // (Welford) of z = (y + bias) * snorm over its rows for the BatchNorm that follows.
@@ -267,16 +286,49 @@ __global__ void __launch_bounds__(kPostThreads, 1) post_fwd_kernel(const __grid_
             cnt = nt_;
           }
         }
-        float* part = g.stat_parts + (size_t)(blockIdx.x * g.ksplit + rank) * 3 * g.Fo;
-        part[n0 + tid] = cnt;
-        part[g.Fo + n0 + tid] = mean;
-        part[2 * g.Fo + n0 + tid] = m2;
+        if (g.ksplit > 1) {                                   // combined over the cluster below: one slab per row tile
+          float* sfin = sred + 12 * PN;
+          sfin[tid] = cnt; sfin[PN + tid] = mean; sfin[2 * PN + tid] = m2;
+        } else {
+          float* part = g.stat_parts + (size_t)blockIdx.x * 3 * g.Fo;
+          part[n0 + tid] = cnt; part[g.Fo + n0 + tid] = mean; part[2 * g.Fo + n0 + tid] = m2;
+        }
       }
     }
   }
+  if (tid == 0) stamp(g, 5);
   if (g.ksplit > 1) cluster_sync_all();                               // peers may still be reading this CTA's patch
+  if (g.stat_parts && g.ksplit > 1) {
+    // rank 0 merges the per-rank statistics of the row tile over DSMEM (rank order) into ONE slab
+    if (rank == 0 && tid < PN && n0 + tid < g.Fo) {
+      const uint32_t local = s32(reinterpret_cast<float*>(sm.base + 40 * 1024) + 12 * PN + tid);
+      float pn[8], pm[8], p2[8];
+#pragma unroll
+      for (int p = 0; p < 8; ++p) {
+        const bool ok = p < g.ksplit;
+        const uint32_t a = ok ? dsmem_addr(local, (uint32_t)p) : 0u;
+        pn[p] = ok ? dsmem_ld(a) : 0.f;
+        pm[p] = ok ? dsmem_ld(a + PN * 4) : 0.f;
+        p2[p] = ok ? dsmem_ld(a + 2 * PN * 4) : 0.f;
+      }
+      float cnt = 0.f, mean = 0.f, m2 = 0.f;
+#pragma unroll
+      for (int p = 0; p < 8; ++p) {
+        if (pn[p] > 0.f) {
+          const float nt_ = cnt + pn[p], d = pm[p] - mean;
+          mean += d * (pn[p] / nt_);
+          m2 += p2[p] + d * d * (cnt * pn[p] / nt_);
+          cnt = nt_;
+        }
+      }
+      float* part = g.stat_parts + (size_t)blockIdx.x * 3 * g.Fo;
+      part[n0 + tid] = cnt; part[g.Fo + n0 + tid] = mean; part[2 * g.Fo + n0 + tid] = m2;
+    }
+    cluster_sync_all();                                               // rank 0 has read its peers' shared memory
+  }
   __syncwarp();
   if (warp == kLoad / 32) tmem_dealloc_n(tmem_d, tmem_cols);
+  if (tid == 0) stamp(g, 6);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -296,52 +348,98 @@ __global__ void __launch_bounds__(kPostThreads, 1) post_bwd_kernel(const __grid_
   const int tmem_cols = nt * PN;
   const uint32_t tmem_d = prologue(sm, tmem_cols);
 
+  // fused prologue: per-column constants of the norm backward [7][Fo]: bias, mean, rstd, gamma, beta, mean(g1), mean(g1 xhat)
+  float* cst = reinterpret_cast<float*>(sm.base + 2 * sm.stage_bytes + 128);
+  const bool fused = g.f_gout != nullptr;
+  if (fused) {
+    const bool bn = g.f_gamma != nullptr, stat = bn && g.f_training;
+    for (int c = tid; c < g.Fo; c += kPostThreads) {
+      cst[c] = g.f_ybias ? __ldg(g.f_ybias + c) : 0.f;
+      cst[g.Fo + c] = bn ? g.f_stats[c] : 0.f;
+      cst[2 * g.Fo + c] = bn ? g.f_stats[g.Fo + c] : 1.f;
+      cst[3 * g.Fo + c] = bn ? __ldg(g.f_gamma + c) : 1.f;
+      cst[4 * g.Fo + c] = bn ? __ldg(g.f_beta + c) : 0.f;
+      cst[5 * g.Fo + c] = stat ? g.f_stats[2 * g.Fo + c] : 0.f;
+      cst[6 * g.Fo + c] = stat ? g.f_stats[3 * g.Fo + c] : 0.f;
+    }
+    __syncthreads();
+  }
+  const int n_real = g.f_nrows_dev ? *g.f_nrows_dev : g.N;
+
   if (warp < kLoad / 32) {
     float4 va[PM * 8 / kLoad], vb[kMaxTerms][PN * 8 / kLoad];
+    // d_y chunk (row, 4 columns) of the fused prologue: same arithmetic as norm_bwd_apply_kernel (dgn_norm.cu)
+    auto fetch_dy = [&](int k0, float4 (&a)[PM * 8 / kLoad]) {
+#pragma unroll
+      for (int i = 0; i < PM * 8 / kLoad; ++i) {
+        const int id = tid + i * kLoad;
+        const int row = id >> 3, ch = id & 7;
+        const int gr = m0 + row, gk = k0 + ch * 4;
+        a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gr < g.N && gk < g.Fo) {
+          if (gr < n_real) {
+            const float4 go = __ldg(reinterpret_cast<const float4*>(g.f_gout + (size_t)gr * g.f_ld_go + gk));
+            const float4 yv = __ldg(reinterpret_cast<const float4*>(g.f_y + (size_t)gr * g.f_ld_y + gk));
+            const float sn = g.f_snorm ? __ldg(g.f_snorm + gr) : 1.f;
+            const float gg[4] = {go.x, go.y, go.z, go.w}, yy[4] = {yv.x, yv.y, yv.z, yv.w};
+            float d[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int c = gk + j;
+              const float z = (yy[j] + cst[c]) * sn;
+              const float xhat = (z - cst[g.Fo + c]) * cst[2 * g.Fo + c];
+              const float ga = cst[3 * g.Fo + c];
+              float g1 = gg[j];
+              if (g.f_relu && !(xhat * ga + cst[4 * g.Fo + c] > 0.f)) g1 = 0.f;
+              float dz = g.f_gamma ? ga * cst[2 * g.Fo + c] * (g1 - cst[5 * g.Fo + c] - xhat * cst[6 * g.Fo + c]) : g1;
+              d[j] = dz * sn;
+            }
+            a[i] = make_float4(d[0], d[1], d[2], d[3]);
+          }
+          if (blockIdx.y == 0) *reinterpret_cast<float4*>(g.f_dy + (size_t)gr * g.f_ld_dy + gk) = a[i];
+        }
+      }
+    };
     auto fetch = [&](int kb, float4 (&a)[PM * 8 / kLoad], float4 (&b)[kMaxTerms][PN * 8 / kLoad]) {
-      fetch_k<PM, kLoad>(g.dy, g.ld_dy, m0, g.N, kb * BK, g.Fo, a, tid);
+      if (fused) fetch_dy(kb * BK, a);
+      else fetch_k<PM, kLoad>(g.dy, g.ld_dy, m0, g.N, kb * BK, g.Fo, a, tid);
 #pragma unroll
       for (int t = 0; t < kMaxTerms; ++t)
         if (t < nt)
           fetch_mn<PN, kLoad>(g.W + (lead ? 0 : g.F + (size_t)t * g.Ka), g.ld_w, c0, seg, kb * BK, g.Fo, -1, b[t], tid);
     };
-    fetch(0, va, vb);
-    for (int i = 0; i < nkb; ++i) {
+    float4 wa[PM * 8 / kLoad], wb[kMaxTerms][PN * 8 / kLoad];
+    auto step = [&](int i, float4 (&ca)[PM * 8 / kLoad], float4 (&cb)[kMaxTerms][PN * 8 / kLoad],
+                    float4 (&xa)[PM * 8 / kLoad], float4 (&xb)[kMaxTerms][PN * 8 / kLoad]) {
       const int s = i & 1;
-      float4 na[PM * 8 / kLoad], nb[kMaxTerms][PN * 8 / kLoad];
-      if (i + 1 < nkb) fetch(i + 1, na, nb);
+      if (i + 1 < nkb) fetch(i + 1, xa, xb);
       if (i >= 2) mb_wait(&sm.empty[s], ((i >> 1) - 1) & 1);
       unsigned char* st = sm.stage(s);
-      store_k<PM, kLoad>(va, st, st + A_BYTES, tid);
+      store_k<PM, kLoad>(ca, st, st + A_BYTES, tid);
 #pragma unroll
       for (int t = 0; t < kMaxTerms; ++t)
         if (t < nt)
-          store_mn<PN, kLoad>(vb[t], st + 2 * A_BYTES + t * 2 * B_BYTES, st + 2 * A_BYTES + t * 2 * B_BYTES + B_BYTES, tid);
+          store_mn_wide<kLoad>(cb[t], st + 2 * A_BYTES, st + 2 * A_BYTES + g.S * B_BYTES, tid, nt * PN, t);
       fence_async_smem();
       mb_arrive(&sm.full[s]);
-      if (i + 1 < nkb) {
-#pragma unroll
-        for (int q = 0; q < PM * 8 / kLoad; ++q) va[q] = na[q];
-#pragma unroll
-        for (int t = 0; t < kMaxTerms; ++t)
-#pragma unroll
-          for (int q = 0; q < PN * 8 / kLoad; ++q) vb[t][q] = nb[t][q];
-      }
+    };
+    fetch(0, va, vb);
+    for (int i = 0; i < nkb; i += 2) {
+      step(i, va, vb, wa, wb);
+      if (i + 1 < nkb) step(i + 1, wa, wb, va, vb);
     }
   } else if (lane == 0) {
-    constexpr uint32_t idesc = instr_desc_tf32(PM, PN, false, true);
+    const uint32_t idesc = instr_desc_tf32(PM, nt * PN, false, true);      // all terms in one wide-N instruction
     for (int i = 0; i < nkb; ++i) {
       const int s = i & 1;
       mb_wait(&sm.full[s], (i >> 1) & 1);
       tc_fence_after();
       const uint32_t a_hi = s32(sm.stage(s)), a_lo = a_hi + A_BYTES;
-      for (int t = 0; t < nt; ++t) {
-        const uint32_t b_hi = a_hi + 2 * A_BYTES + t * 2 * B_BYTES, b_lo = b_hi + B_BYTES;
+      const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + g.S * B_BYTES;
 #pragma unroll
-        for (int kk = 0; kk < BK / 8; ++kk)
-          umma_tf32x3(tmem_d + t * PN, tile_desc<PM, true>(a_hi, kk), tile_desc<PM, true>(a_lo, kk),
-                      tile_desc<PN, false>(b_hi, kk), tile_desc<PN, false>(b_lo, kk), idesc, (i > 0 || kk > 0) ? 1u : 0u);
-      }
+      for (int kk = 0; kk < BK / 8; ++kk)
+        umma_tf32x3(tmem_d, tile_desc<PM, true>(a_hi, kk), tile_desc<PM, true>(a_lo, kk), tile_desc_mn(b_hi, kk, nt * PN),
+                    tile_desc_mn(b_lo, kk, nt * PN), idesc, (i > 0 || kk > 0) ? 1u : 0u);
       umma_commit(&sm.empty[s]);
     }
     umma_commit(sm.accum_full);
@@ -449,43 +547,38 @@ __global__ void __launch_bounds__(kPostThreads, 1) wgrad_kernel(const __grid_con
         }
       }
     };
-    if (nkb > 0) fetch(kb0, va, vb);
-    for (int i = 0; i < nkb; ++i) {
+    float4 wa[PM * 8 / kLoad], wb[kMaxTerms][PN * 8 / kLoad];
+    auto step = [&](int i, float4 (&ca)[PM * 8 / kLoad], float4 (&cb)[kMaxTerms][PN * 8 / kLoad],
+                    float4 (&xa)[PM * 8 / kLoad], float4 (&xb)[kMaxTerms][PN * 8 / kLoad]) {
       const int s = i & 1;
-      float4 na[PM * 8 / kLoad], nb[kMaxTerms][PN * 8 / kLoad];
-      if (i + 1 < nkb) fetch(kb0 + i + 1, na, nb);
+      if (i + 1 < nkb) fetch(kb0 + i + 1, xa, xb);
       if (i >= 2) mb_wait(&sm.empty[s], ((i >> 1) - 1) & 1);
       unsigned char* st = sm.stage(s);
-      store_mn<PM, kLoad>(va, st, st + A_BYTES, tid);
+      store_mn<PM, kLoad>(ca, st, st + A_BYTES, tid);
 #pragma unroll
       for (int t = 0; t < kMaxTerms; ++t)
         if (t < nt)
-          store_mn<PN, kLoad>(vb[t], st + 2 * A_BYTES + t * 2 * B_BYTES, st + 2 * A_BYTES + t * 2 * B_BYTES + B_BYTES, tid);
+          store_mn_wide<kLoad>(cb[t], st + 2 * A_BYTES, st + 2 * A_BYTES + kMaxTerms * B_BYTES, tid, nt * PN, t);
       fence_async_smem();
       mb_arrive(&sm.full[s]);
-      if (i + 1 < nkb) {
-#pragma unroll
-        for (int q = 0; q < PM * 8 / kLoad; ++q) va[q] = na[q];
-#pragma unroll
-        for (int t = 0; t < kMaxTerms; ++t)
-#pragma unroll
-          for (int q = 0; q < PN * 8 / kLoad; ++q) vb[t][q] = nb[t][q];
-      }
+    };
+    if (nkb > 0) fetch(kb0, va, vb);
+    for (int i = 0; i < nkb; i += 2) {
+      step(i, va, vb, wa, wb);
+      if (i + 1 < nkb) step(i + 1, wa, wb, va, vb);
     }
   } else if (lane == 0) {
-    constexpr uint32_t idesc = instr_desc_tf32(PM, PN, true, true);
+    const uint32_t idesc = instr_desc_tf32(PM, nt * PN, true, true);       // all terms in one wide-N instruction
     for (int i = 0; i < nkb; ++i) {
       const int s = i & 1;
       mb_wait(&sm.full[s], (i >> 1) & 1);
       tc_fence_after();
       const uint32_t a_hi = s32(sm.stage(s)), a_lo = a_hi + A_BYTES;
-      for (int t = 0; t < nt; ++t) {
-        const uint32_t b_hi = a_hi + 2 * A_BYTES + t * 2 * B_BYTES, b_lo = b_hi + B_BYTES;
+      const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + kMaxTerms * B_BYTES;
 #pragma unroll
-        for (int kk = 0; kk < BK / 8; ++kk)
-          umma_tf32x3(tmem_d + t * PN, tile_desc<PM, false>(a_hi, kk), tile_desc<PM, false>(a_lo, kk),
-                      tile_desc<PN, false>(b_hi, kk), tile_desc<PN, false>(b_lo, kk), idesc, (i > 0 || kk > 0) ? 1u : 0u);
-      }
+      for (int kk = 0; kk < BK / 8; ++kk)
+        umma_tf32x3(tmem_d, tile_desc<PM, false>(a_hi, kk), tile_desc<PM, false>(a_lo, kk), tile_desc_mn(b_hi, kk, nt * PN),
+                    tile_desc_mn(b_lo, kk, nt * PN), idesc, (i > 0 || kk > 0) ? 1u : 0u);
       umma_commit(&sm.empty[s]);
     }
     umma_commit(sm.accum_full);
@@ -629,6 +722,8 @@ static int pick_ksplit(int tiles, int nkb, int limit) {
   return ks;
 }
 
+int launch_norm_bwd_reduce(const DgnNormArgs* a, const DgnNormGrad* g, cudaStream_t st);   // dgn_norm.cu
+
 }  // namespace dgn
 
 using namespace dgn;
@@ -639,6 +734,21 @@ static int done(cudaError_t e) {
   return DGN_OK;
 }
 
+static int launch_post_bwd(PostK& k, cudaStream_t st) {
+  k.ksplit = 1;
+  const int mt = (k.N + PM - 1) / PM;
+  const int smem = smem_bytes(k.S) + 7 * 4 * k.Fo;
+  static int smem_set = 0;
+  cudaError_t e = cudaSuccess;
+  if (smem > 220 * 1024) return DGN_ERR_UNSUPPORTED;
+  if (smem_set < smem) { e = set_smem(post_bwd_kernel, smem, false); smem_set = smem; }
+  if (e == cudaSuccess) e = launch_cluster(post_bwd_kernel, dim3(mt, k.n_lead_tiles + k.n_agg_tiles, 1), 1, smem, st, k);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) { g_dgn_last_cuda = e; return DGN_ERR_CUDA; }
+  return DGN_OK;
+}
+
+
 extern "C" int dgn_post_forward(const DgnPostArgs* a, float* y, int32_t ld_y, const DgnPostStats* st, int32_t* stat_parts,
                                 void* stream) {
   PostK k;
@@ -647,13 +757,17 @@ extern "C" int dgn_post_forward(const DgnPostArgs* a, float* y, int32_t ld_y, co
   if (!y) return DGN_ERR_INVALID;
   if (k.N == 0) return DGN_OK;
   k.y = y; k.ld_y = ld_y;
+  {   // DGN_POST_DBG=<device pointer, hex>: phase time stamps of every CTA (tools/post_phases.py)
+    static const unsigned long long dbg = [] { const char* e = getenv("DGN_POST_DBG"); return e ? strtoull(e, nullptr, 16) : 0ull; }();
+    k.dbg = reinterpret_cast<unsigned long long*>(dbg);
+  }
   const int mt = (k.N + PM - 1) / PM, ntl = (k.Fo + PN - 1) / PN, nkb = k.n_lead_kb + k.n_agg_kb;
   k.ksplit = pick_ksplit(mt * ntl, nkb, 8);
   // statistics slabs live behind the [mean | rstd] header of the norm workspace: 2 C + parts * 3 C <= DGN_NORM_WS_FLOATS(C)
-  if (st && st->stats && stat_parts && 2 + 3 * (long long)mt * k.ksplit <= DGN_NORM_WS_FLOATS(1)) {
+  if (st && st->stats && stat_parts && 2 + 3 * (long long)mt <= DGN_NORM_WS_FLOATS(1)) {
     k.stat_parts = st->stats + 2 * k.Fo;
     k.y_bias = st->y_bias; k.snorm = st->snorm; k.n_rows_dev = st->n_rows_dev;
-    *stat_parts = mt * k.ksplit;
+    *stat_parts = mt;
   }
   int cost[4096];
   if (nkb > 4096) return DGN_ERR_UNSUPPORTED;
@@ -675,15 +789,26 @@ extern "C" int dgn_post_backward(const DgnPostArgs* a, const float* d_y, int32_t
   if (ld_dy % 4 || ld_dcat % 4 || !al16(d_y) || !al16(d_cat)) return DGN_ERR_UNSUPPORTED;
   if (k.N == 0) return DGN_OK;
   k.dy = d_y; k.ld_dy = ld_dy; k.dcat = d_cat; k.ld_dcat = ld_dcat;
-  k.ksplit = 1;
-  const int mt = (k.N + PM - 1) / PM;
-  const int smem = smem_bytes(k.S);
-  static int smem_set = 0;
-  cudaError_t e = cudaSuccess;
-  if (smem_set < smem) { e = set_smem(post_bwd_kernel, smem, false); smem_set = smem; }
-  if (e == cudaSuccess)
-    e = launch_cluster(post_bwd_kernel, dim3(mt, k.n_lead_tiles + k.n_agg_tiles, 1), 1, smem, (cudaStream_t)stream, k);
-  return done(e);
+  return launch_post_bwd(k, (cudaStream_t)stream);
+}
+
+extern "C" int dgn_post_backward_norm(const DgnPostArgs* a, const DgnNormArgs* n, const DgnNormGrad* g, float* d_cat,
+                                      int32_t ld_dcat, void* stream) {
+  PostK k;
+  if (int rc = fill_post(a, k)) return rc;
+  if (!n || !g || !d_cat || !n->y || !g->g_out || !g->d_y || !g->counter) return DGN_ERR_INVALID;
+  if (n->n_cols != k.Fo || n->n_rows != k.N) return DGN_ERR_INVALID;
+  if (n->gamma && !n->stats) return DGN_ERR_INVALID;
+  if (ld_dcat % 4 || !al16(d_cat) || n->ld_y % 4 || g->ld_go % 4 || g->ld_dy % 4 || !al16(n->y) || !al16(g->g_out) ||
+      !al16(g->d_y))
+    return DGN_ERR_UNSUPPORTED;
+  if (k.N == 0) return DGN_OK;
+  if (int rc = launch_norm_bwd_reduce(n, g, (cudaStream_t)stream)) return rc;
+  k.dcat = d_cat; k.ld_dcat = ld_dcat;
+  k.f_gout = g->g_out; k.f_ld_go = g->ld_go; k.f_y = n->y; k.f_ld_y = n->ld_y; k.f_ybias = n->y_bias; k.f_snorm = n->snorm;
+  k.f_gamma = n->gamma; k.f_beta = n->beta; k.f_stats = n->stats; k.f_training = n->training; k.f_relu = n->relu;
+  k.f_dy = g->d_y; k.f_ld_dy = g->ld_dy; k.f_nrows_dev = n->n_rows_dev;
+  return launch_post_bwd(k, (cudaStream_t)stream);
 }
 
 static int launch_wgrad(WgK& k, int tiles, cudaStream_t st) {

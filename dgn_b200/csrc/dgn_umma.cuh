@@ -246,5 +246,28 @@ __device__ __forceinline__ void store_mn(const float4 (&v)[ROWS * 8 / NT], unsig
   }
 }
 
+// MN-major tile that is part of a WIDE operand of rows_total (a multiple of 64) MN-floats: the 64-column tile `term`
+// lands at MN-columns [64 term, 64 term + 64) of the wide tile, so that one tcgen05.mma with N = rows_total consumes all
+// terms at once (a narrow N = 64 MMA is bound by re-reading the A operand from shared memory: measured 69 instead of 32
+// cycles per instruction).
+template <int NT>
+__device__ __forceinline__ void store_mn_wide(const float4 (&v)[64 * 8 / NT], unsigned char* hi, unsigned char* lo, int t,
+                                              int rows_total, int term) {
+  constexpr int CPR = 64 / 4;
+#pragma unroll
+  for (int i = 0; i < 64 * 8 / NT; ++i) {
+    const int id = t + i * NT;
+    const int krow = id / CPR, ch = term * CPR + id % CPR;
+    const uint32_t kl = krow & 3, c16 = ch & 7;
+    const uint32_t off = (uint32_t)(krow >> 2) * (uint32_t)(rows_total / 32) * 512u + (uint32_t)(ch >> 3) * 512u + kl * 128u +
+                         ((((c16 >> 1) ^ kl)) << 5) + ((c16 & 1u) << 4);
+    split_store(hi, lo, off, v[i]);
+  }
+}
+__device__ __forceinline__ uint64_t tile_desc_mn(uint32_t tile_addr, int kk, int rows_total) {
+  const uint32_t KA = (uint32_t)(rows_total / 32) * 512u;
+  return smem_desc(tile_addr + kk * 2 * KA, 512, KA, kLayoutSW128Base32);
+}
+
 }  // namespace umma
 }  // namespace dgn

@@ -27,8 +27,8 @@ from __future__ import annotations
 import torch
 
 from . import _lib, ops
-from .ops import (agg_backward_raw, agg_forward_raw, gemm, norm_backward_raw, norm_forward_raw, pair_linear_backward,
-                  pair_linear_forward, post_backward, post_forward, post_wgrad, pre_wgrad, side_queue, _f32c, _need_cuda)
+from .ops import (agg_backward_raw, agg_forward_raw, gemm, norm_backward_raw, norm_forward_raw, norm_pair_forward,
+                  pair_linear_backward, pair_linear_forward, post_backward, post_forward, post_wgrad, pre_wgrad, side_queue, _f32c, _need_cuda)
 
 _ONES = {}
 
@@ -45,10 +45,13 @@ def _ones(n, device):
 class LayerConfig:
     """Non-tensor state of one fused layer call."""
     __slots__ = ("graph", "spec", "eig", "snorm", "bn", "training", "relu", "residual", "direct", "in_dim",
-                 "has_pretrans", "params", "aspec", "post")
+                 "has_pretrans", "params", "aspec", "post", "pq", "next_w", "pq_out")
 
     def __init__(self, graph, spec, eig, snorm, bn, training, relu, residual, direct, in_dim, has_pretrans, params,
-                 spec_raw=None, post=None):
+                 spec_raw=None, post=None, pq=None, next_w=None):
+        # pq: (P, Q) of THIS layer already computed by the previous layer's epilogue; next_w: pretrans weight of the
+        # NEXT layer, whose P / Q this layer's epilogue computes (returned through pq_out)
+        self.pq, self.next_w, self.pq_out = pq, next_w, None
         self.graph, self.spec, self.eig, self.snorm, self.bn = graph, spec, eig, snorm, bn
         self.training, self.relu, self.residual, self.direct = training, relu, residual, direct
         self.in_dim, self.has_pretrans, self.params = in_dim, has_pretrans, params
@@ -66,7 +69,10 @@ class _FusedLayer(torch.autograd.Function):
         N, dev = h.shape[0], h.device
         P = Q = None
         if cfg.has_pretrans:
-            P, Q = pair_linear_forward(h, W_pre, Fi)     # h @ W_src^T, h @ W_dst^T in one launch
+            if cfg.pq is not None:
+                P, Q = cfg.pq                            # computed by the previous layer's fused epilogue
+            else:
+                P, Q = pair_linear_forward(h, W_pre, Fi)     # h @ W_src^T, h @ W_dst^T in one launch
             cat = torch.empty((N, Fi + spec.out_width), device=dev, dtype=torch.float32)
             agg_forward_raw(g, spec, _lib.MSG_AFFINE, P, Q, R, h, cfg.eig, cat, True, q_bias=b_pre)
         else:                                            # simple layer: message = h[src], no h block
@@ -90,14 +96,27 @@ class _FusedLayer(torch.autograd.Function):
                                           getattr(g, "n_rows_dev", None))
         else:
             y = gemm(cat, W_post)                        # cat @ W_post^T
+        # epilogue, fused with the next layer's node-level pretrans halves when that layer is known and the batch
+        # statistics are final (or not needed)
+        fuse_next = (cfg.next_w is not None and N > 0 and cfg.next_w.shape[1] >= 2 * Co and
+                     (bn is None or not use_batch or stat_parts > 0))
         nargs = norm_forward_raw(
-            y, out, stats, snorm=cfg.snorm, y_bias=b_post,
+            y, out, stats, snorm=cfg.snorm, y_bias=b_post, launch=not fuse_next,
             gamma=gamma if bn is not None else None, beta=beta if bn is not None else None,
             running_mean=bn.running_mean if bn is not None else None,
             running_var=bn.running_var if bn is not None else None,
             momentum=(0.1 if bn is None or bn.momentum is None else bn.momentum),
             eps=(1e-5 if bn is None else bn.eps), training=use_batch, relu=cfg.relu,
             residual=h if cfg.residual else None, n_rows_dev=getattr(g, "n_rows_dev", None), stat_parts=stat_parts)
+        if fuse_next:
+            Fn = cfg.next_w.shape[0]
+            Pn = torch.empty((N, Fn), device=dev, dtype=torch.float32)
+            Qn = torch.empty((N, Fn), device=dev, dtype=torch.float32)
+            if norm_pair_forward(nargs, cfg.next_w, Pn, Qn):
+                cfg.pq_out = (Pn, Qn)
+            else:                                        # shapes outside the fused kernel: plain epilogue
+                ops.check(ops.lib.dgn_norm_forward(ops.C.byref(nargs), ops._stream(y)), "dgn_norm_forward")
+                ops._count(1)
         ctx.cfg, ctx.nargs = cfg, nargs
         ctx.save_for_backward(h, R, P, Q, cat, y, stats, W_pre, b_pre, W_post, b_post, gamma, beta)
         return out
@@ -123,14 +142,18 @@ class _FusedLayer(torch.autograd.Function):
             d_gamma = torch.empty(Co, device=dev) if has_bn else None
             d_beta = torch.empty(Co, device=dev) if has_bn else None
             d_bpost = torch.empty(Co, device=dev)
-        norm_backward_raw(ctx.nargs, g_out, d_y, scratch, d_gamma, d_beta, d_bpost, accumulate=direct)
-
-        # ---- posttrans GEMM --------------------------------------------------------------------------------------------
         fold = cfg.post is not None and N > 0
+        d_cat = None
         if fold:
-            d_cat = torch.empty_like(cat)                # [d_y W_h | sum_s c_s (d_y W_s)]: gradient of [h | raw aggregates]
-            post_backward(cfg.post, g, cat, W_post, d_y, d_cat)
+            # [d_y W_h | sum_s c_s (d_y W_s)]: gradient of [h | raw aggregates]; d_y itself is evaluated by the GEMM's
+            # operand loader from g_out and y (2 launches for norm backward + posttrans backward)
+            d_cat = torch.empty_like(cat)
+            if not ops.post_backward_norm(cfg.post, g, cat, W_post, ctx.nargs, g_out, d_y, scratch, d_gamma, d_beta,
+                                          d_bpost, direct, d_cat):
+                norm_backward_raw(ctx.nargs, g_out, d_y, scratch, d_gamma, d_beta, d_bpost, accumulate=direct)
+                post_backward(cfg.post, g, cat, W_post, d_y, d_cat)
         else:
+            norm_backward_raw(ctx.nargs, g_out, d_y, scratch, d_gamma, d_beta, d_bpost, accumulate=direct)
             d_cat = gemm(d_y, W_post, b_kmajor=False)    # d_y @ W_post
         # dW_post = d_y^T @ cat, computed as (cat^T @ d_y)^T so the 128-row tile dimension is the wide one.
         # Weight gradients are off the critical path: with direct accumulation they run on the side stream.
@@ -164,9 +187,16 @@ class _FusedLayer(torch.autograd.Function):
                 # zeros: only rows of real edges are written; the padding rows of a fixed-capacity batch flow into
                 # dW_e = d_R^T @ e (and the pretrans MLP backward) and must not carry allocator garbage
                 d_R = torch.zeros((max(E, 1), Fi), device=dev, dtype=torch.float32)[:E]
-            agg_backward_raw(g, spec, _lib.MSG_AFFINE, P, Q, R, h, cfg.eig, d_cat, True, d_x=d_P, d_q=d_Q, d_r=d_R,
-                             d_h=d_h, edge_ws=ws, q_bias=b_pre, d_h_addend=resid)
-            pair_linear_backward(d_P, d_Q, W_pre, Fi, d_h)                                   # += d_P W_src + d_Q W_dst
+            if N > 0 and W_pre.stride(1) == 1 and ops.pair_gather_supported(Fi, d_P.shape[1], ws, d_Q, W_pre, d_h, d_P):
+                # the per-edge message gradients stay in `ws`; their source-side reduction happens inside the
+                # pretrans input-gradient kernel (one launch instead of two)
+                agg_backward_raw(g, spec, _lib.MSG_AFFINE, P, Q, R, h, cfg.eig, d_cat, True, d_x=None, d_q=d_Q, d_r=d_R,
+                                 d_h=d_h, edge_ws=ws, q_bias=b_pre, d_h_addend=resid)
+                ops.pair_gather_backward(g, ws, d_Q, W_pre, Fi, d_h, d_P)
+            else:
+                agg_backward_raw(g, spec, _lib.MSG_AFFINE, P, Q, R, h, cfg.eig, d_cat, True, d_x=d_P, d_q=d_Q, d_r=d_R,
+                                 d_h=d_h, edge_ws=ws, q_bias=b_pre, d_h_addend=resid)
+                pair_linear_backward(d_P, d_Q, W_pre, Fi, d_h)                               # += d_P W_src + d_Q W_dst
             if direct:
                 gW = pW_pre.grad
                 ones = _ones(N, dev)
@@ -202,7 +232,7 @@ class _FusedLayer(torch.autograd.Function):
 
 
 def fused_layer(graph, spec, eig, h, R, pretrans_lin, posttrans_lin, bn, snorm, training, relu, residual, in_dim,
-                direct_grads=None, spec_raw=None, post=None):
+                direct_grads=None, spec_raw=None, post=None, pq=None, next_w=None):
     """One DGN layer (complex / tower when ``pretrans_lin`` is given, simple otherwise) as a single autograd node.
 
     ``direct_grads``: accumulate parameter gradients in place when every parameter already has ``.grad``; defaults
@@ -223,5 +253,6 @@ def fused_layer(graph, spec, eig, h, R, pretrans_lin, posttrans_lin, bn, snorm, 
             snorm = snorm.contiguous()
     eig = _f32c(eig)
     cfg = LayerConfig(graph, spec, eig, snorm, bn, training, relu, residual, direct_grads, in_dim, has_pre, params,
-                      spec_raw, post)
-    return _FusedLayer.apply(cfg, h, R, W_pre, b_pre, posttrans_lin.weight, posttrans_lin.bias, gamma, beta)
+                      spec_raw, post, pq, next_w)
+    out = _FusedLayer.apply(cfg, h, R, W_pre, b_pre, posttrans_lin.weight, posttrans_lin.bias, gamma, beta)
+    return out, cfg.pq_out

@@ -18,6 +18,8 @@ The GEMMs stay plain fp32 library calls (TF32 would break the 1e-5 parity bound)
 """
 from __future__ import annotations
 
+import weakref
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -31,6 +33,10 @@ from .layers import MLP, FCLayer
 from .scalers import SCALERS
 
 EPS = 1e-5      # rb/nets/dgn_layer.py:1 (unused there as well; the live EPS is aggregators.EPS)
+
+# producer layer -> weak reference to the pretrans Linear of the layer that consumed its output last time (see
+# _FusedConv._fused_forward); kept outside the modules so that state_dict / deepcopy / pickle never see it
+_NEXT_PRE = weakref.WeakKeyDictionary()
 
 
 def _avg_log(avg_d) -> float:
@@ -96,11 +102,33 @@ class _FusedConv(nn.Module):
         spec_raw, pspec = self._folded(eig.shape[1], self.in_dim if pre is not None else 0, post.out_features)
         if pspec is not None and post.in_features != pspec.w_cols:
             spec_raw = pspec = None
-        out = fused_layer(g, self._spec(eig.shape[1]), eig, h, R, pre, post,
-                          self.batchnorm_h if self.batch_norm else None, snorm_n if self.graph_norm else None,
-                          self.training, relu, residual, self.in_dim, spec_raw=spec_raw, post=pspec)
+        # Cross-layer fusion without touching the caller's loop (``for conv in self.layers: h = conv(g, h, e, snorm_n)``,
+        # rb/nets/*/dgn_net.py): a layer tags its output with itself; the layer that receives the tensor registers its
+        # pretrans weight with the producer, whose epilogue from then on also computes this layer's P = h W_src^T,
+        # Q = h W_dst^T (one launch less per layer) and hands them over on the tensor.  Anything that does not match
+        # (another consumer, changed weights, different graph) simply recomputes.
+        pq = None
+        if pre is not None:
+            tag = getattr(h, "_dgn_pq", None)
+            if tag is not None and tag[0] is pre.weight and tag[1] == pre.weight._version and tag[2] is g:
+                pq = tag[3]
+            producer = getattr(h, "_dgn_from", None)
+            if producer is not None and producer() is not None:
+                _NEXT_PRE[producer()] = weakref.ref(pre)
+        ref = _NEXT_PRE.get(self)
+        nxt = ref() if ref is not None else None
+        next_w = None
+        if nxt is not None and nxt.weight.is_cuda and nxt.weight.dtype == torch.float32 and not (self.dropout and self.training):
+            next_w = nxt.weight
+        out, pq_out = fused_layer(g, self._spec(eig.shape[1]), eig, h, R, pre, post,
+                                  self.batchnorm_h if self.batch_norm else None, snorm_n if self.graph_norm else None,
+                                  self.training, relu, residual, self.in_dim, spec_raw=spec_raw, post=pspec, pq=pq,
+                                  next_w=next_w)
         if self.dropout and self.training:
             out = F.dropout(out, self.dropout, training=True)
+        out._dgn_from = weakref.ref(self)
+        if pq_out is not None:
+            out._dgn_pq = (next_w, next_w._version, g, pq_out)
         return out
 
     def _pretrans_aggregate(self, g, h, e, cat_input=True):

@@ -127,6 +127,8 @@ def agg_backward_raw(graph, spec, mode, x, q, r, h_in, eig, g_out, cat_input, d_
         gr.g_hcopy = g_out.data_ptr()
     if d_x is not None:
         gr.d_x, gr.ld_dx, gr.edge_ws = d_x.data_ptr(), d_x.stride(0), edge_ws.data_ptr()
+    elif edge_ws is not None:
+        gr.edge_ws = edge_ws.data_ptr()          # spill only: the caller reduces over the out-edges (pair_gather_backward)
     if d_q is not None:
         gr.d_q, gr.ld_dq = d_q.data_ptr(), d_q.stride(0)
     if d_r is not None:
@@ -193,7 +195,7 @@ def aggregate(graph, spec: AggSpec, mode: int, h_in, eig, x=None, q=None, r=None
 
 def norm_forward_raw(y, out, stats, snorm=None, y_bias=None, gamma=None, beta=None, running_mean=None,
                      running_var=None, momentum=0.1, eps=1e-5, training=True, relu=True, residual=None,
-                     n_rows_dev=None, stat_parts=0):
+                     n_rows_dev=None, stat_parts=0, launch=True):
     """dgn_norm_forward on pre-allocated tensors; returns the filled DgnNormArgs (needed by the backward)."""
     N, Cn = y.shape
     a = _lib.DgnNormArgs()
@@ -213,9 +215,22 @@ def norm_forward_raw(y, out, stats, snorm=None, y_bias=None, gamma=None, beta=No
     if n_rows_dev is not None:
         a.n_rows_dev = n_rows_dev.data_ptr()
     a.stat_parts = int(stat_parts)
-    check(lib.dgn_norm_forward(C.byref(a), _stream(y)), "dgn_norm_forward")
-    _count(2 if (gamma is not None and training and not stat_parts) else 1)
+    if launch:
+        check(lib.dgn_norm_forward(C.byref(a), _stream(y)), "dgn_norm_forward")
+        _count(2 if (gamma is not None and training and not stat_parts) else 1)
     return a
+
+
+def norm_pair_forward(a, W_next, P, Q):
+    """The apply pass of ``a`` (a filled DgnNormArgs whose statistics are final) fused with ``P = out W_src^T``,
+    ``Q = out W_dst^T`` of the next layer's pretrans weight; False when the shapes are outside the kernel's range."""
+    rc = lib.dgn_norm_pair_forward(C.byref(a), P.shape[1], W_next.data_ptr(), W_next.stride(0), P.data_ptr(), P.stride(0),
+                                   Q.data_ptr(), Q.stride(0), torch.cuda.current_stream(P.device).cuda_stream)
+    if rc == -2:
+        return False
+    check(rc, "dgn_norm_pair_forward")
+    _count(1)
+    return True
 
 
 def norm_backward_raw(a, g_out, d_y, scratch, d_gamma=None, d_beta=None, d_bias=None, accumulate=False):
@@ -473,9 +488,23 @@ class PostSpec:
         return a
 
 
+_COUNTERS = {}
+
+
+def _counter(device):
+    """One zero-initialised device int32 per (device, stream): 'last CTA' counters return to zero after every launch."""
+    key = (str(device), torch.cuda.current_stream(device).cuda_stream)
+    c = _COUNTERS.get(key)
+    if c is None:
+        c = torch.zeros(4, dtype=torch.int32, device=device)
+        _COUNTERS[key] = c
+    return c
+
+
 def post_forward(ps: PostSpec, graph, cat, W, y, stats=None, y_bias=None, snorm=None, n_rows_dev=None):
     """``y = h W_h^T + sum_s c_s (agg W_s^T)``.  With ``stats`` (the workspace of the norm call that follows) the kernel
-    also leaves partial batch statistics of ``(y + y_bias) * snorm`` there; returns their number (0 = not written)."""
+    also leaves partial batch statistics of ``(y + y_bias) * snorm`` there, one slab per 128-row tile.  Returns
+    ``stat_parts`` for ``norm_forward_raw``: 0 = nothing written, > 0 = that many slabs."""
     st, parts = None, C.c_int32(0)
     if stats is not None:
         st = _lib.DgnPostStats(stats.data_ptr(), y_bias.data_ptr() if y_bias is not None else None,
@@ -492,6 +521,28 @@ def post_backward(ps: PostSpec, graph, cat, W, d_y, d_cat):
     check(lib.dgn_post_backward(C.byref(ps.args(graph, cat, W)), d_y.data_ptr(), d_y.stride(0), d_cat.data_ptr(),
                                 d_cat.stride(0), _stream(cat)), "dgn_post_backward")
     _count(1)
+
+
+def post_backward_norm(ps: PostSpec, graph, cat, W, nargs, g_out, d_y, scratch, d_gamma, d_beta, d_bias, accumulate, d_cat):
+    """Backward of the layer epilogue and of the folded posttrans in two launches: the column sums of the norm backward
+    (finalised by their last CTA) and ``dgn_post_backward`` whose operand loader evaluates ``d_y`` on the fly (``d_y`` is
+    also written: the weight gradient reads it).  Returns False when the shapes are outside the kernels' range."""
+    gr = _lib.DgnNormGrad()
+    gr.g_out, gr.ld_go, gr.d_y, gr.ld_dy, gr.scratch = (g_out.data_ptr(), g_out.stride(0), d_y.data_ptr(), d_y.stride(0),
+                                                    scratch.data_ptr())
+    if d_gamma is not None:
+        gr.d_gamma, gr.d_beta = d_gamma.data_ptr(), d_beta.data_ptr()
+    if d_bias is not None:
+        gr.d_bias = d_bias.data_ptr()
+    gr.accumulate = int(accumulate)
+    gr.counter = _counter(cat.device).data_ptr()
+    rc = lib.dgn_post_backward_norm(C.byref(ps.args(graph, cat, W)), C.byref(nargs), C.byref(gr), d_cat.data_ptr(),
+                                    d_cat.stride(0), _stream(cat))
+    if rc == -2:
+        return False
+    check(rc, "dgn_post_backward_norm")
+    _count(2)
+    return True
 
 
 def post_wgrad(ps: PostSpec, graph, cat, W, d_y, d_w, accumulate):
@@ -607,6 +658,22 @@ def pair_linear_forward(h, W, Fi):
     check(rc, "dgn_pair_linear_forward")
     _count(1)
     return P, Q
+
+
+def pair_gather_supported(Fi, Fo, *tensors):
+    return (FOLD_ENABLED and 0 < Fi <= 128 and 0 < Fo <= 128 and Fi % 4 == 0 and Fo % 4 == 0 and
+            all(t.stride(0) % 4 == 0 and t.data_ptr() % 16 == 0 for t in tensors))
+
+
+def pair_gather_backward(graph, edge_ws, d_Q, W, Fi, d_h, d_P):
+    """``d_P[u] = sum_{out-edges} edge_ws[slot]`` ; ``d_h += d_P W[:, :Fi] + d_Q W[:, Fi:2Fi]`` ; ``d_P`` written - the
+    source-side reduction of the aggregation backward and the pretrans input gradient in one launch."""
+    N, Fo = d_Q.shape
+    check(lib.dgn_pair_gather_backward(N, Fi, Fo, graph.out_ptr.data_ptr(), graph.out_slot.data_ptr(),
+                                       edge_ws.data_ptr(), edge_ws.stride(0), d_Q.data_ptr(), d_Q.stride(0),
+                                       W.data_ptr(), W.stride(0), d_h.data_ptr(), d_h.stride(0), d_P.data_ptr(),
+                                       d_P.stride(0), _stream(d_h)), "dgn_pair_gather_backward")
+    _count(1)
 
 
 def pair_linear_backward(d_P, d_Q, W, Fi, d_h):

@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define DGN_ABI_VERSION 6
+#define DGN_ABI_VERSION 8
 #define DGN_MAX_AGG 32      /* aggregators per layer (the reference registry has 24)        */
 #define DGN_MAX_SCALERS 4   /* scalers per layer (the reference registry has 3)             */
 #define DGN_MAX_SLOTS 8     /* distinct eigen-weighted feature sums one launch can carry    */
@@ -175,7 +175,8 @@ typedef struct {
   const float* d_h_addend;/* [N,F] optional: added into d_h_in (e.g. the residual branch's gradient)     */
   int32_t ld_dha;
   float* edge_ws;         /* [E,F] workspace (slot order) for the deterministic source-side reduction;
-                             required when d_x != NULL                                                   */
+                             required when d_x != NULL.  With d_x == NULL the per-edge message gradients are
+                             only left here (the caller reduces them, see dgn_pair_gather_backward)      */
   int32_t fold_h_in;      /* 1: d_x += d_h_in (SOURCE mode where x and h_in are the same tensor)         */
 } DgnAggGrad;
 
@@ -237,6 +238,13 @@ typedef struct {
 
 int dgn_norm_forward(const DgnNormArgs* a, void* stream);
 
+/* dgn_norm_forward (apply pass only: a->stat_parts > 0, or no batch statistics needed) fused with the node-level halves
+ * of the NEXT layer's pretrans: out = epilogue(y) as above, P = out W_src^T, Q = out W_dst^T with W = [W_src | W_dst | ..]
+ * of shape [f_out, >= 2 C] - one launch instead of dgn_norm_forward + dgn_pair_linear_forward.  C, f_out <= 128 and
+ * multiples of 4, else DGN_ERR_UNSUPPORTED. */
+int dgn_norm_pair_forward(const DgnNormArgs* a, int32_t f_out, const float* w, int32_t ld_w, float* p, int32_t ld_p,
+                          float* q, int32_t ld_q, void* stream);
+
 /* Backward of dgn_norm_forward: given g_out it writes d_y, d_residual (may alias nothing; NULL to
  * skip), d_gamma, d_beta.  Needs the forward's `out` (for the ReLU mask) and `stats`. */
 typedef struct {
@@ -248,6 +256,11 @@ typedef struct {
   float* d_bias;           /* [C] optional: gradient of y_bias = column sums of d_y                     */
   int32_t accumulate;      /* 1: d_gamma / d_beta / d_bias are accumulated (+=) instead of overwritten  */
   float* scratch;          /* [DGN_NORM_WS_FLOATS(C)] fp32 workspace                                    */
+  int32_t* counter;        /* optional: one device int32, zero before the first call (left zero again).  With it the
+                              LAST CTA of the column-sum pass finalises them: d_gamma / d_beta / d_bias are written
+                              there and the two per-column means the apply pass needs are left in a->stats[2C, 4C)
+                              (the forward's statistics slabs are dead by then), so the apply pass - or the fused
+                              prologue of dgn_post_backward_norm - only reads 2 C floats                     */
 } DgnNormGrad;
 
 int dgn_norm_backward(const DgnNormArgs* a, const DgnNormGrad* g, void* stream);
@@ -315,8 +328,9 @@ typedef struct {
 
 /* Optional by-product of dgn_post_forward: partial batch statistics (count, mean, M2 per column and per row slab) of
  * z = (y + y_bias) * snorm, i.e. of what BatchNorm1d normalises at rb/nets/dgn_layer.py:122-126, written into the
- * workspace of the dgn_norm_forward call that follows.  *stat_parts receives the number of slabs (pass it on as
- * DgnNormArgs.stat_parts), 0 when the layout does not fit the workspace (then run the norm's own statistics pass). */
+ * workspace of the dgn_norm_forward call that follows, one slab per 128-row tile (the CTAs of a cluster combine theirs
+ * over distributed shared memory).  *stat_parts receives the number of slabs (pass it on as DgnNormArgs.stat_parts),
+ * 0 when the layout does not fit the workspace (then run the norm's own statistics pass). */
 typedef struct {
   float* stats;              /* DgnNormArgs.stats of the following dgn_norm_forward, [DGN_NORM_WS_FLOATS(n_out)] */
   const float* y_bias;       /* [n_out] or NULL                                                                */
@@ -327,6 +341,11 @@ typedef struct {
 int dgn_post_forward(const DgnPostArgs* a, float* y, int32_t ld_y, const DgnPostStats* st, int32_t* stat_parts,
                      void* stream);
 int dgn_post_backward(const DgnPostArgs* a, const float* d_y, int32_t ld_dy, float* d_cat, int32_t ld_dcat, void* stream);
+/* dgn_norm_backward + dgn_post_backward in two launches instead of three: the column sums of the norm backward
+ * (finalised by their last CTA, g->counter required) followed by dgn_post_backward whose operand loader evaluates
+ * d_y = d(epilogue)/dy on the fly from g->g_out and n->y; d_y is also written to g->d_y (the weight gradient reads it). */
+int dgn_post_backward_norm(const DgnPostArgs* a, const DgnNormArgs* n, const DgnNormGrad* g, float* d_cat, int32_t ld_dcat,
+                           void* stream);
 int dgn_post_wgrad(const DgnPostArgs* a, const float* d_y, int32_t ld_dy, float* d_w, int32_t ld_dw, int32_t accumulate,
                    void* stream);
 
@@ -347,6 +366,15 @@ int dgn_pair_linear_forward(int32_t N, int32_t Fi, int32_t Fo, const float* h, i
                             float* P, int32_t ld_p, float* Q, int32_t ld_q, void* stream);
 int dgn_pair_linear_backward(int32_t N, int32_t Fi, int32_t Fo, const float* dP, int32_t ld_p, const float* dQ,
                              int32_t ld_q, const float* W, int32_t ld_w, float* d_h, int32_t ld_dh, void* stream);
+
+/* dgn_pair_linear_backward with the source-side reduction of dgn_agg_backward folded in: call dgn_agg_backward with
+ * DgnAggGrad.d_x = NULL and edge_ws set (the per-edge message gradients are left in edge_ws, slot order, and the
+ * source-side launch is skipped), then
+ *   d_P[u] = sum over out-edges j of u of edge_ws[out_slot[j]] ;  d_h[u] += d_P[u] W_src + d_Q[u] W_dst
+ * in ONE launch; d_P is written out (the weight gradient needs it).  out_ptr / out_slot: DgnGraph's by-source transpose. */
+int dgn_pair_gather_backward(int32_t N, int32_t Fi, int32_t Fo, const int32_t* out_ptr, const int32_t* out_slot,
+                             const float* edge_ws, int32_t ld_ws, const float* dQ, int32_t ld_q, const float* W,
+                             int32_t ld_w, float* d_h, int32_t ld_dh, float* dP, int32_t ld_p, void* stream);
 
 /* MLPReadout with L = 2 hidden layers (rb/nets/mlp_readout_layer.py:11-30):
  *   y = W3 relu(W2 relu(W1 x + b1) + b2) + b3      x [n_rows, d0], W1 [d1, d0], W2 [d2, d1], W3 [d_out, d2]
