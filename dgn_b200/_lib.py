@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DGN_LIB_PATH") or os.path.join(_HERE, "libdgn_b200.so")
 
 MAX_AGG, MAX_SCALERS, MAX_SLOTS = 32, 4, 8
-ABI_VERSION = 8
+ABI_VERSION = 10
 NORM_WS_PER_COL = 640
 
 # DgnAggKind / DgnScalerKind / DgnMsgMode
@@ -69,7 +69,7 @@ class DgnNormArgs(C.Structure):
 class DgnNormGrad(C.Structure):
     _fields_ = [("g_out", C.c_void_p), ("ld_go", C.c_int32), ("d_y", C.c_void_p), ("ld_dy", C.c_int32),
                 ("d_residual", C.c_void_p), ("ld_dres", C.c_int32), ("d_gamma", C.c_void_p), ("d_beta", C.c_void_p),
-                ("d_bias", C.c_void_p), ("accumulate", C.c_int32), ("scratch", C.c_void_p), ("counter", C.c_void_p)]
+                ("d_bias", C.c_void_p), ("accumulate", C.c_int32), ("scratch", C.c_void_p)]
 
 
 class DgnHeadArgs(C.Structure):
@@ -88,6 +88,28 @@ class DgnPostArgs(C.Structure):
 
 class DgnPostStats(C.Structure):
     _fields_ = [("stats", C.c_void_p), ("y_bias", C.c_void_p), ("snorm", C.c_void_p), ("n_rows_dev", C.c_void_p)]
+
+
+MAX_PAYLOADS = 6
+
+
+class DgnPayload(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("row_bytes", C.c_int32), ("per", C.c_int32)]
+
+
+class DgnDataset(C.Structure):
+    _fields_ = [("n_graphs", C.c_int32), ("node_off", C.c_void_p), ("edge_off", C.c_void_p), ("ovf_off", C.c_void_p),
+                ("in_ptr", C.c_void_p), ("in_src", C.c_void_p), ("in_eid", C.c_void_p), ("out_ptr", C.c_void_p),
+                ("out_slot", C.c_void_p), ("src", C.c_void_p), ("dst", C.c_void_p), ("log_deg", C.c_void_p),
+                ("ovf_ptr", C.c_void_p)]
+
+
+class DgnBatchOut(C.Structure):
+    _fields_ = [("n_cap", C.c_int32), ("e_cap", C.c_int32), ("b_cap", C.c_int32), ("in_ptr", C.c_void_p),
+                ("in_src", C.c_void_p), ("in_eid", C.c_void_p), ("out_ptr", C.c_void_p), ("out_slot", C.c_void_p),
+                ("src", C.c_void_p), ("dst", C.c_void_p), ("graph_ptr", C.c_void_p), ("ovf_ptr", C.c_void_p),
+                ("meta", C.c_void_p), ("log_deg", C.c_void_p), ("snorm_n", C.c_void_p), ("n_payloads", C.c_int32),
+                ("payload", DgnPayload * MAX_PAYLOADS)]
 
 
 class DgnHeadGrad(C.Structure):
@@ -125,8 +147,6 @@ SIGNATURES = {
     "dgn_post_forward": (C.c_int, [C.POINTER(DgnPostArgs), C.c_void_p, C.c_int32, C.POINTER(DgnPostStats),
                                    C.POINTER(C.c_int32), C.c_void_p]),
     "dgn_post_backward": (C.c_int, [C.POINTER(DgnPostArgs), C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
-    "dgn_post_backward_norm": (C.c_int, [C.POINTER(DgnPostArgs), C.POINTER(DgnNormArgs), C.POINTER(DgnNormGrad), C.c_void_p,
-                                         C.c_int32, C.c_void_p]),
     "dgn_post_wgrad": (C.c_int, [C.POINTER(DgnPostArgs), C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
                                  C.c_void_p]),
     "dgn_pre_wgrad": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
@@ -138,6 +158,10 @@ SIGNATURES = {
     "dgn_pair_gather_backward": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                            C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
                                            C.c_void_p, C.c_int32, C.c_void_p]),
+    "dgn_eig_precompute": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                     C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "dgn_eig_flip": (C.c_int, [C.c_void_p, C.c_int64, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "dgn_collate_device": (C.c_int, [C.POINTER(DgnDataset), C.c_void_p, C.c_int32, C.POINTER(DgnBatchOut), C.c_void_p]),
     "dgn_head_forward": (C.c_int, [C.POINTER(DgnHeadArgs), C.c_void_p]),
     "dgn_head_backward": (C.c_int, [C.POINTER(DgnHeadArgs), C.POINTER(DgnHeadGrad), C.c_void_p]),
     "dgn_l1_loss_forward": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

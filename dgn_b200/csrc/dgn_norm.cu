@@ -226,55 +226,6 @@ __global__ void __launch_bounds__(kTX * kTY) norm_bwd_reduce_kernel(const DgnNor
       part[q * a.n_cols + col] = t;
     }
   }
-  if (!g.counter) return;
-  // ---- finalize by the last CTA: slab partials -> d_gamma / d_beta / d_bias and the two means of the apply pass ----
-  __shared__ bool is_last;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0 && threadIdx.y == 0) {
-    const unsigned total = gridDim.x * gridDim.y;
-    const unsigned done = atomicAdd(reinterpret_cast<unsigned*>(g.counter), 1u);
-    is_last = (done == total - 1);
-    if (is_last) *g.counter = 0;
-  }
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
-  const double inv_n = (n > 0) ? 1.0 / (double)n : 0.0;
-  for (int c = threadIdx.y * kTX + threadIdx.x; c < a.n_cols; c += kTX * kTY) {
-    double s5[kBwdSums] = {0.0, 0.0, 0.0, 0.0, 0.0};
-    for (int p0 = 0; p0 < kParts; p0 += 8) {                // 8 slabs per batch: independent loads, fixed summation order
-      double v[8][kBwdSums];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const double* part = reinterpret_cast<const double*>(g.scratch) + (size_t)(p0 + j) * kBwdSums * a.n_cols;
-#pragma unroll
-        for (int q = 0; q < kBwdSums; ++q) v[j][q] = __ldcg(part + q * a.n_cols + c);
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-#pragma unroll
-        for (int q = 0; q < kBwdSums; ++q) s5[q] += v[j][q];
-    }
-    const bool stat = a.gamma && a.training;
-    if (a.stats) {
-      a.stats[2 * a.n_cols + c] = stat ? (float)(s5[0] * inv_n) : 0.f;    // mean of g1
-      a.stats[3 * a.n_cols + c] = stat ? (float)(s5[1] * inv_n) : 0.f;    // mean of g1 * xhat
-    }
-    const float keep = g.accumulate ? 1.f : 0.f;
-    if (a.gamma) {
-      if (g.d_beta) g.d_beta[c] = keep * g.d_beta[c] + (float)s5[0];
-      if (g.d_gamma) g.d_gamma[c] = keep * g.d_gamma[c] + (float)s5[1];
-    }
-    if (g.d_bias) {
-      double db = s5[2];
-      if (a.gamma) {
-        if (a.training) db = s5[2] - (s5[0] * inv_n) * s5[3] - (s5[1] * inv_n) * s5[4];
-        db *= (double)a.gamma[c] * (double)a.stats[a.n_cols + c];
-      }
-      g.d_bias[c] = keep * g.d_bias[c] + (float)db;
-    }
-  }
 }
 
 __global__ void __launch_bounds__(kTX * kTY) norm_bwd_apply_kernel(const DgnNormArgs a, const DgnNormGrad g) {
@@ -283,12 +234,7 @@ __global__ void __launch_bounds__(kTX * kTY) norm_bwd_apply_kernel(const DgnNorm
   const int col = blockIdx.y * kTX + threadIdx.x;
   __shared__ float s_b[kTX], s_g[kTX];
   __shared__ double sh[kBwdSums][kTY][kTX];
-  if (g.counter) {                                     // finalised by the column-sum pass
-    if (threadIdx.y == 0 && col < a.n_cols) {
-      s_b[threadIdx.x] = a.stats ? a.stats[2 * a.n_cols + col] : 0.f;
-      s_g[threadIdx.x] = a.stats ? a.stats[3 * a.n_cols + col] : 0.f;
-    }
-  } else {
+  {
     constexpr int PER = kParts / kTY;
     double acc[kBwdSums] = {0.0, 0.0, 0.0, 0.0, 0.0};
     if (col < a.n_cols) {
@@ -540,17 +486,6 @@ extern "C" int dgn_norm_forward(const DgnNormArgs* a, void* stream) {
   launch_pdl(norm_apply_kernel, norm_grid_apply(a), block, 0, st, *a);
   return check_launch();
 }
-
-namespace dgn {
-// column-sum pass of the norm backward alone (finalised by its last CTA): used by dgn_post_backward_norm
-int launch_norm_bwd_reduce(const DgnNormArgs* a, const DgnNormGrad* g, cudaStream_t st) {
-  if (!a || !g || !a->y || !g->g_out || !g->scratch || !g->counter || a->n_cols <= 0) return DGN_ERR_INVALID;
-  if (a->gamma && !a->stats) return DGN_ERR_INVALID;
-  if (a->n_rows == 0) return DGN_OK;
-  launch_pdl(norm_bwd_reduce_kernel, dim3(kParts, (a->n_cols + kTX - 1) / kTX), dim3(kTX, kTY), 0, st, *a, *g);
-  return check_launch();
-}
-}  // namespace dgn
 
 extern "C" int dgn_norm_backward(const DgnNormArgs* a, const DgnNormGrad* g, void* stream) {
   if (!a || !g || !a->y || !g->g_out || !g->d_y || !g->scratch || a->n_cols <= 0) return DGN_ERR_INVALID;

@@ -63,10 +63,6 @@ struct PostK {
   int n_lead_tiles, n_agg_tiles;
   // optional BatchNorm partial statistics of z = (y + y_bias) * snorm, one slab per row tile: [cnt | mean | M2][Fo]
   float* stat_parts; const float* y_bias; const float* snorm; const int* n_rows_dev;
-  // optional fused prologue of the backward: d_y = d(epilogue)/dy evaluated by the operand loader (dy == nullptr then)
-  const float* f_gout; int f_ld_go; const float* f_y; int f_ld_y; const float* f_ybias; const float* f_snorm;
-  const float* f_gamma; const float* f_beta; const float* f_stats; int f_training, f_relu;
-  float* f_dy; int f_ld_dy; const int* f_nrows_dev;
   unsigned long long* dbg;                 // optional [n_ctas][8] %globaltimer stamps of the forward kernel's phases (tools/)
 };
 
@@ -348,61 +344,10 @@ __global__ void __launch_bounds__(kPostThreads, 1) post_bwd_kernel(const __grid_
   const int tmem_cols = nt * PN;
   const uint32_t tmem_d = prologue(sm, tmem_cols);
 
-  // fused prologue: per-column constants of the norm backward [7][Fo]: bias, mean, rstd, gamma, beta, mean(g1), mean(g1 xhat)
-  float* cst = reinterpret_cast<float*>(sm.base + 2 * sm.stage_bytes + 128);
-  const bool fused = g.f_gout != nullptr;
-  if (fused) {
-    const bool bn = g.f_gamma != nullptr, stat = bn && g.f_training;
-    for (int c = tid; c < g.Fo; c += kPostThreads) {
-      cst[c] = g.f_ybias ? __ldg(g.f_ybias + c) : 0.f;
-      cst[g.Fo + c] = bn ? g.f_stats[c] : 0.f;
-      cst[2 * g.Fo + c] = bn ? g.f_stats[g.Fo + c] : 1.f;
-      cst[3 * g.Fo + c] = bn ? __ldg(g.f_gamma + c) : 1.f;
-      cst[4 * g.Fo + c] = bn ? __ldg(g.f_beta + c) : 0.f;
-      cst[5 * g.Fo + c] = stat ? g.f_stats[2 * g.Fo + c] : 0.f;
-      cst[6 * g.Fo + c] = stat ? g.f_stats[3 * g.Fo + c] : 0.f;
-    }
-    __syncthreads();
-  }
-  const int n_real = g.f_nrows_dev ? *g.f_nrows_dev : g.N;
-
   if (warp < kLoad / 32) {
     float4 va[PM * 8 / kLoad], vb[kMaxTerms][PN * 8 / kLoad];
-    // d_y chunk (row, 4 columns) of the fused prologue: same arithmetic as norm_bwd_apply_kernel (dgn_norm.cu)
-    auto fetch_dy = [&](int k0, float4 (&a)[PM * 8 / kLoad]) {
-#pragma unroll
-      for (int i = 0; i < PM * 8 / kLoad; ++i) {
-        const int id = tid + i * kLoad;
-        const int row = id >> 3, ch = id & 7;
-        const int gr = m0 + row, gk = k0 + ch * 4;
-        a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (gr < g.N && gk < g.Fo) {
-          if (gr < n_real) {
-            const float4 go = __ldg(reinterpret_cast<const float4*>(g.f_gout + (size_t)gr * g.f_ld_go + gk));
-            const float4 yv = __ldg(reinterpret_cast<const float4*>(g.f_y + (size_t)gr * g.f_ld_y + gk));
-            const float sn = g.f_snorm ? __ldg(g.f_snorm + gr) : 1.f;
-            const float gg[4] = {go.x, go.y, go.z, go.w}, yy[4] = {yv.x, yv.y, yv.z, yv.w};
-            float d[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int c = gk + j;
-              const float z = (yy[j] + cst[c]) * sn;
-              const float xhat = (z - cst[g.Fo + c]) * cst[2 * g.Fo + c];
-              const float ga = cst[3 * g.Fo + c];
-              float g1 = gg[j];
-              if (g.f_relu && !(xhat * ga + cst[4 * g.Fo + c] > 0.f)) g1 = 0.f;
-              float dz = g.f_gamma ? ga * cst[2 * g.Fo + c] * (g1 - cst[5 * g.Fo + c] - xhat * cst[6 * g.Fo + c]) : g1;
-              d[j] = dz * sn;
-            }
-            a[i] = make_float4(d[0], d[1], d[2], d[3]);
-          }
-          if (blockIdx.y == 0) *reinterpret_cast<float4*>(g.f_dy + (size_t)gr * g.f_ld_dy + gk) = a[i];
-        }
-      }
-    };
     auto fetch = [&](int kb, float4 (&a)[PM * 8 / kLoad], float4 (&b)[kMaxTerms][PN * 8 / kLoad]) {
-      if (fused) fetch_dy(kb * BK, a);
-      else fetch_k<PM, kLoad>(g.dy, g.ld_dy, m0, g.N, kb * BK, g.Fo, a, tid);
+      fetch_k<PM, kLoad>(g.dy, g.ld_dy, m0, g.N, kb * BK, g.Fo, a, tid);
 #pragma unroll
       for (int t = 0; t < kMaxTerms; ++t)
         if (t < nt)
@@ -722,8 +667,6 @@ static int pick_ksplit(int tiles, int nkb, int limit) {
   return ks;
 }
 
-int launch_norm_bwd_reduce(const DgnNormArgs* a, const DgnNormGrad* g, cudaStream_t st);   // dgn_norm.cu
-
 }  // namespace dgn
 
 using namespace dgn;
@@ -737,7 +680,7 @@ static int done(cudaError_t e) {
 static int launch_post_bwd(PostK& k, cudaStream_t st) {
   k.ksplit = 1;
   const int mt = (k.N + PM - 1) / PM;
-  const int smem = smem_bytes(k.S) + 7 * 4 * k.Fo;
+  const int smem = smem_bytes(k.S);
   static int smem_set = 0;
   cudaError_t e = cudaSuccess;
   if (smem > 220 * 1024) return DGN_ERR_UNSUPPORTED;
@@ -789,25 +732,6 @@ extern "C" int dgn_post_backward(const DgnPostArgs* a, const float* d_y, int32_t
   if (ld_dy % 4 || ld_dcat % 4 || !al16(d_y) || !al16(d_cat)) return DGN_ERR_UNSUPPORTED;
   if (k.N == 0) return DGN_OK;
   k.dy = d_y; k.ld_dy = ld_dy; k.dcat = d_cat; k.ld_dcat = ld_dcat;
-  return launch_post_bwd(k, (cudaStream_t)stream);
-}
-
-extern "C" int dgn_post_backward_norm(const DgnPostArgs* a, const DgnNormArgs* n, const DgnNormGrad* g, float* d_cat,
-                                      int32_t ld_dcat, void* stream) {
-  PostK k;
-  if (int rc = fill_post(a, k)) return rc;
-  if (!n || !g || !d_cat || !n->y || !g->g_out || !g->d_y || !g->counter) return DGN_ERR_INVALID;
-  if (n->n_cols != k.Fo || n->n_rows != k.N) return DGN_ERR_INVALID;
-  if (n->gamma && !n->stats) return DGN_ERR_INVALID;
-  if (ld_dcat % 4 || !al16(d_cat) || n->ld_y % 4 || g->ld_go % 4 || g->ld_dy % 4 || !al16(n->y) || !al16(g->g_out) ||
-      !al16(g->d_y))
-    return DGN_ERR_UNSUPPORTED;
-  if (k.N == 0) return DGN_OK;
-  if (int rc = launch_norm_bwd_reduce(n, g, (cudaStream_t)stream)) return rc;
-  k.dcat = d_cat; k.ld_dcat = ld_dcat;
-  k.f_gout = g->g_out; k.f_ld_go = g->ld_go; k.f_y = n->y; k.f_ld_y = n->ld_y; k.f_ybias = n->y_bias; k.f_snorm = n->snorm;
-  k.f_gamma = n->gamma; k.f_beta = n->beta; k.f_stats = n->stats; k.f_training = n->training; k.f_relu = n->relu;
-  k.f_dy = g->d_y; k.f_ld_dy = g->ld_dy; k.f_nrows_dev = n->n_rows_dev;
   return launch_post_bwd(k, (cudaStream_t)stream);
 }
 

@@ -22,7 +22,9 @@ import torch
 import ctypes as C
 
 from . import _lib, ops
-from .parallel import allreduce_mean_, flatten_parameters
+import os
+
+from .parallel import allreduce_sum_, flatten_parameters
 
 
 class FlatAdam:
@@ -68,14 +70,22 @@ class FlatAdam:
 
 class TrainStep:
     def __init__(self, net, template_graph, targets_like, lr=1e-3, weight_decay=0.0, graphed=True,
-                 node_key="feat", edge_key="feat", warmup_iters=3):
-        """``template_graph``: a (padded, for graphed=True) host ``BatchedGraph`` defining the batch layout."""
+                 node_key="feat", edge_key="feat", warmup_iters=3, loss_weight=None):
+        """``template_graph``: a (padded, for graphed=True) host ``BatchedGraph`` defining the batch layout.
+        ``loss_weight``: this rank's share factor of the global mean loss (``parallel.shard_loss_weight``); it lives in
+        device memory (``set_loss_weight``) so a captured step follows batches whose shards differ in size."""
+        import torch.distributed as dist
         self.net = net
         self.dev = next(net.parameters()).device
         self.graphed = graphed
         self.node_key, self.edge_key = node_key, edge_key
         self.flat_p, self.flat_g = flatten_parameters(net)
-        self.opt = FlatAdam(self.flat_p, self.flat_g, lr=lr, weight_decay=weight_decay)
+        self.world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        # gradient average over the ranks = SUM all-reduce + 1 / world folded into the Adam kernel
+        self.opt = FlatAdam(self.flat_p, self.flat_g, lr=lr, weight_decay=weight_decay, grad_scale=1.0 / self.world)
+        self.loss_weight = None
+        if loss_weight is not None:
+            self.loss_weight = torch.full((), float(loss_weight), device=self.dev)
         if graphed and not template_graph.padded:
             raise ValueError("graphed=True needs batches padded to a fixed capacity (BatchedGraph(capacity=...))")
         # static device-side batch: the graph object is re-bound onto this buffer once
@@ -85,11 +95,10 @@ class TrainStep:
         self.targets = torch.zeros(targets_like.shape, dtype=targets_like.dtype, device=self.dev)
         self.targets.copy_(targets_like)
         self.loss = torch.zeros((), device=self.dev)
-        # With more than one rank the gradient all-reduce and the Adam launch stay OUTSIDE the captured graph
-        # (2 extra launches per step): replaying NCCL collectives from a CUDA graph is fragile across
-        # NCCL / driver versions, and the collective is latency bound either way.
-        import torch.distributed as dist
-        self.split_update = graphed and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        # With more than one rank the NCCL all-reduce of the flat gradient and the Adam launch stay OUTSIDE the captured
+        # graph (2 eager launches per step).  Capturing the collective (DGN_GRAPH_ALLREDUCE=1) was tried on B200 / NCCL
+        # 2.28.9 / torch 2.11: the capture of a graph that also forks a side stream hung, so it is opt-in only.
+        self.split_update = graphed and self.world > 1 and os.environ.get("DGN_GRAPH_ALLREDUCE", "0") != "1"
         self.launches_per_step = 0
         self.cuda_graph = None
         if graphed:
@@ -106,12 +115,18 @@ class TrainStep:
             scores = self.net(g, g.ndata[self.node_key], g.edata[self.edge_key], g.snorm_n, None)
             scope.flush_bn_counters()
             loss = self.net.loss(scores, self.targets)
-            loss.backward()
+            (loss * self.loss_weight if self.loss_weight is not None else loss).backward()
         return loss
 
+    def set_loss_weight(self, w: float):
+        """This rank's share factor for the NEXT step (stream-ordered 4-byte copy; see ``parallel.shard_loss_weight``)."""
+        if self.loss_weight is None:
+            raise ValueError("construct TrainStep(loss_weight=...) to train with weighted shards")
+        self.loss_weight.fill_(float(w))
+
     def _reduce_and_update(self):
-        allreduce_mean_(self.flat_g)          # one NCCL all-reduce of the flat gradient (no-op on a single rank)
-        self.opt.step()
+        allreduce_sum_(self.flat_g)           # one NCCL all-reduce of the flat gradient (no-op on a single rank)
+        self.opt.step()                       # Adam on grad / world (grad_scale)
 
     def _step_body(self):
         loss = self._fwd_bwd()
@@ -143,6 +158,18 @@ class TrainStep:
             raise ValueError("batch layout differs from the template (capacity / feature keys must match)")
         self.blob.copy_(host_graph._host_blob, non_blocking=True)
         self.targets.copy_(host_targets, non_blocking=True)
+
+    def load_ids(self, dataset, ids_host):
+        """Stage the batch made of the dataset graphs ``ids_host`` (pinned int32 ``[B]``): a ``4 B``-byte H2D copy of the
+        index list, then ONE launch assembles the batch (and its targets) in HBM from the dataset-resident fragments
+        (``dgn_b200.data.device_dataset.DeviceDataset``) - the host never touches graph data in the training loop."""
+        if self.cuda_graph is not None and int(ids_host.numel()) != self.g.graph_capacity:
+            raise ValueError("a captured step needs exactly %d graphs per batch (got %d)"
+                             % (self.g.graph_capacity, int(ids_host.numel())))
+        if getattr(self, "_ids", None) is None or self._ids.numel() != ids_host.numel():
+            self._ids = torch.empty(ids_host.numel(), dtype=torch.int32, device=self.dev)
+        self._ids.copy_(ids_host, non_blocking=True)
+        dataset.collate_into(self.g, self._ids, self.targets if dataset.targets is not None else None)
 
     def load_device(self, device_blob, device_targets):
         """Stage a batch that is already resident in HBM (device-to-device copy)."""

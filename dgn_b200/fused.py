@@ -142,18 +142,12 @@ class _FusedLayer(torch.autograd.Function):
             d_gamma = torch.empty(Co, device=dev) if has_bn else None
             d_beta = torch.empty(Co, device=dev) if has_bn else None
             d_bpost = torch.empty(Co, device=dev)
+        norm_backward_raw(ctx.nargs, g_out, d_y, scratch, d_gamma, d_beta, d_bpost, accumulate=direct)
         fold = cfg.post is not None and N > 0
-        d_cat = None
         if fold:
-            # [d_y W_h | sum_s c_s (d_y W_s)]: gradient of [h | raw aggregates]; d_y itself is evaluated by the GEMM's
-            # operand loader from g_out and y (2 launches for norm backward + posttrans backward)
-            d_cat = torch.empty_like(cat)
-            if not ops.post_backward_norm(cfg.post, g, cat, W_post, ctx.nargs, g_out, d_y, scratch, d_gamma, d_beta,
-                                          d_bpost, direct, d_cat):
-                norm_backward_raw(ctx.nargs, g_out, d_y, scratch, d_gamma, d_beta, d_bpost, accumulate=direct)
-                post_backward(cfg.post, g, cat, W_post, d_y, d_cat)
+            d_cat = torch.empty_like(cat)                # [d_y W_h | sum_s c_s (d_y W_s)]: gradient of [h | raw aggregates]
+            post_backward(cfg.post, g, cat, W_post, d_y, d_cat)
         else:
-            norm_backward_raw(ctx.nargs, g_out, d_y, scratch, d_gamma, d_beta, d_bpost, accumulate=direct)
             d_cat = gemm(d_y, W_post, b_kmajor=False)    # d_y @ W_post
         # dW_post = d_y^T @ cat, computed as (cat^T @ d_y)^T so the 128-row tile dimension is the wide one.
         # Weight gradients are off the critical path: with direct accumulation they run on the side stream.

@@ -69,7 +69,7 @@ class BatchedGraph:
                "meta", "ovf_ptr")
 
     def __init__(self, n_nodes, src, dst, batch_num_nodes=None, batch_num_edges=None, ndata=None, edata=None,
-                 pin_memory=None, capacity=None):
+                 pin_memory=None, capacity=None, graph_capacity=None):
         """``capacity=(N_cap, E_cap)`` pads the arrays to a fixed size (isolated padding nodes, unused
         padding slots) so that batches of different sizes share one memory layout - the shape a
         captured CUDA graph is replayed with.  ``number_of_nodes()`` then returns ``N_cap`` (the row
@@ -91,6 +91,8 @@ class BatchedGraph:
         self.batch_num_edges = [int(x) for x in (batch_num_edges if batch_num_edges is not None else [self._e])]
         assert sum(self.batch_num_nodes) == self.n_real_nodes
         B = len(self.batch_num_nodes)
+        # graph_capacity: room for that many graphs in graph_ptr (device-side collation fills batches of varying size)
+        self.graph_capacity = max(int(graph_capacity), B) if graph_capacity else B
         Nr, Er = self.n_real_nodes, self.n_real_edges
         ndata = dict(ndata or {})
         edata = dict(edata or {})
@@ -99,7 +101,8 @@ class BatchedGraph:
         N, E = self._n, self._e
         for name, shape, dt in (("in_ptr", (N + 1,), np.int32), ("in_src", (E,), np.int32), ("in_eid", (E,), np.int32),
                                 ("out_ptr", (N + 1,), np.int32), ("out_slot", (E,), np.int32),
-                                ("graph_ptr", (B + 1,), np.int32), ("src", (E,), np.int32), ("dst", (E,), np.int32),
+                                ("graph_ptr", (self.graph_capacity + 1,), np.int32), ("src", (E,), np.int32),
+                                ("dst", (E,), np.int32),
                                 ("log_deg", (N,), np.float32), ("snorm_n", (N, 1), np.float32),
                                 ("meta", (4,), np.int32), ("ovf_ptr", (N + 1,), np.int32)):
             pack.add(name, shape, dt)
@@ -120,7 +123,8 @@ class BatchedGraph:
         hv["src"][:Er] = src
         hv["dst"][:Er] = dst
         hv["graph_ptr"][0] = 0
-        np.cumsum(self.batch_num_nodes, out=hv["graph_ptr"][1:])
+        np.cumsum(self.batch_num_nodes, out=hv["graph_ptr"][1:B + 1])
+        hv["graph_ptr"][B + 1:] = Nr
         sizes = np.asarray(self.batch_num_nodes, dtype=np.float32)
         # collate(): snorm_n = sqrt(1 / n_g) per node  (rb/data/molecules.py:222-224)
         hv["snorm_n"][:Nr, 0] = np.repeat(np.sqrt(np.float32(1.0) / sizes), self.batch_num_nodes)
@@ -199,7 +203,8 @@ class BatchedGraph:
 
     @property
     def batch_size(self):
-        return len(self.batch_num_nodes)
+        """Number of graph slots the readouts run over (graphs past the real count are empty segments)."""
+        return self.graph_capacity if self.batch_num_nodes is None else len(self.batch_num_nodes)
 
     def edges(self):
         return self._t["src"].long(), self._t["dst"].long()
@@ -275,7 +280,7 @@ class BatchedGraph:
         return int((p[1:] - p[:-1]).max()) if self._n else 0
 
 
-def collate(samples, node_key="feat", edge_key="feat", extra_ndata=(), capacity=None):
+def collate(samples, node_key="feat", edge_key="feat", extra_ndata=(), capacity=None, graph_capacity=None):
     """``dataset.collate`` + ``dgl.batch`` (rb/data/molecules.py:219-230) for synthetic samples.
 
     Returns ``(graph, labels)``; ``graph.ndata`` holds ``feat`` and ``eig``, ``graph.edata`` holds
@@ -291,7 +296,7 @@ def collate(samples, node_key="feat", edge_key="feat", extra_ndata=(), capacity=
         ndata[k] = np.concatenate([np.asarray(s[k]) for s in samples], 0)
     edata = {edge_key: np.concatenate([np.asarray(s["edge_feat"]) for s in samples], 0)}
     g = BatchedGraph(int(offs[-1]), src, dst, sizes, [len(s["src"]) for s in samples], ndata, edata,
-                     capacity=capacity)
+                     capacity=capacity, graph_capacity=graph_capacity)
     if np.ndim(samples[0]["label"]) == 0:
         labels = torch.from_numpy(np.asarray([s["label"] for s in samples]))
     else:

@@ -403,6 +403,21 @@ def embedding(weight, idx, n_rows_dev=None, direct_grad=None):
     return _Embedding.apply(weight, idx, n_rows_dev, direct_grad)
 
 
+def eig_flip_(eig, seed, step):
+    """In-place entry-wise random sign flip of ``ndata['eig']`` on the device - the ``--flip`` augmentation of
+    rb/train/train_molecules_graph_regression.py:29-33 (one Bernoulli(1/2) per ENTRY, like the reference)."""
+    _need_cuda(eig)
+    if eig.dtype != torch.float32 or not eig.is_contiguous():
+        raise _lib.DgnError("eig_flip_ needs a contiguous float32 tensor")
+    check(lib.dgn_eig_flip(eig.data_ptr(), eig.numel(), int(seed), int(step), _stream(eig)), "dgn_eig_flip")
+    _count(1)
+    try:                                   # tell torch (and BatchedGraph.field's staleness check) about the in-place change
+        torch._C._autograd._unsafe_set_version_counter([eig], [eig._version + 1])
+    except Exception:
+        eig.add_(0)
+    return eig
+
+
 # ---------------------------------------------------------------------------------------------------------
 # fp32-accurate tensor-core GEMM (tcgen05, 3xTF32)
 # ---------------------------------------------------------------------------------------------------------
@@ -488,19 +503,6 @@ class PostSpec:
         return a
 
 
-_COUNTERS = {}
-
-
-def _counter(device):
-    """One zero-initialised device int32 per (device, stream): 'last CTA' counters return to zero after every launch."""
-    key = (str(device), torch.cuda.current_stream(device).cuda_stream)
-    c = _COUNTERS.get(key)
-    if c is None:
-        c = torch.zeros(4, dtype=torch.int32, device=device)
-        _COUNTERS[key] = c
-    return c
-
-
 def post_forward(ps: PostSpec, graph, cat, W, y, stats=None, y_bias=None, snorm=None, n_rows_dev=None):
     """``y = h W_h^T + sum_s c_s (agg W_s^T)``.  With ``stats`` (the workspace of the norm call that follows) the kernel
     also leaves partial batch statistics of ``(y + y_bias) * snorm`` there, one slab per 128-row tile.  Returns
@@ -521,28 +523,6 @@ def post_backward(ps: PostSpec, graph, cat, W, d_y, d_cat):
     check(lib.dgn_post_backward(C.byref(ps.args(graph, cat, W)), d_y.data_ptr(), d_y.stride(0), d_cat.data_ptr(),
                                 d_cat.stride(0), _stream(cat)), "dgn_post_backward")
     _count(1)
-
-
-def post_backward_norm(ps: PostSpec, graph, cat, W, nargs, g_out, d_y, scratch, d_gamma, d_beta, d_bias, accumulate, d_cat):
-    """Backward of the layer epilogue and of the folded posttrans in two launches: the column sums of the norm backward
-    (finalised by their last CTA) and ``dgn_post_backward`` whose operand loader evaluates ``d_y`` on the fly (``d_y`` is
-    also written: the weight gradient reads it).  Returns False when the shapes are outside the kernels' range."""
-    gr = _lib.DgnNormGrad()
-    gr.g_out, gr.ld_go, gr.d_y, gr.ld_dy, gr.scratch = (g_out.data_ptr(), g_out.stride(0), d_y.data_ptr(), d_y.stride(0),
-                                                    scratch.data_ptr())
-    if d_gamma is not None:
-        gr.d_gamma, gr.d_beta = d_gamma.data_ptr(), d_beta.data_ptr()
-    if d_bias is not None:
-        gr.d_bias = d_bias.data_ptr()
-    gr.accumulate = int(accumulate)
-    gr.counter = _counter(cat.device).data_ptr()
-    rc = lib.dgn_post_backward_norm(C.byref(ps.args(graph, cat, W)), C.byref(nargs), C.byref(gr), d_cat.data_ptr(),
-                                    d_cat.stride(0), _stream(cat))
-    if rc == -2:
-        return False
-    check(rc, "dgn_post_backward_norm")
-    _count(2)
-    return True
 
 
 def post_wgrad(ps: PostSpec, graph, cat, W, d_y, d_w, accumulate):

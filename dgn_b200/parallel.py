@@ -7,8 +7,10 @@ parameters (and their gradients) are views into ONE flat fp32 buffer, so the ste
 NCCL all-reduce of ~0.1-0.5 M floats (latency-bound over NVLink/NVSwitch; bucketing or overlap would
 buy nothing at this size) and a single fused optimizer update over the flat buffer.
 
-Semantics versus the single-GPU reference: BatchNorm uses per-rank batch
-statistics; mean losses are averaged over ranks (equal shard sizes).
+Semantics versus the single-GPU reference: BatchNorm uses per-rank (per-shard) batch
+statistics; a mean loss over the GLOBAL batch is the shard losses weighted by their share of the batch
+(``shard_loss_weight``: n_r * world / B, which the 1 / world of the gradient average turns into n_r / B), so ranks with
+unequal shards still produce the gradient of the global mean.
 """
 from __future__ import annotations
 
@@ -58,6 +60,20 @@ def shard_samples(samples, rank: int, world: int):
         bounds.append(min(bounds[-1] + 1, len(samples)))
     bounds.append(len(samples))
     return list(samples[bounds[rank]:bounds[rank + 1]])
+
+
+def shard_loss_weight(n_local: int, n_global: int, world: int) -> float:
+    """Factor for a rank's MEAN loss over its ``n_local`` units (graphs, or nodes for node-level losses) so that the
+    average of the rank gradients is the gradient of the mean over all ``n_global`` units."""
+    return float(n_local) * float(world) / float(max(n_global, 1))
+
+
+def allreduce_sum_(flat_grad: torch.Tensor, group=None) -> None:
+    """In-place SUM of the flat gradient over the ranks (no-op without an initialised group); the 1 / world of the
+    average is folded into the optimizer kernel (``FlatAdam.grad_scale``) instead of a separate launch."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return
+    dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
 
 
 def allreduce_mean_(flat_grad: torch.Tensor, group=None) -> None:

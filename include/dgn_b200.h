@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define DGN_ABI_VERSION 8
+#define DGN_ABI_VERSION 10
 #define DGN_MAX_AGG 32      /* aggregators per layer (the reference registry has 24)        */
 #define DGN_MAX_SCALERS 4   /* scalers per layer (the reference registry has 3)             */
 #define DGN_MAX_SLOTS 8     /* distinct eigen-weighted feature sums one launch can carry    */
@@ -256,11 +256,6 @@ typedef struct {
   float* d_bias;           /* [C] optional: gradient of y_bias = column sums of d_y                     */
   int32_t accumulate;      /* 1: d_gamma / d_beta / d_bias are accumulated (+=) instead of overwritten  */
   float* scratch;          /* [DGN_NORM_WS_FLOATS(C)] fp32 workspace                                    */
-  int32_t* counter;        /* optional: one device int32, zero before the first call (left zero again).  With it the
-                              LAST CTA of the column-sum pass finalises them: d_gamma / d_beta / d_bias are written
-                              there and the two per-column means the apply pass needs are left in a->stats[2C, 4C)
-                              (the forward's statistics slabs are dead by then), so the apply pass - or the fused
-                              prologue of dgn_post_backward_norm - only reads 2 C floats                     */
 } DgnNormGrad;
 
 int dgn_norm_backward(const DgnNormArgs* a, const DgnNormGrad* g, void* stream);
@@ -341,11 +336,6 @@ typedef struct {
 int dgn_post_forward(const DgnPostArgs* a, float* y, int32_t ld_y, const DgnPostStats* st, int32_t* stat_parts,
                      void* stream);
 int dgn_post_backward(const DgnPostArgs* a, const float* d_y, int32_t ld_dy, float* d_cat, int32_t ld_dcat, void* stream);
-/* dgn_norm_backward + dgn_post_backward in two launches instead of three: the column sums of the norm backward
- * (finalised by their last CTA, g->counter required) followed by dgn_post_backward whose operand loader evaluates
- * d_y = d(epilogue)/dy on the fly from g->g_out and n->y; d_y is also written to g->d_y (the weight gradient reads it). */
-int dgn_post_backward_norm(const DgnPostArgs* a, const DgnNormArgs* n, const DgnNormGrad* g, float* d_cat, int32_t ld_dcat,
-                           void* stream);
 int dgn_post_wgrad(const DgnPostArgs* a, const float* d_y, int32_t ld_dy, float* d_w, int32_t ld_dw, int32_t accumulate,
                    void* stream);
 
@@ -412,6 +402,61 @@ int dgn_head_backward(const DgnHeadArgs* a, const DgnHeadGrad* g, void* stream);
  * summation order; backward: d_y[i] = g_loss[0] * sign(y[i] - target[i]) / n with sign(0) = 0. */
 int dgn_l1_loss_forward(int32_t n, const float* y, const float* target, float* loss, void* stream);
 int dgn_l1_loss_backward(int32_t n, const float* y, const float* target, const float* g_loss, float* d_y, void* stream);
+
+/* Device-side collation: dgl.batch + dataset.collate (rb/data/molecules.py:219-230) without the host.
+ * The whole dataset lives in HBM as ONE pre-batched graph ("fragments"): node / edge ranges per graph, the CSR of the
+ * giant block-diagonal batch, per-node log-degree and overflow-group counts, and the payload arrays (node features,
+ * eigenvectors, edge features, per-graph targets).  A mini-batch is then an index list: one launch copies the selected
+ * graphs' fragments behind each other into the fixed-capacity batch layout the kernels read (BatchedGraph), adding the
+ * node / edge offsets on the fly; snorm_n, graph_ptr, ovf_ptr, meta and the zero padding are produced in the same
+ * launch.  Bit-identical to dgn_build_csr_host + dgn_build_groups_host on the concatenated edge lists (block-diagonal
+ * batches sort per graph). */
+#define DGN_MAX_PAYLOADS 6
+typedef struct {
+  const void* src;        /* dataset array, rows of row_bytes (multiple of 4)                                     */
+  void* dst;              /* batch array of the same row size; padding rows are zeroed                           */
+  int32_t row_bytes;
+  int32_t per;            /* 0: per node, 1: per edge, 2: per graph                                              */
+} DgnPayload;
+typedef struct {
+  int32_t n_graphs;       /* graphs in the dataset                                                               */
+  const int32_t* node_off;/* [G+1] node range of every graph in the dataset arrays                               */
+  const int32_t* edge_off;/* [G+1] edge range                                                                    */
+  const int32_t* ovf_off; /* [G+1] overflow-group range (dgn_build_groups_host over the whole dataset)           */
+  const int32_t* in_ptr;  /* [Nt+1] CSR of the whole dataset as one batch (dgn_build_csr_host), global ids       */
+  const int32_t* in_src;  /* [Et]                                                                                */
+  const int32_t* in_eid;  /* [Et]                                                                                */
+  const int32_t* out_ptr; /* [Nt+1]                                                                              */
+  const int32_t* out_slot;/* [Et]                                                                                */
+  const int32_t* src;     /* [Et] edge list, global ids                                                          */
+  const int32_t* dst;     /* [Et]                                                                                */
+  const float* log_deg;   /* [Nt]                                                                                */
+  const int32_t* ovf_ptr; /* [Nt+1] dataset-wide overflow-group offsets                                          */
+} DgnDataset;
+typedef struct {
+  int32_t n_cap, e_cap, b_cap;   /* capacities of the batch layout (nodes, edges, graphs)                        */
+  int32_t *in_ptr, *in_src, *in_eid, *out_ptr, *out_slot, *src, *dst, *graph_ptr, *ovf_ptr, *meta;
+  float *log_deg, *snorm_n;
+  int32_t n_payloads;
+  DgnPayload payload[DGN_MAX_PAYLOADS];
+} DgnBatchOut;
+/* ids: DEVICE int32 [n_ids] graph indices in batch order.  Returns DGN_ERR_INVALID for bad arguments; a batch that
+ * exceeds the capacities is truncated on the device and flagged in meta[3] = 1 (callers check it lazily). */
+int dgn_collate_device(const DgnDataset* ds, const int32_t* ids, int32_t n_ids, const DgnBatchOut* out, void* stream);
+
+/* Laplacian eigenvectors of every graph on the device: the per-graph host loop of the reference's loaders
+ * (scipy.sparse.linalg.eigs on L, rb/data/molecules.py:100-116, rb/data/SBMs.py:110-139, rb/data/HIV.py:17-46).
+ * node_off [G+1] node range of every graph; in_ptr / in_src: CSR with GLOBAL node ids (DgnDataset / DgnGraph arrays);
+ * the adjacency is symmetrised, deg = clip(row sum, 1).  norm: 0 = 'none' (L = D - A), 1 = 'sym' (I - D^-1/2 A D^-1/2),
+ * 2 = 'walk' (I - D^-1 A).  eig [N_total, ld_eig] receives the k eigenvectors of smallest eigenvalue (ascending, unit
+ * norm, largest-magnitude entry positive; zero columns for graphs with fewer than k nodes), eigval [G, k] (optional)
+ * the eigenvalues.  One CTA per graph, one-sided Jacobi in shared memory: max_nodes (the largest graph) <= 238. */
+int dgn_eig_precompute(int32_t n_graphs, const int32_t* node_off, const int32_t* in_ptr, const int32_t* in_src,
+                       int32_t max_nodes, int32_t norm, int32_t k, float* eig, int32_t ld_eig, float* eigval, void* stream);
+/* The sign-flip augmentation of rb/train/train_molecules_graph_regression.py:29-33 on the device: every ENTRY of eig
+ * is negated with probability 1/2 (counter-based generator over (seed, step, index): replayable from a CUDA graph when
+ * `step` lives in the caller's loop). */
+int dgn_eig_flip(float* eig, int64_t n_elems, uint64_t seed, uint64_t step, void* stream);
 
 int dgn_readout_forward(int32_t n_graphs, const int32_t* graph_ptr, int32_t n_cols, const float* h, int32_t ld_h,
                         int32_t op, float* out, int32_t ld_o, void* stream);

@@ -1,9 +1,10 @@
 """Byte-compile the UNMODIFIED reference's hot-path modules into ``oracle/_ref/`` (build container only).
 
 TEST INFRASTRUCTURE (see oracle/__init__.py).  The reference is a python code drop: "compiling it from the
-sources where they lie" means ``py_compile`` of ``realworld_benchmark/nets/**/*.py`` into SOURCELESS ``.pyc`` files
-under the git-ignored ``oracle/_ref/nets/`` (no reference source is copied into the repository; the directory is
-not gpurun-ignored, so the compiled modules travel to the GPU box like the built ``.so``).  ``bench.py --impl
+sources where they lie" means compiling ``realworld_benchmark/nets/**/*.py`` into SOURCELESS code objects
+(``<module>.refbin`` = marshalled bytecode; ``*.pyc`` files are stripped from gpurun snapshots) under the git-ignored
+``oracle/_ref/nets/`` (no reference source is copied into the repository; the directory is not gpurun-ignored, so the
+compiled modules travel to the GPU box like the built ``.so``).  ``bench.py --impl
 reference`` and the ``cpu_baseline`` leg import them from there - on top of the DGL-0.4.2 stand-in of
 ``oracle/standin`` - and time the reference's own python path (``kind: "reference"``); when ``oracle/_ref`` is absent
 they fall back to the oracle port (``kind: "port"``).
@@ -12,13 +13,16 @@ they fall back to the oracle port (``kind: "port"``).
 """
 from __future__ import annotations
 
+import importlib.abc
+import importlib.machinery
+import marshal
 import os
-import py_compile
 import sys
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = os.environ.get("DGN_REFERENCE", "/root/reference/realworld_benchmark")
 OUT = os.path.join(REPO, "oracle", "_ref")
+EXT = ".refbin"
 
 
 def build_ref(verbose: bool = False) -> int:
@@ -34,9 +38,11 @@ def build_ref(verbose: bool = False) -> int:
                 continue
             dst_dir = os.path.join(OUT, rel)
             os.makedirs(dst_dir, exist_ok=True)
-            dst = os.path.join(dst_dir, f[:-3] + ".pyc")
-            py_compile.compile(os.path.join(dirpath, f), cfile=dst, dfile=os.path.join("<reference>", rel, f),
-                               doraise=True)
+            dst = os.path.join(dst_dir, f[:-3] + EXT)
+            with open(os.path.join(dirpath, f), "rb") as fh:
+                code = compile(fh.read(), os.path.join("<reference>", rel, f), "exec", dont_inherit=True)
+            with open(dst, "wb") as fh:
+                fh.write(marshal.dumps(code))
             n += 1
             if verbose:
                 print("compiled", os.path.join(rel, f), "->", os.path.relpath(dst, REPO))
@@ -49,9 +55,36 @@ def ref_available() -> bool:
     tag = os.path.join(OUT, "PYTHON")
     try:
         return (open(tag).read().strip() == "%d.%d" % sys.version_info[:2] and
-                os.path.exists(os.path.join(OUT, "nets", "dgn_layer.pyc")))
+                os.path.exists(os.path.join(OUT, "nets", "dgn_layer" + EXT)))
     except OSError:
         return False
+
+
+class _RefFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
+    """Imports ``nets`` / ``nets.*`` from the marshalled code objects under ``oracle/_ref``."""
+
+    def find_spec(self, fullname, path=None, target=None):
+        if fullname != "nets" and not fullname.startswith("nets."):
+            return None
+        base = os.path.join(OUT, *fullname.split("."))
+        if os.path.isdir(base):
+            spec = importlib.machinery.ModuleSpec(fullname, self, is_package=True)
+            spec.submodule_search_locations = [base]
+            return spec
+        if os.path.exists(base + EXT):
+            return importlib.machinery.ModuleSpec(fullname, self, origin=base + EXT)
+        return None
+
+    def create_module(self, spec):
+        return None
+
+    def exec_module(self, module):
+        origin = module.__spec__.origin
+        if origin is None:                       # a (namespace-like) package directory
+            return
+        module.__file__ = origin
+        with open(origin, "rb") as fh:
+            exec(marshal.loads(fh.read()), module.__dict__)
 
 
 def import_ref():
@@ -61,8 +94,8 @@ def import_ref():
     GPUs (``CUDA_VISIBLE_DEVICES=""``) before torch initialises CUDA."""
     from oracle import use_standin_dgl
     use_standin_dgl()
-    if OUT not in sys.path:
-        sys.path.insert(1, OUT)
+    if not any(isinstance(f, _RefFinder) for f in sys.meta_path):
+        sys.meta_path.insert(0, _RefFinder())
     import nets.aggregators as ra
     import nets.scalers as rs
     import nets.dgn_layer as rl

@@ -20,25 +20,18 @@ sys.path.insert(0, REPO)
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--workload", default="zinc")
     ap.add_argument("--out", default=os.path.join(REPO, "gpurun_out", "step_trace.json"))
     args = ap.parse_args()
     import bench
     from dgn_b200.data.synthetic import make_samples, avg_log_degree
-    from dgn_b200.engine import TrainStep
-    from dgn_b200.graph import collate
-    from dgn_b200.task_nets.molecules_graph_regression import DGNNet
     dev = torch.device("cuda", 0)
     torch.backends.cuda.matmul.allow_tf32 = False
-    avg_log = avg_log_degree(make_samples("zinc", 1000, seed=12345))
-    pool = make_samples("zinc", bench.BATCH, seed=0)
-    cap_n = (int(sum(s["n"] for s in pool) * 1.03) + 63) // 64 * 64
-    cap_e = (int(sum(len(s["src"]) for s in pool) * 1.03) + 63) // 64 * 64
-    g, labels = collate(pool, capacity=(cap_n, cap_e))
-    tg = labels.float().unsqueeze(1).pin_memory()
-    torch.manual_seed(41)
-    net = DGNNet(bench.net_params(avg_log, dev)).to(dev).train()
-    template, _ = collate(pool, capacity=(cap_n, cap_e))
-    step = TrainStep(net, template, tg, lr=1e-3, weight_decay=3e-6, graphed=True)
+    w = bench.WORKLOADS[args.workload]
+    avg_log = avg_log_degree(make_samples(w["kind"], 1000 if w["kind"] != "pattern" else 64, seed=12345))
+    pools = [make_samples(w["kind"], w["graphs_per_gpu"], seed=0)]
+    net, step, host_batches, targets_host, _, _ = bench.build_step(w, pools, avg_log, dev, eager=False)
+    g, tg = host_batches[0], targets_host[0]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     for _ in range(5):
         step.load(g, tg)
