@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DGN_LIB_PATH") or os.path.join(_HERE, "libdgn_b200.so")
 
 MAX_AGG, MAX_SCALERS, MAX_SLOTS = 32, 4, 8
-ABI_VERSION = 10
+ABI_VERSION = 11
 NORM_WS_PER_COL = 640
 
 # DgnAggKind / DgnScalerKind / DgnMsgMode
@@ -161,6 +161,7 @@ SIGNATURES = {
     "dgn_eig_precompute": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                      C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "dgn_eig_flip": (C.c_int, [C.c_void_p, C.c_int64, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "dgn_segment_copy": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "dgn_collate_device": (C.c_int, [C.POINTER(DgnDataset), C.c_void_p, C.c_int32, C.POINTER(DgnBatchOut), C.c_void_p]),
     "dgn_head_forward": (C.c_int, [C.POINTER(DgnHeadArgs), C.c_void_p]),
     "dgn_head_backward": (C.c_int, [C.POINTER(DgnHeadArgs), C.POINTER(DgnHeadGrad), C.c_void_p]),

@@ -161,3 +161,43 @@ extern "C" int dgn_collate_device(const DgnDataset* ds, const int32_t* ids, int3
   if (e != cudaSuccess) { g_dgn_last_cuda = e; return DGN_ERR_CUDA; }
   return DGN_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Block scatter / gather between the per-tower parameters of a DGNLayerTower (rb/nets/dgn_layer.py:279-307) and the dense
+// block-structured operands the single-launch tower path runs on: one launch moves up to a few hundred rectangular
+// segments described by a device table (built once per layer).
+// ---------------------------------------------------------------------------------------------------------------
+namespace dgn {
+
+struct Seg {                       // 32 bytes
+  float* a;                        // tower-side tensor element (0, 0) of the segment
+  float* b;                        // dense-side tensor element (0, 0) of the segment
+  int32_t rows, cols, ld_a, ld_b;
+};
+
+// dir 0: b = a (pack); 1: a = b (unpack, overwrite); 2: a += b (unpack, accumulate)
+__global__ void __launch_bounds__(256) seg_copy_kernel(const Seg* __restrict__ segs, int dir) {
+  pdl_prologue();
+  const Seg s = segs[blockIdx.x];
+  const int n = s.rows * s.cols;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int r = i / s.cols, c = i - r * s.cols;
+    float* pa = s.a + (size_t)r * s.ld_a + c;
+    float* pb = s.b + (size_t)r * s.ld_b + c;
+    if (dir == 0) *pb = *pa;
+    else if (dir == 1) *pa = *pb;
+    else *pa += *pb;
+  }
+}
+
+}  // namespace dgn
+
+extern "C" int dgn_segment_copy(const void* seg_table, int32_t n_segments, int32_t direction, void* stream) {
+  if (!seg_table || n_segments < 0 || direction < 0 || direction > 2) return DGN_ERR_INVALID;
+  if (n_segments == 0) return DGN_OK;
+  launch_pdl(dgn::seg_copy_kernel, dim3((unsigned)n_segments), dim3(256), 0, (cudaStream_t)stream,
+             reinterpret_cast<const dgn::Seg*>(seg_table), (int)direction);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { g_dgn_last_cuda = e; return DGN_ERR_CUDA; }
+  return DGN_OK;
+}

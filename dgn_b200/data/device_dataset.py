@@ -73,8 +73,7 @@ class DeviceDataset:
         for _ in range(quantile_batches):
             ids = rng.integers(0, self.n_graphs, size=batch_size)
             n, e = max(n, int(self.sizes[ids].sum())), max(e, int(self.esizes[ids].sum()))
-        top = np.sort(self.sizes)[-batch_size:].sum(), np.sort(self.esizes)[-batch_size:].sum()
-        n, e = min(int(n * slack) + 64, int(top[0])), min(int(e * slack) + 64, int(top[1]))
+        n, e = int(n * slack) + 64, int(e * slack) + 64
         return (n + 63) // 64 * 64, (e + 63) // 64 * 64
 
     def template(self, batch_size, capacity):
@@ -83,6 +82,7 @@ class DeviceDataset:
         s = self._template_sample
         g, _ = collate([s], node_key=self.node_key, edge_key=self.edge_key, capacity=capacity,
                        graph_capacity=batch_size)
+        g.batch_num_nodes = None                 # batch_size = graph_capacity: all graph slots are live for the readouts
         return g
 
     def collate_into(self, graph: BatchedGraph, ids_dev: torch.Tensor, targets_out: torch.Tensor = None):

@@ -246,11 +246,17 @@ class DGNLayerTower(nn.Module):
 
     def forward(self, g, h, e, snorm_n):
         w = self.input_tower
-        if self.divide_input:
-            parts = [tw(g, h[:, i * w:(i + 1) * w], e, snorm_n) for i, tw in enumerate(self.towers)]
+        fusion = self.__dict__.get("_fusion")
+        if fusion is None:
+            from dgn_b200.towers import TowerFusion
+            fusion = self.__dict__["_fusion"] = TowerFusion(self)      # kept out of the module's parameters / state_dict
+        if fusion.supported(h):
+            # all towers as ONE block-structured layer: one aggregation launch, one posttrans GEMM, one epilogue
+            y = fusion.forward(g, h, snorm_n)
+        elif self.divide_input:
+            y = torch.cat([tw(g, h[:, i * w:(i + 1) * w], e, snorm_n) for i, tw in enumerate(self.towers)], dim=1)
         else:
-            parts = [tw(g, h, e, snorm_n) for tw in self.towers]
-        y = torch.cat(parts, dim=1)
+            y = torch.cat([tw(g, h, e, snorm_n) for tw in self.towers], dim=1)
         if len(self.towers) > 1:
             y = self.mixing_network(y)
         return h + y if self.residual else y

@@ -1,0 +1,241 @@
+"""Single-launch tower layer: all T towers of a ``DGNLayerTower`` in ONE fused layer call.
+
+The reference runs its towers one after the other (rb/nets/dgn_layer.py:309-325): T x (pretrans -> update_all -> posttrans ->
+graph norm -> BatchNorm).  Every aggregator is column-wise independent and BatchNorm is per column, so the T towers over
+feature slices of width F_t are exactly ONE layer of width F = T * F_t whose weights are block structured:
+
+    W_pre  [F, 2F]          rows / columns of tower t only  (block diagonal, [src | dst] halves)
+    W_post [F_o, (1+S*A) F] row block t reads column slice t of h and of every aggregate block
+
+``TowerFusion`` packs the tower parameters into such dense operands with one ``dgn_segment_copy`` launch (a device table
+of rectangular segments built once), runs the ordinary fused layer (``fused._FusedLayer``: one aggregation launch, one
+posttrans GEMM, one epilogue for all towers) and scatters the weight gradients / BatchNorm running statistics back with
+one launch each.  The zero blocks cost ~T x redundant flops in GEMMs that are latency bound at these sizes.
+"""
+from __future__ import annotations
+
+import types
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+from .fused import LayerConfig, _FusedLayer
+
+_SEG = np.dtype([("a", "<u8"), ("b", "<u8"), ("rows", "<i4"), ("cols", "<i4"), ("ld_a", "<i4"), ("ld_b", "<i4")])
+
+
+class _Ctx:
+    """Minimal stand-in for an autograd context, so that ``_FusedLayer.forward / backward`` can be driven directly."""
+
+    def save_for_backward(self, *tensors):
+        self.saved_tensors = tensors
+
+
+def _launch(table, direction, device):
+    _lib.check(_lib.lib.dgn_segment_copy(table.data_ptr(), table.numel() // _SEG.itemsize, direction,
+                                         torch.cuda.current_stream(device).cuda_stream), "dgn_segment_copy")
+    ops._count(1)
+
+
+class _TowerFused(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, fusion, g, eig, snorm, training, h, *tower_params):
+        f = fusion
+        dev = h.device
+        f.prepare(dev)
+        _launch(f.t_params, 0, dev)                               # tower parameters -> dense block operands (1 launch)
+        has_bn = f.bn is not None
+        if has_bn:
+            _launch(f.t_running, 0, dev)                          # running statistics -> concatenated buffers
+        direct = ops.DIRECT_GRADS and all(p.grad is not None for p in tower_params)
+        cfg = LayerConfig(g, f.spec(eig.shape[1]), eig, snorm, f.bn, training, False, False, True, f.F, True,
+                          (f.W_pre, f.b_pre, f.W_post, f.b_post, f.gamma if has_bn else None, f.beta if has_bn else None),
+                          *f.folded(eig.shape[1]))
+        inner = _Ctx()
+        out = _FusedLayer.forward(inner, cfg, h, None, f.W_pre, f.b_pre, f.W_post, f.b_post,
+                                  f.gamma if has_bn else None, f.beta if has_bn else None)
+        if has_bn and training:
+            _launch(f.t_running, 1, dev)                          # updated running statistics back to the towers
+            for bn in f.tower_bns:
+                ops.count_bn_batch(bn)
+        ctx.fusion, ctx.inner, ctx.direct, ctx.n_params = f, inner, direct, len(tower_params)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        f, dev = ctx.fusion, g_out.device
+        f.dense_grad.zero_()                                      # the fused layer accumulates into these (direct mode)
+        res = _FusedLayer.backward(ctx.inner, g_out)
+        d_h = res[1]
+        side = ops.side_queue(dev)
+        if ctx.direct:
+            def _scatter():
+                _launch(f.t_grads_direct, 2, dev)                 # dense gradients += into the towers' .grad (1 launch)
+            if side is not None:
+                side.run(_scatter)                                # after the weight-gradient GEMMs on the same queue
+            else:
+                _scatter()
+            return (None,) * 5 + (d_h,) + (None,) * ctx.n_params
+        if side is not None:
+            side.join()
+        _launch(f.t_grads_stage, 1, dev)
+        return (None,) * 5 + (d_h,) + tuple(t.clone() for t in f.stage_views)
+
+
+class TowerFusion:
+    """Packing state of one ``DGNLayerTower`` (built lazily on the first fused call)."""
+
+    def __init__(self, layer):
+        self.layer = layer
+        self._key = None
+        self._specs = {}
+
+    # ---- eligibility -------------------------------------------------------------------------------------------
+    def supported(self, h) -> bool:
+        L = self.layer
+        if not (ops.FOLD_ENABLED and h.is_cuda and len(L.towers) > 1 and L.divide_input and not L.edge_features):
+            return False
+        t0 = L.towers[0]
+        if t0.dropout and t0.training:
+            return False
+        for tw in L.towers:
+            if tw._affine(tw.pretrans) is None or tw._affine(tw.posttrans) is None:
+                return False
+        Ft, Fo = L.input_tower, L.output_tower
+        return Ft % 4 == 0 and Fo % 4 == 0 and (Ft * len(L.towers)) <= 512
+
+    # ---- specs ---------------------------------------------------------------------------------------------------
+    def spec(self, n_eig):
+        sp = self._specs.get(n_eig)
+        if sp is None:
+            t0 = self.layer.towers[0]
+            sp = ops.AggSpec(t0.aggregators, t0.scalers, float(t0._spec(n_eig).avg_log), self.F, n_eig)
+            self._specs[n_eig] = sp
+        return sp
+
+    def folded(self, n_eig):
+        key = ("fold", n_eig)
+        ent = self._specs.get(key)
+        if ent is None:
+            from .nets.scalers import SCALERS
+            spec = self.spec(n_eig)
+            post = ops.PostSpec(spec, self.F, self.Fo)
+            if post.supported(spec):
+                ent = (ops.AggSpec(spec.aggregators, [SCALERS["identity"]], spec.avg_log, self.F, n_eig), post)
+            else:
+                ent = (None, None)
+            self._specs[key] = ent
+        return ent
+
+    # ---- dense operands and segment tables ----------------------------------------------------------------------
+    def _tower_tensors(self):
+        L = self.layer
+        pre = [tw._affine(tw.pretrans) for tw in L.towers]
+        post = [tw._affine(tw.posttrans) for tw in L.towers]
+        bns = [tw.batchnorm_h for tw in L.towers] if L.towers[0].batch_norm else None
+        params = []
+        for t in range(len(L.towers)):
+            params += [pre[t].weight, pre[t].bias, post[t].weight, post[t].bias]
+            if bns is not None:
+                params += [bns[t].weight, bns[t].bias]
+        return pre, post, bns, params
+
+    def tower_params(self):
+        return self._tower_tensors()[3]
+
+    def prepare(self, dev):
+        L = self.layer
+        pre, post, bns, params = self._tower_tensors()
+        key = (str(dev),) + tuple(p.data_ptr() for p in params) + tuple(
+            (p.grad.data_ptr() if p.grad is not None else 0) for p in params) + (
+            tuple(b.running_mean.data_ptr() for b in bns) if bns is not None and bns[0].running_mean is not None else ())
+        if key == self._key:
+            return
+        T, Ft, Fo = len(L.towers), L.input_tower, L.output_tower
+        self.F, self.Fo = T * Ft, T * Fo
+        F, FO = self.F, self.Fo
+        blocks = post[0].weight.shape[1] // Ft                    # 1 + S * A
+        n_pre, n_post = F * 2 * F, FO * blocks * F
+        sizes = [n_pre, F, n_post, FO, FO, FO, FO, FO]             # W_pre, b_pre, W_post, b_post, gamma, beta, rm, rv
+        offs = np.concatenate([[0], np.cumsum([(s + 3) // 4 * 4 for s in sizes])])
+        self.dense = torch.zeros(int(offs[-1]), device=dev)        # zero blocks stay zero: only tower blocks are written
+        self.dense_grad = torch.zeros(int(offs[6]), device=dev)
+        v = lambda buf, i, shape: buf[int(offs[i]):int(offs[i]) + int(np.prod(shape))].view(shape)
+        self.W_pre, self.b_pre = v(self.dense, 0, (F, 2 * F)), v(self.dense, 1, (F,))
+        self.W_post, self.b_post = v(self.dense, 2, (FO, blocks * F)), v(self.dense, 3, (FO,))
+        self.gamma, self.beta = v(self.dense, 4, (FO,)), v(self.dense, 5, (FO,))
+        rm, rv = v(self.dense, 6, (FO,)), v(self.dense, 7, (FO,))
+        gviews = [v(self.dense_grad, 0, (F, 2 * F)), v(self.dense_grad, 1, (F,)), v(self.dense_grad, 2, (FO, blocks * F)),
+                  v(self.dense_grad, 3, (FO,)), v(self.dense_grad, 4, (FO,)), v(self.dense_grad, 5, (FO,))]
+        for t_, g_ in zip((self.W_pre, self.b_pre, self.W_post, self.b_post, self.gamma, self.beta), gviews):
+            t_.grad = g_                                           # the fused layer's direct mode accumulates here
+        self.tower_bns = bns
+        if bns is not None:
+            b0 = bns[0]
+            self.bn = types.SimpleNamespace(weight=self.gamma, bias=self.beta, running_mean=rm, running_var=rv,
+                                            momentum=b0.momentum, eps=b0.eps, track_running_stats=b0.track_running_stats,
+                                            num_batches_tracked=None)
+            if not b0.track_running_stats or b0.running_mean is None:
+                self.bn.running_mean = self.bn.running_var = None
+        else:
+            self.bn = None
+        # staging buffer for the non-direct path: one persistent tensor per tower parameter (fixed addresses)
+        self.stage = torch.zeros(sum((p.numel() + 3) // 4 * 4 for p in params), device=dev)
+        self.stage_views, o = [], 0
+        for p in params:
+            self.stage_views.append(self.stage[o:o + p.numel()].view(p.shape))
+            o += (p.numel() + 3) // 4 * 4
+
+        def segs(get_a, dense_ptr):
+            """segments (tower-side pointer getter, dense-side base pointers) for every tower parameter"""
+            rows = []
+            per = 6 if bns is not None else 4
+            for t in range(T):
+                a = [get_a(t * per + i) for i in range(per)]        # (ptr, ld) of W_pre, b_pre, W_post, b_post[, gamma, beta]
+                wp, bp, wq, bq = a[0], a[1], a[2], a[3]
+                for half in range(2):                                 # [src | dst] halves of the block-diagonal pretrans
+                    rows.append((wp[0] + 4 * half * Ft, dense_ptr[0] + 4 * ((t * Ft) * 2 * F + half * F + t * Ft), Ft, Ft,
+                                 wp[1], 2 * F))
+                rows.append((bp[0], dense_ptr[1] + 4 * t * Ft, 1, Ft, Ft, F))
+                for j in range(blocks):                               # h block and every aggregate block
+                    rows.append((wq[0] + 4 * j * Ft, dense_ptr[2] + 4 * ((t * Fo) * blocks * F + j * F + t * Ft), Fo, Ft,
+                                 wq[1], blocks * F))
+                rows.append((bq[0], dense_ptr[3] + 4 * t * Fo, 1, Fo, Fo, FO))
+                if bns is not None:
+                    rows.append((a[4][0], dense_ptr[4] + 4 * t * Fo, 1, Fo, Fo, FO))
+                    rows.append((a[5][0], dense_ptr[5] + 4 * t * Fo, 1, Fo, Fo, FO))
+            arr = np.array(rows, dtype=_SEG)
+            return torch.from_numpy(arr.view(np.uint8).copy()).to(dev)
+
+        dense_ptrs = [x.data_ptr() for x in (self.W_pre, self.b_pre, self.W_post, self.b_post, self.gamma, self.beta)]
+        grad_ptrs = [x.data_ptr() for x in gviews]
+        ld = lambda p: p.stride(0) if p.dim() == 2 else p.numel()
+        self.t_params = segs(lambda i: (params[i].data_ptr(), ld(params[i])), dense_ptrs)
+        self.t_grads_stage = segs(lambda i: (self.stage_views[i].data_ptr(), ld(self.stage_views[i])), grad_ptrs)
+        if all(p.grad is not None for p in params):
+            self.t_grads_direct = segs(lambda i: (params[i].grad.data_ptr(), ld(params[i].grad)), grad_ptrs)
+        else:
+            self.t_grads_direct = None
+        if self.bn is not None and self.bn.running_mean is not None:
+            rows = []
+            for t, b in enumerate(bns):
+                rows.append((b.running_mean.data_ptr(), rm.data_ptr() + 4 * t * Fo, 1, Fo, Fo, FO))
+                rows.append((b.running_var.data_ptr(), rv.data_ptr() + 4 * t * Fo, 1, Fo, Fo, FO))
+            self.t_running = torch.from_numpy(np.array(rows, dtype=_SEG).view(np.uint8).copy()).to(dev)
+        else:
+            self.t_running = torch.zeros(0, dtype=torch.uint8, device=dev)
+        self._key = key
+
+    # ---- the layer ------------------------------------------------------------------------------------------------
+    def forward(self, g, h, snorm_n):
+        L = self.layer
+        t0 = L.towers[0]
+        eig = t0._eig(g, h)
+        snorm = None
+        if t0.graph_norm and snorm_n is not None:
+            snorm = snorm_n.reshape(-1)
+            if snorm.dtype != torch.float32 or not snorm.is_contiguous():
+                snorm = snorm.float().contiguous()
+        params = self.tower_params()
+        return _TowerFused.apply(self, g, ops._f32c(eig), snorm, t0.training, h, *params)

@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define DGN_ABI_VERSION 10
+#define DGN_ABI_VERSION 11
 #define DGN_MAX_AGG 32      /* aggregators per layer (the reference registry has 24)        */
 #define DGN_MAX_SCALERS 4   /* scalers per layer (the reference registry has 3)             */
 #define DGN_MAX_SLOTS 8     /* distinct eigen-weighted feature sums one launch can carry    */
@@ -443,6 +443,13 @@ typedef struct {
 /* ids: DEVICE int32 [n_ids] graph indices in batch order.  Returns DGN_ERR_INVALID for bad arguments; a batch that
  * exceeds the capacities is truncated on the device and flagged in meta[3] = 1 (callers check it lazily). */
 int dgn_collate_device(const DgnDataset* ds, const int32_t* ids, int32_t n_ids, const DgnBatchOut* out, void* stream);
+
+/* One launch that copies n_segments rectangular fp32 blocks between two sets of tensors, described by a DEVICE table of
+ *   struct { float* a; float* b; int32_t rows, cols, ld_a, ld_b; }           (32 bytes per entry)
+ * direction 0: b = a; 1: a = b; 2: a += b.  Used to pack the per-tower parameters of DGNLayerTower
+ * (rb/nets/dgn_layer.py:279-307) into the dense block-structured operands of the single-launch tower path and to scatter
+ * the gradients / running statistics back. */
+int dgn_segment_copy(const void* seg_table, int32_t n_segments, int32_t direction, void* stream);
 
 /* Laplacian eigenvectors of every graph on the device: the per-graph host loop of the reference's loaders
  * (scipy.sparse.linalg.eigs on L, rb/data/molecules.py:100-116, rb/data/SBMs.py:110-139, rb/data/HIV.py:17-46).

@@ -175,3 +175,45 @@ def test_cross_layer_fusion_hands_over_pretrans_halves():
             for n, q in r.named_parameters():
                 assert_close(grads["%d.%s" % (m_i, n)], q.grad, rel=2e-5, what="%d.%s" % (m_i, n))
     assert torch.equal(runs[1][0], runs[2][0]) and torch.equal(runs[1][1], runs[2][1])
+
+
+@pytest.mark.parametrize("towers,F,bn", [(4, 80, True), (5, 20, True), (2, 16, False)])
+def test_single_launch_towers_equal_tower_loop(towers, F, bn):
+    """DGNLayerTower as ONE block-structured fused layer (dgn_b200/towers.py) vs the per-tower loop of the reference
+    (rb/nets/dgn_layer.py:309-325): outputs, input / parameter gradients, BatchNorm running statistics."""
+    from dgn_b200 import ops
+    from dgn_b200.data.synthetic import make_samples, avg_log_degree
+    samples = make_samples("molhiv", 12, seed=21)
+    avg = avg_log_degree(samples)
+    args = (F, F, 0.0, True, bn, "mean max min dir1-dx dir2-dx dir1-av dir2-av", "identity", {"log": torch.tensor(avg)},
+            "towers", True)
+    g, _ = collate(samples)
+    g.to(DEV)
+    torch.manual_seed(5)
+    h = torch.randn(g.number_of_nodes(), F, device=DEV)
+    gy = torch.randn(g.number_of_nodes(), F, device=DEV)
+    res = []
+    for fused in (True, False):
+        ops.FOLD_ENABLED = fused                       # the tower fusion is part of the folded path
+        try:
+            torch.manual_seed(41)
+            layer = DGNLayer(*args, towers=towers, edge_features=False, edge_dim=0).model.to(DEV).train()
+            before = ops.LAUNCHES
+            for _ in range(2):                          # twice: running statistics accumulate, buffers are reused
+                layer.zero_grad(set_to_none=True)
+                hh = h.clone().requires_grad_(True)
+                y = layer(g, hh, None, g.snorm_n)
+                y.backward(gy)
+            res.append((y.detach(), hh.grad, {k: p.grad.clone() for k, p in layer.named_parameters() if p.grad is not None},
+                        {k: b.clone() for k, b in layer.named_buffers()}, ops.LAUNCHES - before))
+        finally:
+            ops.FOLD_ENABLED = True
+    (y1, d1, p1, b1, n1), (y0, d0, p0, b0, n0) = res
+    assert n1 < n0 / 2, "single-launch towers should need far fewer launches (%d vs %d)" % (n1, n0)
+    assert_close(y1, y0, what="y")
+    assert_close(d1, d0, what="d_h")
+    assert sorted(p0) == sorted(p1)
+    for k in p0:
+        assert_close(p1[k], p0[k], rel=2e-5, what=k)
+    for k in b0:
+        assert_close(b1[k].float(), b0[k].float(), what=k)
