@@ -262,10 +262,10 @@ __global__ void __launch_bounds__(kTX * kTY) norm_bwd_apply_kernel(const DgnNorm
       s_b[threadIdx.x] = (float)(acc[0] * inv_n);      // mean of g1
       s_g[threadIdx.x] = (float)(acc[1] * inv_n);      // mean of g1 * xhat
       if (blockIdx.x == 0) {
-        const float keep = g.accumulate ? 1.f : 0.f;
+        // (select, not 0 * old: the destination of a non-accumulating call is uninitialised memory, possibly NaN)
         if (a.gamma) {
-          if (g.d_beta) g.d_beta[col] = keep * g.d_beta[col] + (float)acc[0];
-          if (g.d_gamma) g.d_gamma[col] = keep * g.d_gamma[col] + (float)acc[1];
+          if (g.d_beta) g.d_beta[col] = (g.accumulate ? g.d_beta[col] : 0.f) + (float)acc[0];
+          if (g.d_gamma) g.d_gamma[col] = (g.accumulate ? g.d_gamma[col] : 0.f) + (float)acc[1];
         }
         if (g.d_bias) {
           // d_bias = sum_r d_y[r] with d_y = s * ga*rstd*(g1 - mb - xhat*mg) (training BN), s*ga*rstd*g1 (eval), s*g1 (no BN)
@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(kTX * kTY) norm_bwd_apply_kernel(const DgnNorm
             if (a.training) db = acc[2] - (acc[0] * inv_n) * acc[3] - (acc[1] * inv_n) * acc[4];
             db *= (double)a.gamma[col] * (double)a.stats[a.n_cols + col];
           }
-          g.d_bias[col] = keep * g.d_bias[col] + (float)db;
+          g.d_bias[col] = (g.accumulate ? g.d_bias[col] : 0.f) + (float)db;
         }
       }
     }

@@ -154,9 +154,11 @@ WELL_CONDITIONED = [a for a in FULL if a != "std"]
     ("zinc", 128, 64, WELL_CONDITIONED, 6),                                               # BASELINE cfg2 (std: below)
     ("cifar", 128, 65, ["mean", "dir1-dx", "dir2-dx"], 3),                                # cfg3 (unaligned F)
     ("pattern", 24, 48, ["mean", "dir1-dx", "dir2-dx", "dir3-dx", "dir4-dx"], 5),         # cfg5 (reduced batch)
+    ("pattern", 128, 48, ["mean", "dir1-dx", "dir2-dx", "dir3-dx", "dir4-dx"], 5),        # cfg5, 128 graphs (~0.9 M edges)
+    ("molhiv", 512, 80, ["mean", "max", "min", "dir1-dx", "dir2-dx", "dir1-av", "dir2-av"], 4),   # cfg4 width, b=512
 ])
 def test_baseline_shapes_match_oracle(kind, ng, F, aggs, K):
-    scs = ["identity"] if kind == "cifar" else S3
+    scs = ["identity"] if kind in ("cifar", "molhiv") else S3
     g, samples, eig, h, P, Q, R, avg = _graph_case(kind, ng, 5, F, K)
     N = g.number_of_nodes()
     src, dst = g.host("src").astype(np.int64), g.host("dst").astype(np.int64)
