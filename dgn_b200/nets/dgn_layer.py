@@ -95,6 +95,15 @@ class _FusedConv(nn.Module):
         pre = self._affine(self.pretrans) if hasattr(self, "pretrans") else None
         if post is None or (hasattr(self, "pretrans") and pre is None) or not h.is_cuda:
             return None
+        if pre is not None and (self.in_dim % 4 or post.out_features % 4) and not getattr(self, "_in_padded", False):
+            # widths off the 16 B grid (the reference's 45 / 47 / 65 ...): layer-owned zero-padded operands
+            pad = self.__dict__.get("_padded")
+            if pad is None:
+                from dgn_b200.towers import TowerFusion
+                pad = self.__dict__["_padded"] = TowerFusion([self], self.in_dim, post.out_features, relu=relu,
+                                                             residual=residual)
+            if pad.supported(h):
+                return pad.forward(g, h, snorm_n)
         eig = self._eig(g, h)
         R = None
         if pre is not None and self.edge_features:
@@ -249,8 +258,8 @@ class DGNLayerTower(nn.Module):
         fusion = self.__dict__.get("_fusion")
         if fusion is None:
             from dgn_b200.towers import TowerFusion
-            fusion = self.__dict__["_fusion"] = TowerFusion(self)      # kept out of the module's parameters / state_dict
-        if fusion.supported(h):
+            fusion = self.__dict__["_fusion"] = TowerFusion(self.towers, self.input_tower, self.output_tower)
+        if len(self.towers) > 1 and self.divide_input and fusion.supported(h):
             # all towers as ONE block-structured layer: one aggregation launch, one posttrans GEMM, one epilogue
             y = fusion.forward(g, h, snorm_n)
         elif self.divide_input:

@@ -1,4 +1,7 @@
-"""Single-launch tower layer: all T towers of a ``DGNLayerTower`` in ONE fused layer call.
+"""Single-launch tower layer: all T towers of a ``DGNLayerTower`` in ONE fused layer call - and, with T = 1, the padded
+fast path for layer widths that are not multiples of 4 floats (the reference's own configs use 45 / 47 / 65 / 70:
+rb/configs/*.json): the layer OWNS zero-padded operands (45 -> 48 columns) so that every row is 16 B aligned, the
+128-bit row kernels and the tcgen05 GEMMs are taken, and the padding columns stay exactly zero through the layer.
 
 The reference runs its towers one after the other (rb/nets/dgn_layer.py:309-325): T x (pretrans -> update_all -> posttrans ->
 graph norm -> BatchNorm).  Every aggregator is column-wise independent and BatchNorm is per column, so the T towers over
@@ -49,7 +52,7 @@ class _TowerFused(torch.autograd.Function):
         if has_bn:
             _launch(f.t_running, 0, dev)                          # running statistics -> concatenated buffers
         direct = ops.DIRECT_GRADS and all(p.grad is not None for p in tower_params)
-        cfg = LayerConfig(g, f.spec(eig.shape[1]), eig, snorm, f.bn, training, False, False, True, f.F, True,
+        cfg = LayerConfig(g, f.spec(eig.shape[1]), eig, snorm, f.bn, training, f.relu, f.residual, True, f.F, True,
                           (f.W_pre, f.b_pre, f.W_post, f.b_post, f.gamma if has_bn else None, f.beta if has_bn else None),
                           *f.folded(eig.shape[1]))
         inner = _Ctx()
@@ -86,30 +89,35 @@ class _TowerFused(torch.autograd.Function):
 class TowerFusion:
     """Packing state of one ``DGNLayerTower`` (built lazily on the first fused call)."""
 
-    def __init__(self, layer):
-        self.layer = layer
+    def __init__(self, convs, in_width, out_width, relu=False, residual=False):
+        """``convs``: the T conv modules (``DGNTower``s, or one ``DGNLayerComplex``) of per-tower widths
+        ``in_width -> out_width``; ``relu`` / ``residual``: the epilogue of the fused layer (towers have neither)."""
+        self.convs = list(convs)
+        self.Ft, self.Fo_t = int(in_width), int(out_width)
+        self.Ftp, self.Fop = (self.Ft + 3) // 4 * 4, (self.Fo_t + 3) // 4 * 4        # layer-owned padded widths
+        self.relu, self.residual = bool(relu), bool(residual)
         self._key = None
         self._specs = {}
 
     # ---- eligibility -------------------------------------------------------------------------------------------
     def supported(self, h) -> bool:
-        L = self.layer
-        if not (ops.FOLD_ENABLED and h.is_cuda and len(L.towers) > 1 and L.divide_input and not L.edge_features):
+        t0 = self.convs[0]
+        if not (ops.FOLD_ENABLED and h.is_cuda and not getattr(t0, "edge_features", False)):
             return False
-        t0 = L.towers[0]
         if t0.dropout and t0.training:
             return False
-        for tw in L.towers:
-            if tw._affine(tw.pretrans) is None or tw._affine(tw.posttrans) is None:
+        for tw in self.convs:
+            if not hasattr(tw, "pretrans") or tw._affine(tw.pretrans) is None or tw._affine(tw.posttrans) is None:
                 return False
-        Ft, Fo = L.input_tower, L.output_tower
-        return Ft % 4 == 0 and Fo % 4 == 0 and (Ft * len(L.towers)) <= 512
+        if self.residual and self.Ftp != self.Fop:
+            return False
+        return self.Ftp * len(self.convs) <= 512 and self.Fop * len(self.convs) <= 512
 
     # ---- specs ---------------------------------------------------------------------------------------------------
     def spec(self, n_eig):
         sp = self._specs.get(n_eig)
         if sp is None:
-            t0 = self.layer.towers[0]
+            t0 = self.convs[0]
             sp = ops.AggSpec(t0.aggregators, t0.scalers, float(t0._spec(n_eig).avg_log), self.F, n_eig)
             self._specs[n_eig] = sp
         return sp
@@ -130,12 +138,11 @@ class TowerFusion:
 
     # ---- dense operands and segment tables ----------------------------------------------------------------------
     def _tower_tensors(self):
-        L = self.layer
-        pre = [tw._affine(tw.pretrans) for tw in L.towers]
-        post = [tw._affine(tw.posttrans) for tw in L.towers]
-        bns = [tw.batchnorm_h for tw in L.towers] if L.towers[0].batch_norm else None
+        pre = [tw._affine(tw.pretrans) for tw in self.convs]
+        post = [tw._affine(tw.posttrans) for tw in self.convs]
+        bns = [tw.batchnorm_h for tw in self.convs] if self.convs[0].batch_norm else None
         params = []
-        for t in range(len(L.towers)):
+        for t in range(len(self.convs)):
             params += [pre[t].weight, pre[t].bias, post[t].weight, post[t].bias]
             if bns is not None:
                 params += [bns[t].weight, bns[t].bias]
@@ -145,15 +152,15 @@ class TowerFusion:
         return self._tower_tensors()[3]
 
     def prepare(self, dev):
-        L = self.layer
         pre, post, bns, params = self._tower_tensors()
         key = (str(dev),) + tuple(p.data_ptr() for p in params) + tuple(
             (p.grad.data_ptr() if p.grad is not None else 0) for p in params) + (
             tuple(b.running_mean.data_ptr() for b in bns) if bns is not None and bns[0].running_mean is not None else ())
         if key == self._key:
             return
-        T, Ft, Fo = len(L.towers), L.input_tower, L.output_tower
-        self.F, self.Fo = T * Ft, T * Fo
+        T, Ft, Fo = len(self.convs), self.Ft, self.Fo_t            # real per-tower widths
+        Fp, Fq = self.Ftp, self.Fop                                # padded per-tower widths (multiples of 4)
+        self.F, self.Fo = T * Fp, T * Fq
         F, FO = self.F, self.Fo
         blocks = post[0].weight.shape[1] // Ft                    # 1 + S * A
         n_pre, n_post = F * 2 * F, FO * blocks * F
@@ -195,16 +202,16 @@ class TowerFusion:
                 a = [get_a(t * per + i) for i in range(per)]        # (ptr, ld) of W_pre, b_pre, W_post, b_post[, gamma, beta]
                 wp, bp, wq, bq = a[0], a[1], a[2], a[3]
                 for half in range(2):                                 # [src | dst] halves of the block-diagonal pretrans
-                    rows.append((wp[0] + 4 * half * Ft, dense_ptr[0] + 4 * ((t * Ft) * 2 * F + half * F + t * Ft), Ft, Ft,
+                    rows.append((wp[0] + 4 * half * Ft, dense_ptr[0] + 4 * ((t * Fp) * 2 * F + half * F + t * Fp), Ft, Ft,
                                  wp[1], 2 * F))
-                rows.append((bp[0], dense_ptr[1] + 4 * t * Ft, 1, Ft, Ft, F))
+                rows.append((bp[0], dense_ptr[1] + 4 * t * Fp, 1, Ft, Ft, F))
                 for j in range(blocks):                               # h block and every aggregate block
-                    rows.append((wq[0] + 4 * j * Ft, dense_ptr[2] + 4 * ((t * Fo) * blocks * F + j * F + t * Ft), Fo, Ft,
+                    rows.append((wq[0] + 4 * j * Ft, dense_ptr[2] + 4 * ((t * Fq) * blocks * F + j * F + t * Fp), Fo, Ft,
                                  wq[1], blocks * F))
-                rows.append((bq[0], dense_ptr[3] + 4 * t * Fo, 1, Fo, Fo, FO))
+                rows.append((bq[0], dense_ptr[3] + 4 * t * Fq, 1, Fo, Fo, FO))
                 if bns is not None:
-                    rows.append((a[4][0], dense_ptr[4] + 4 * t * Fo, 1, Fo, Fo, FO))
-                    rows.append((a[5][0], dense_ptr[5] + 4 * t * Fo, 1, Fo, Fo, FO))
+                    rows.append((a[4][0], dense_ptr[4] + 4 * t * Fq, 1, Fo, Fo, FO))
+                    rows.append((a[5][0], dense_ptr[5] + 4 * t * Fq, 1, Fo, Fo, FO))
             arr = np.array(rows, dtype=_SEG)
             return torch.from_numpy(arr.view(np.uint8).copy()).to(dev)
 
@@ -220,8 +227,8 @@ class TowerFusion:
         if self.bn is not None and self.bn.running_mean is not None:
             rows = []
             for t, b in enumerate(bns):
-                rows.append((b.running_mean.data_ptr(), rm.data_ptr() + 4 * t * Fo, 1, Fo, Fo, FO))
-                rows.append((b.running_var.data_ptr(), rv.data_ptr() + 4 * t * Fo, 1, Fo, Fo, FO))
+                rows.append((b.running_mean.data_ptr(), rm.data_ptr() + 4 * t * Fq, 1, Fo, Fo, FO))
+                rows.append((b.running_var.data_ptr(), rv.data_ptr() + 4 * t * Fq, 1, Fo, Fo, FO))
             self.t_running = torch.from_numpy(np.array(rows, dtype=_SEG).view(np.uint8).copy()).to(dev)
         else:
             self.t_running = torch.zeros(0, dtype=torch.uint8, device=dev)
@@ -229,8 +236,17 @@ class TowerFusion:
 
     # ---- the layer ------------------------------------------------------------------------------------------------
     def forward(self, g, h, snorm_n):
-        L = self.layer
-        t0 = L.towers[0]
+        t0 = self.convs[0]
+        T, N = len(self.convs), h.shape[0]
+        if self.Ftp != self.Ft:                                    # zero-pad every tower's column slice (45 -> 48)
+            h = torch.nn.functional.pad(h.reshape(N, T, self.Ft), (0, self.Ftp - self.Ft)).reshape(N, T * self.Ftp)
+        out = self._forward_padded(g, h, snorm_n)
+        if self.Fop != self.Fo_t:
+            out = out.reshape(N, T, self.Fop)[:, :, :self.Fo_t].reshape(N, T * self.Fo_t)
+        return out
+
+    def _forward_padded(self, g, h, snorm_n):
+        t0 = self.convs[0]
         eig = t0._eig(g, h)
         snorm = None
         if t0.graph_norm and snorm_n is not None:

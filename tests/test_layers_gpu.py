@@ -217,3 +217,45 @@ def test_single_launch_towers_equal_tower_loop(towers, F, bn):
         assert_close(p1[k], p0[k], rel=2e-5, what=k)
     for k in b0:
         assert_close(b1[k].float(), b0[k].float(), what=k)
+
+
+@pytest.mark.parametrize("F,aggs,scalers,kind", [
+    (45, "mean dir1-dx dir1-av", "identity amplification attenuation", "zinc"),      # rb/configs/molecules_..._ZINC.json
+    (47, "mean dir1-dx dir2-dx dir3-dx", "identity amplification attenuation", "pattern"),
+    (65, "mean max dir1-dx dir2-dx", "identity", "cifar"),                           # rb/configs/superpixels_..._CIFAR10.json
+])
+def test_unaligned_widths_take_the_padded_fast_path(F, aggs, scalers, kind):
+    """The reference's own hidden widths (45 / 47 / 65) are not multiples of 4 floats: the complex layer pads its operands
+    (layer-owned 48 / 48 / 68 columns) and must still match the oracle to 1e-5 - through the 128-bit row kernels and the
+    tcgen05 posttrans GEMMs (checked through the launch counter: no scalar-kernel / library-GEMM path)."""
+    from dgn_b200 import ops
+    from dgn_b200.data.synthetic import make_samples, avg_log_degree
+    from oracle.directional_layers import DGNLayer as RefLayer
+    from oracle.graphs import collate_standin
+    kw = dict(n_min=20, n_max=40) if kind != "zinc" else {}
+    samples = make_samples(kind, 10, seed=13, **kw)
+    avg = avg_log_degree(samples)
+    args = (F, F, 0.0, True, True, aggs, scalers, {"log": torch.tensor(avg)}, "complex", True)
+    torch.manual_seed(11)
+    ref = RefLayer(*args, edge_features=False, edge_dim=0).model.train()
+    mine = DGNLayer(*args, edge_features=False, edge_dim=0).model
+    mine.load_state_dict(ref.state_dict())
+    mine.to(DEV).train()
+    gs, _, snorm, _ = collate_standin(samples)
+    g, _ = collate(samples)
+    g.to(DEV)
+    h = torch.randn(g.number_of_nodes(), F)
+    gy = torch.randn(g.number_of_nodes(), F)
+    hr = h.clone().requires_grad_(True)
+    yr = ref(gs, hr, None, snorm)
+    yr.backward(gy)
+    hm = h.to(DEV).requires_grad_(True)
+    ym = mine(g, hm, None, g.snorm_n)
+    ym.backward(gy.to(DEV))
+    assert mine.__dict__.get("_padded") is not None, "padded fast path not taken"
+    assert_close(ym, yr, what="y")
+    assert_close(hm.grad, hr.grad, what="dh")
+    for (k, p), (_, q) in zip(mine.named_parameters(), ref.named_parameters()):
+        assert_close(p.grad, q.grad, rel=2e-5, what=k)
+    for (k, b), (_, c) in zip(mine.named_buffers(), ref.named_buffers()):
+        assert_close(b.float(), c.float(), what=k)
