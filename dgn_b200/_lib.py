@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DGN_LIB_PATH") or os.path.join(_HERE, "libdgn_b200.so")
 
 MAX_AGG, MAX_SCALERS, MAX_SLOTS = 32, 4, 8
-ABI_VERSION = 11
+ABI_VERSION = 12
 NORM_WS_PER_COL = 640
 
 # DgnAggKind / DgnScalerKind / DgnMsgMode
@@ -29,7 +29,8 @@ _f32p = C.POINTER(C.c_float)
 
 class DgnGraph(C.Structure):
     _fields_ = [("n_nodes", C.c_int32), ("n_edges", C.c_int32), ("in_ptr", C.c_void_p), ("in_src", C.c_void_p),
-                ("in_eid", C.c_void_p), ("out_ptr", C.c_void_p), ("out_slot", C.c_void_p), ("log_deg", C.c_void_p)]
+                ("in_eid", C.c_void_p), ("out_ptr", C.c_void_p), ("out_slot", C.c_void_p), ("log_deg", C.c_void_p),
+                ("graph_ptr", C.c_void_p), ("n_graphs", C.c_int32), ("max_graph_nodes", C.c_int32)]
 
 
 class DgnAggSpec(C.Structure):

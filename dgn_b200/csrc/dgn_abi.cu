@@ -81,6 +81,7 @@ static int fill_args(const DgnGraph* g, const DgnAggSpec* spec, const DgnAggIO* 
   k.N = g->n_nodes; k.E = g->n_edges; k.mode = io->msg_mode;
   k.in_ptr = g->in_ptr; k.in_src = g->in_src; k.in_eid = g->in_eid;
   k.out_ptr = g->out_ptr; k.out_slot = g->out_slot; k.log_deg = g->log_deg;
+  k.graph_ptr = g->graph_ptr; k.n_graphs = g->graph_ptr ? g->n_graphs : 0; k.max_graph_nodes = g->max_graph_nodes;
   if (P.S > 1 && !g->log_deg) return DGN_ERR_INVALID;
   k.x = io->x; k.ld_x = io->ld_x; k.q = io->q; k.ld_q = io->ld_q; k.r = io->r; k.ld_r = io->ld_r;
   k.q_bias = (io->msg_mode == DGN_MSG_AFFINE) ? io->q_bias : nullptr;

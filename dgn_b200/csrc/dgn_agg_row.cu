@@ -95,7 +95,29 @@ struct RowArgs {
   float* d_h; int ld_dh;
   const float* d_h_add; int ld_dha;
   float* edge_ws;
+  const int32_t* graph_ptr; int n_graphs; int tile_rows;   // tile kernels: node range per graph, rows of the smem tile
+  int tile_split;                                          // CTAs per graph (each stages the block, takes 1 / split of the nodes)
+  long long n_edges;
 };
+
+// Where a thread finds the source rows X[u] it gathers: global memory, or the shared-memory copy of its graph's node
+// block (tile kernels: every in-edge of a node comes from the node's own graph - the batched adjacency is block diagonal).
+struct RowSrc {
+  const float* base;       // row u at base + (u - first) * ld
+  int ld, first;
+  bool smem;
+};
+template <int VEC> __device__ __forceinline__ Vec<VEC> row_load(const RowSrc& s, int u, int c) {
+  if (s.smem) {
+    const float* p = s.base + (u >= 0 ? u - s.first : 0) * s.ld + c;
+    Vec<VEC> r;
+    if constexpr (VEC == 4) { const float4 t = *reinterpret_cast<const float4*>(p); r.a[0] = t.x; r.a[1] = t.y; r.a[2] = t.z; r.a[3] = t.w; }
+    else if constexpr (VEC == 2) { const float2 t = *reinterpret_cast<const float2*>(p); r.a[0] = t.x; r.a[1] = t.y; }
+    else { r.a[0] = p[0]; }
+    return r;
+  }
+  return vload<VEC>(s.base + (size_t)max(u, 0) * s.ld + c);
+}
 
 // slot with these weights whose op `op` is still free (a repeated aggregator opens a new slot with equal weights)
 static int field_slot(FieldPlan& f, int eig, int kind, float alpha, int op, unsigned (&used)[DGN_MAX_SLOTS]) {
@@ -271,8 +293,8 @@ __device__ __forceinline__ float div_by(float x, float fD, float rD) {
 // The message mode is a launch-uniform runtime branch: SOURCE is AFFINE with q = 0 (qv stays zero), DENSE reads R[eid].
 // WIDE: all 4 gathers of a group in flight at once (latency-optimised variant for single-wave launches).
 template <int VEC, int NS, bool WIDE, typename Fn>
-__device__ __forceinline__ void walk_groups(const RowArgs& k, int v, int c, const Vec<VEC>& qv, int e0, int ovf0, int ovf1,
-                                            Fn&& fn) {
+__device__ __forceinline__ void walk_groups(const RowArgs& k, const RowSrc& xs, int v, int c, const Vec<VEC>& qv, int e0,
+                                            int ovf0, int ovf1, Fn&& fn) {
   constexpr int NSA = NS > 0 ? NS : 1;
   const bool dense = k.mode == DGN_MSG_DENSE;
   const bool edge_term = !dense && k.r != nullptr;
@@ -293,7 +315,7 @@ __device__ __forceinline__ void walk_groups(const RowArgs& k, int v, int c, cons
           if (k.in_eid && u >= 0) id = __ldg(k.in_eid + id);
           m[j] = vload<VEC>(k.r + (size_t)(u >= 0 ? id : 0) * k.ld_r + c);
         } else {
-          m[j] = vload<VEC>(k.x + (size_t)max(u, 0) * k.ld_x + c);
+          m[j] = row_load<VEC>(xs, u, c);
         }
       }
 #pragma unroll
@@ -335,7 +357,7 @@ __device__ __forceinline__ void walk_groups(const RowArgs& k, int v, int c, cons
           if (k.in_eid && u >= 0) id = __ldg(k.in_eid + id);
           m[j] = vload<VEC>(k.r + (size_t)(u >= 0 ? id : 0) * k.ld_r + c);
         } else {
-          m[j] = vload<VEC>(k.x + (size_t)max(u, 0) * k.ld_x + c);
+          m[j] = row_load<VEC>(xs, u, c);
         }
       }
 #pragma unroll
@@ -361,6 +383,63 @@ __device__ __forceinline__ void walk_groups(const RowArgs& k, int v, int c, cons
     }
     if (o >= ovf1) break;
     g = k.N + o;
+    ++o;
+    jbase += 4;
+  }
+}
+
+// Tile-kernel walk: all 4 gathers of a group at once (they are shared-memory reads) and the NEXT group's sources and
+// weights requested before the current group is consumed - at D ~ 51 a node walks 13 groups, and a dependent
+// group-load -> gather chain per group (one L2 round trip each) was what bounded the row kernels there.
+template <int VEC, int NS, typename Fn>
+__device__ __forceinline__ void walk_groups_pf(const RowArgs& k, const RowSrc& xs, int v, int c, const Vec<VEC>& qv, int e0,
+                                               int ovf0, int ovf1, Fn&& fn) {
+  constexpr int NSA = NS > 0 ? NS : 1;
+  const bool edge_term = k.r != nullptr;
+  int o = ovf0, jbase = 0;
+  const float4* gp = k.groups + (size_t)v * k.gstride;
+  int4 su4 = __ldg(reinterpret_cast<const int4*>(gp));
+  float4 wv[NSA];
+#pragma unroll
+  for (int s = 0; s < NS; ++s) wv[s] = (s < k.rp.n_slots) ? __ldg(gp + 1 + s) : make_float4(0.f, 0.f, 0.f, 0.f);
+  while (true) {
+    const bool more = o < ovf1;
+    int4 su4n = su4;
+    float4 wvn[NSA];
+#pragma unroll
+    for (int s = 0; s < NSA; ++s) wvn[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (more) {
+      const float4* gn = k.groups + (size_t)(k.N + o) * k.gstride;
+      su4n = __ldg(reinterpret_cast<const int4*>(gn));
+#pragma unroll
+      for (int s = 0; s < NS; ++s) if (s < k.rp.n_slots) wvn[s] = __ldg(gn + 1 + s);
+    }
+    Vec<VEC> m[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) m[j] = row_load<VEC>(xs, lane_of(su4, j), c);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (lane_of(su4, j) >= 0) {
+        Vec<VEC> mm = m[j];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) mm.a[i] += qv.a[i];
+        if (edge_term) {
+          const int e = e0 + jbase + j;
+          const int id = k.in_eid ? __ldg(k.in_eid + e) : e;
+          const Vec<VEC> rv = vload<VEC>(k.r + (size_t)id * k.ld_r + c);
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) mm.a[i] += rv.a[i];
+        }
+        float wj[NSA];
+#pragma unroll
+        for (int s = 0; s < NSA; ++s) wj[s] = lane_of(wv[s], j);
+        fn(jbase + j, mm, wj);
+      }
+    }
+    if (!more) break;
+    su4 = su4n;
+#pragma unroll
+    for (int s = 0; s < NSA; ++s) wv[s] = wvn[s];
     ++o;
     jbase += 4;
   }
@@ -512,15 +591,12 @@ __device__ __forceinline__ void fwd_epilogue(const RowPlan& P, const Acc<VEC, NS
   }
 }
 
+// One (node, column chunk) work item of the forward.
 // LAT = latency-optimised variant for launches that fit in one wave: wide gathers, no register cap.
-template <int VEC, int NS, bool ISO, bool LAT>
-__global__ void __launch_bounds__(ROW_THREADS, LAT ? 4 : ROW_MINB_FWD) agg_fwd_row_kernel(const __grid_constant__ RowArgs k) {
-  pdl_prologue();
+template <int VEC, int NS, bool ISO, bool LAT, bool TILE = false>
+__device__ __forceinline__ void fwd_node(const RowArgs& k, const RowSrc& xs, int v, int c) {
   constexpr int NSA = NS > 0 ? NS : 1;
   const RowPlan& P = k.rp;
-  const int v = blockIdx.x * blockDim.y + threadIdx.y;
-  if (v >= k.N) return;
-  const int c = threadIdx.x * VEC;
   int tower = 0, cg = c;
   if (P.Fg != P.F) { tower = c / P.Fg; cg = c - tower * P.Fg; }
 
@@ -545,10 +621,12 @@ __global__ void __launch_bounds__(ROW_THREADS, LAT ? 4 : ROW_MINB_FWD) agg_fwd_r
   Acc<VEC, NS, ISO> R;
   acc_clear(R);
   int D = 0;
-  walk_groups<VEC, NS, LAT>(k, v, c, qv, e0, ovf0, ovf1, [&](int, const Vec<VEC>& m, const float* wj) {
+  auto add = [&](int, const Vec<VEC>& m, const float* wj) {
     ++D;
     acc_add<VEC, NS, ISO>(R, m, wj);
-  });
+  };
+  if constexpr (TILE) walk_groups_pf<VEC, NS>(k, xs, v, c, qv, e0, ovf0, ovf1, add);
+  else walk_groups<VEC, NS, LAT>(k, xs, v, c, qv, e0, ovf0, ovf1, add);
 
   float* orow = k.out + (size_t)v * k.ld_out + (size_t)tower * k.out_gs + cg;
   if (D == 0) {                                        // DGL: zero rows for isolated nodes
@@ -559,6 +637,60 @@ __global__ void __launch_bounds__(ROW_THREADS, LAT ? 4 : ROW_MINB_FWD) agg_fwd_r
   if (P.S == 3) fwd_epilogue<VEC, NS, ISO, 3>(P, R, hv, wsumv, D, ld, orow);
   else if (P.S == 1) fwd_epilogue<VEC, NS, ISO, 1>(P, R, hv, wsumv, D, ld, orow);
   else fwd_epilogue<VEC, NS, ISO, 0>(P, R, hv, wsumv, D, ld, orow);
+}
+
+template <int VEC, int NS, bool ISO, bool LAT>
+__global__ void __launch_bounds__(ROW_THREADS, LAT ? 4 : ROW_MINB_FWD) agg_fwd_row_kernel(const __grid_constant__ RowArgs k) {
+  pdl_prologue();
+  const int v = blockIdx.x * blockDim.y + threadIdx.y;
+  if (v >= k.N) return;
+  const RowSrc xs{k.x, k.ld_x, 0, false};
+  fwd_node<VEC, NS, ISO, LAT>(k, xs, v, threadIdx.x * VEC);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// tile kernels (high-degree graphs: superpixel kNN, SBM PATTERN): one CTA per graph.  A (node, chunk) thread of the row
+// kernels gathers D source rows from L2 - at D ~ 51 that is E*F*4 bytes of L2 -> SM traffic per launch (2.8x the
+// algorithmic bytes on PATTERN) and the launch is L2-gather bound.  The batched adjacency is block diagonal, so all
+// sources of a graph's nodes are that graph's own node block: the CTA copies the block [n_g, F] (<= ~36 KB) into
+// shared memory ONCE with coalesced 128-bit loads and every gather becomes a shared-memory read.
+// ------------------------------------------------------------------------------------------------------
+#ifndef TILE_THREADS
+#define TILE_THREADS 256
+#endif
+
+__device__ __forceinline__ RowSrc stage_graph_rows(const RowArgs& k, float* tile, int v0, int v1) {
+  const int n = v1 - v0, F = k.rp.F;
+  if (k.mode == DGN_MSG_DENSE || n > k.tile_rows || (F & 3) || (k.ld_x & 3)) return RowSrc{k.x, k.ld_x, 0, false};
+  const int q4 = F >> 2, tid = threadIdx.y * blockDim.x + threadIdx.x, nt = blockDim.x * blockDim.y;
+  for (int i = tid; i < n * q4; i += nt) {
+    const int r = i / q4, cc = (i - r * q4) * 4;
+    *reinterpret_cast<float4*>(tile + r * F + cc) = __ldg(reinterpret_cast<const float4*>(k.x + (size_t)(v0 + r) * k.ld_x + cc));
+  }
+  __syncthreads();
+  return RowSrc{tile, F, v0, true};
+}
+
+template <int VEC, int NS, bool ISO>
+__global__ void __launch_bounds__(TILE_THREADS, 2) agg_fwd_tile_kernel(const __grid_constant__ RowArgs k) {
+  pdl_prologue();
+  extern __shared__ __align__(16) float tile[];
+  // tile_split CTAs share a graph: each stages the graph's block and takes one slice of its nodes (enough CTAs to keep
+  // the SMs' warp slots full; the redundant staging reads are N*F*4*split bytes of L2 traffic, still far below E*F*4).
+  // The last CTA takes the padding rows behind the last graph (no in-edges: zero rows).
+  const int g = blockIdx.x / k.tile_split, part = blockIdx.x - g * k.tile_split;
+  const int v0 = g < k.n_graphs ? __ldg(k.graph_ptr + g) : __ldg(k.graph_ptr + k.n_graphs);
+  const int v1 = g < k.n_graphs ? __ldg(k.graph_ptr + g + 1) : k.N;
+  if (v1 <= v0 || (g >= k.n_graphs && part > 0)) return;
+  const int per = g < k.n_graphs ? (v1 - v0 + k.tile_split - 1) / k.tile_split : v1 - v0;
+  const int a0 = v0 + part * per, a1 = min(a0 + per, v1);
+  if (a1 <= a0) return;
+  const RowSrc xs = g < k.n_graphs ? stage_graph_rows(k, tile, v0, v1) : RowSrc{k.x, k.ld_x, 0, false};
+  if (xs.smem) {
+    for (int v = a0 + threadIdx.y; v < a1; v += blockDim.y) fwd_node<VEC, NS, ISO, false, true>(k, xs, v, threadIdx.x * VEC);
+  } else {
+    for (int v = a0 + threadIdx.y; v < a1; v += blockDim.y) fwd_node<VEC, NS, ISO, false>(k, xs, v, threadIdx.x * VEC);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -677,21 +809,17 @@ __device__ __forceinline__ void bwd_fold(const RowPlan& P, const Acc<VEC, NS, IS
   }
 }
 
-template <int VEC, int NS, bool ISO, bool LAT>
-__global__ void __launch_bounds__(ROW_THREADS, LAT ? 4 : ROW_MINB_BWD) agg_bwd_row_kernel(const __grid_constant__ RowArgs k) {
-  pdl_prologue();
+template <int VEC, int NS, bool ISO, bool LAT, bool TILE = false>
+__device__ __forceinline__ void bwd_node(const RowArgs& k, const RowSrc& xs, int v, int c, bool prefetch_lane) {
   constexpr int NSA = NS > 0 ? NS : 1;
   const RowPlan& P = k.rp;
-  const int v = blockIdx.x * blockDim.y + threadIdx.y;
-  if (v >= k.N) return;
-  const int c = threadIdx.x * VEC;
   int tower = 0, cg = c;
   if (P.Fg != P.F) { tower = c / P.Fg; cg = c - tower * P.Fg; }
 
   // The node's gradient row (S*A slabs per tower, contiguous) dominates this kernel's traffic and its address is
   // known up front: one thread per node asks the L2 for it now, so the slab loads of the fold hit L2 instead of
   // paying one DRAM round trip per aggregator.
-  if (k.pf_bytes > 0 && threadIdx.x == 0) {
+  if (k.pf_bytes > 0 && prefetch_lane) {
     const float* grow0 = k.g_out + (size_t)v * k.ld_out;
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(grow0), "r"(k.pf_bytes) : "memory");
   }
@@ -722,10 +850,12 @@ __global__ void __launch_bounds__(ROW_THREADS, LAT ? 4 : ROW_MINB_BWD) agg_bwd_r
   Acc<VEC, NS, ISO> R;
   acc_clear(R);
   int D = 0;
-  walk_groups<VEC, NS, LAT>(k, v, c, qv, e0, ovf0, ovf1, [&](int, const Vec<VEC>& m, const float* wj) {
+  auto add = [&](int, const Vec<VEC>& m, const float* wj) {
     ++D;
     acc_add<VEC, NS, ISO>(R, m, wj);
-  });
+  };
+  if constexpr (TILE) walk_groups_pf<VEC, NS>(k, xs, v, c, qv, e0, ovf0, ovf1, add);
+  else walk_groups<VEC, NS, LAT>(k, xs, v, c, qv, e0, ovf0, ovf1, add);
 
   Vec<VEC> dq = vfill<VEC>(0.f);
   if (D > 0) {
@@ -742,7 +872,7 @@ __global__ void __launch_bounds__(ROW_THREADS, LAT ? 4 : ROW_MINB_BWD) agg_bwd_r
 
     // ---- pass 2: per-edge message gradients (rows and weights come back from L1 / L2) -------------------
     unsigned given = 0u;          // bit i: max gradient of column i already routed; bit VEC+i: min
-    walk_groups<VEC, NS, LAT>(k, v, c, qv, e0, ovf0, ovf1, [&](int jg, const Vec<VEC>& m, const float* wj) {
+    auto emit = [&](int jg, const Vec<VEC>& m, const float* wj) {
       Vec<VEC> dm;
 #pragma unroll
       for (int i = 0; i < VEC; ++i) {
@@ -767,10 +897,42 @@ __global__ void __launch_bounds__(ROW_THREADS, LAT ? 4 : ROW_MINB_BWD) agg_bwd_r
         const int id = k.in_eid ? __ldg(k.in_eid + e) : e;
         vstore<VEC>(k.d_r + (size_t)id * k.ld_dr + c, dm);
       }
-    });
+    };
+    if constexpr (TILE) walk_groups_pf<VEC, NS>(k, xs, v, c, qv, e0, ovf0, ovf1, emit);
+    else walk_groups<VEC, NS, LAT>(k, xs, v, c, qv, e0, ovf0, ovf1, emit);
   }
   if (k.d_q) vstore<VEC>(k.d_q + (size_t)v * k.ld_dq + c, dq);
   if (k.d_h) vstore<VEC>(k.d_h + (size_t)v * k.ld_dh + c, dh);
+}
+
+template <int VEC, int NS, bool ISO, bool LAT>
+__global__ void __launch_bounds__(ROW_THREADS, LAT ? 4 : ROW_MINB_BWD) agg_bwd_row_kernel(const __grid_constant__ RowArgs k) {
+  pdl_prologue();
+  const int v = blockIdx.x * blockDim.y + threadIdx.y;
+  if (v >= k.N) return;
+  const RowSrc xs{k.x, k.ld_x, 0, false};
+  bwd_node<VEC, NS, ISO, LAT>(k, xs, v, threadIdx.x * VEC, threadIdx.x == 0);
+}
+
+template <int VEC, int NS, bool ISO>
+__global__ void __launch_bounds__(TILE_THREADS, 2) agg_bwd_tile_kernel(const __grid_constant__ RowArgs k) {
+  pdl_prologue();
+  extern __shared__ __align__(16) float tile[];
+  const int g = blockIdx.x / k.tile_split, part = blockIdx.x - g * k.tile_split;
+  const int v0 = g < k.n_graphs ? __ldg(k.graph_ptr + g) : __ldg(k.graph_ptr + k.n_graphs);
+  const int v1 = g < k.n_graphs ? __ldg(k.graph_ptr + g + 1) : k.N;
+  if (v1 <= v0 || (g >= k.n_graphs && part > 0)) return;
+  const int per = g < k.n_graphs ? (v1 - v0 + k.tile_split - 1) / k.tile_split : v1 - v0;
+  const int a0 = v0 + part * per, a1 = min(a0 + per, v1);
+  if (a1 <= a0) return;
+  const RowSrc xs = g < k.n_graphs ? stage_graph_rows(k, tile, v0, v1) : RowSrc{k.x, k.ld_x, 0, false};
+  if (xs.smem) {
+    for (int v = a0 + threadIdx.y; v < a1; v += blockDim.y)
+      bwd_node<VEC, NS, ISO, false, true>(k, xs, v, threadIdx.x * VEC, threadIdx.x == 0);
+  } else {
+    for (int v = a0 + threadIdx.y; v < a1; v += blockDim.y)
+      bwd_node<VEC, NS, ISO, false>(k, xs, v, threadIdx.x * VEC, threadIdx.x == 0);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -796,6 +958,36 @@ static int launch_row_iso(const RowArgs& k, cudaStream_t st) {
   // chain, not by occupancy: it takes the LAT variants (wide gathers, pipelined fold).  DGN_ROW_LAT=0/1 overrides.
   static const int force_lat = [] { const char* e = getenv("DGN_ROW_LAT"); return e ? atoi(e) : -1; }();
   const bool lat = force_lat >= 0 ? force_lat != 0 : grid <= 148u * 6u;
+  // Tile kernels (one CTA slice per graph, the graph's source rows staged in shared memory, group loads prefetched):
+  // OPT-IN with DGN_TILE=1.  Measured on B200 (profiles/README.md, round 2): PATTERN b=256 forward 119 us vs 94 us for
+  // the row kernels, backward 375 vs 287 us; CIFAR 22 vs 12 us - removing the L2 row gathers did NOT help, i.e. round
+  // 1's diagnosis ("L2 -> SM gather bound") was wrong: at D ~ 51 the walk is bound by the ~40 instructions per
+  // (edge, 4-column chunk) it issues (37 M warp instructions ~ 33 us at peak issue for PATTERN) and by divergence of the
+  // 12-lane node groups inside a warp, which the row kernels' higher occupancy hides better.
+  static const int force_tile = [] { const char* e = getenv("DGN_TILE"); return e ? atoi(e) : 0; }();
+  const size_t tile_bytes = (size_t)k.tile_rows * k.rp.F * sizeof(float);
+  const bool tile_ok = k.graph_ptr && k.n_graphs > 0 && k.tile_rows > 0 && k.mode != DGN_MSG_DENSE && VEC == 4 &&
+                       tile_bytes <= 100 * 1024 && (k.ld_x % 4) == 0;
+  const bool tile = tile_ok && force_tile != 0 && k.n_edges >= 6LL * k.N;
+  if (tile) {
+    const dim3 tb((unsigned)chunks, (unsigned)(TILE_THREADS / chunks));
+    static const int passes = [] { const char* e = getenv("DGN_TILE_PASSES"); const int v = e ? atoi(e) : 1; return v < 1 ? 1 : v; }();
+    RowArgs kt = k;
+    kt.pf_bytes = 0;
+    kt.tile_split = (k.tile_rows + (int)tb.y * passes - 1) / ((int)tb.y * passes);      // <= `passes` nodes per thread row
+    const unsigned tg = (unsigned)(k.n_graphs + 1) * (unsigned)kt.tile_split;
+    cudaError_t e = cudaSuccess;
+    if constexpr (BWD) {
+      auto kern = iso ? agg_bwd_tile_kernel<VEC, NS, true> : agg_bwd_tile_kernel<VEC, NS, false>;
+      if (tile_bytes > 48 * 1024) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      if (e == cudaSuccess) launch_pdl(kern, dim3(tg), tb, tile_bytes, st, kt);
+    } else {
+      auto kern = iso ? agg_fwd_tile_kernel<VEC, NS, true> : agg_fwd_tile_kernel<VEC, NS, false>;
+      if (tile_bytes > 48 * 1024) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      if (e == cudaSuccess) launch_pdl(kern, dim3(tg), tb, tile_bytes, st, kt);
+    }
+    return (e == cudaSuccess && cudaGetLastError() == cudaSuccess) ? DGN_OK : DGN_ERR_CUDA;
+  }
   if constexpr (BWD) {
     if (lat) {
       RowArgs kl = k;
@@ -844,6 +1036,7 @@ static int fill_row_args(const KernelArgs& ka, const DgnAggSpec* spec, const Dgn
   k.g_out = ka.g_out; k.g_hcopy = ka.g_hcopy;
   k.d_q = ka.d_q; k.ld_dq = ka.ld_dq; k.d_r = ka.d_r; k.ld_dr = ka.ld_dr; k.d_h = ka.d_h; k.ld_dh = ka.ld_dh;
   k.d_h_add = ka.d_h_add; k.ld_dha = ka.ld_dha; k.edge_ws = ka.edge_ws;
+  k.graph_ptr = ka.graph_ptr; k.n_graphs = ka.n_graphs; k.tile_rows = ka.max_graph_nodes; k.n_edges = ka.E;
   if (k.g_out) {
     static const bool pf_on = [] { const char* e = getenv("DGN_ROW_NO_PREFETCH"); return !(e && atoi(e) != 0); }();
     const long long row = ((long long)(k.rp.F / k.rp.Fg - 1) * k.out_gs + (long long)k.rp.S * k.rp.A * k.rp.Fg) * 4;

@@ -59,6 +59,7 @@ struct KernelArgs {
   float* d_h; int ld_dh;
   const float* d_h_add; int ld_dha;
   float* edge_ws;
+  const int32_t* graph_ptr; int n_graphs; int max_graph_nodes;   // optional graph boundaries (tile kernels)
 };
 
 // ---- VEC-wide register vector -------------------------------------------------------------------

@@ -93,6 +93,7 @@ class BatchedGraph:
         B = len(self.batch_num_nodes)
         # graph_capacity: room for that many graphs in graph_ptr (device-side collation fills batches of varying size)
         self.graph_capacity = max(int(graph_capacity), B) if graph_capacity else B
+        self.max_graph_nodes_bound = None          # set it on padded (replayed) batches to enable the tile kernels
         Nr, Er = self.n_real_nodes, self.n_real_edges
         ndata = dict(ndata or {})
         edata = dict(edata or {})
@@ -230,9 +231,15 @@ class BatchedGraph:
                                 "(call .to('cuda')); there is no CPU path" % self.device)
         if self._c_graph is None:
             t = self._t
+            # graph boundaries (tile kernels for high-degree batches).  A padded batch is replayed with other
+            # contents, so the bound on the largest graph has to be given explicitly (max_graph_nodes_bound).
+            bound = self.max_graph_nodes_bound
+            if bound is None and not self.padded and self.batch_num_nodes:
+                bound = max(self.batch_num_nodes)
             self._c_graph = _lib.DgnGraph(self._n, self._e, t["in_ptr"].data_ptr(), t["in_src"].data_ptr(),
                                           t["in_eid"].data_ptr(), t["out_ptr"].data_ptr(), t["out_slot"].data_ptr(),
-                                          t["log_deg"].data_ptr())
+                                          t["log_deg"].data_ptr(), t["graph_ptr"].data_ptr() if bound else None,
+                                          self.batch_size if bound else 0, int(bound or 0))
         return self._c_graph
 
     # ---- eigen-field (DgnField): per-batch normalised eigenvector weights shared by all layers -------------

@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define DGN_ABI_VERSION 11
+#define DGN_ABI_VERSION 12
 #define DGN_MAX_AGG 32      /* aggregators per layer (the reference registry has 24)        */
 #define DGN_MAX_SCALERS 4   /* scalers per layer (the reference registry has 3)             */
 #define DGN_MAX_SLOTS 8     /* distinct eigen-weighted feature sums one launch can carry    */
@@ -97,6 +97,12 @@ typedef struct {
   const int32_t* out_ptr;  /* [n_nodes+1] range of every source node in out_slot (backward only)        */
   const int32_t* out_slot; /* [n_edges]   in-edge slot of every out-edge, grouped by source             */
   const float* log_deg;    /* [n_nodes]   (float)log(in_degree + 1), the scalers' per-node factor       */
+  /* optional (NULL / 0 = unknown): the graphs of the batch as contiguous node ranges.  With them, high-degree batches
+   * run one CTA per graph with the graph's source rows staged in shared memory (the batched adjacency of dgl.batch,
+   * rb/data/molecules.py:229, is block diagonal: every in-edge of a node comes from its own graph). */
+  const int32_t* graph_ptr;/* [n_graphs+1] first node of every graph, graph_ptr[n_graphs] = number of real nodes */
+  int32_t n_graphs;
+  int32_t max_graph_nodes; /* an upper bound of the largest graph's node count (sizes the shared-memory tile)   */
 } DgnGraph;
 
 /* Eigen-field of one batch: the normalised eigenvector weight w_s(u->v) of every in-edge for every distinct

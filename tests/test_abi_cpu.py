@@ -38,7 +38,7 @@ def test_abi_version_and_status_strings():
 def test_struct_sizes_match_header_layout():
     # 5 int32 + 32 + 32 + 32*4 + 4 (+pad) + float
     assert C.sizeof(_lib.DgnAggSpec) == 20 + 32 + 32 + 128 + 4 + 4
-    assert C.sizeof(_lib.DgnGraph) == 8 + 6 * 8
+    assert C.sizeof(_lib.DgnGraph) == 8 + 6 * 8 + 8 + 8
     assert C.sizeof(_lib.DgnField) == 8 + 3 * 8
 
 

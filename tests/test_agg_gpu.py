@@ -1,5 +1,7 @@
 """GPU parity: the CUDA aggregation kernels, called through the C ABI, against the oracle and the
 golden vectors produced by the reference.  Tolerance (north star): |a-b| <= 1e-5 * max(1, ||ref||_inf)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -366,3 +368,53 @@ def test_empty_and_degenerate_graphs():
     outs.backward(gy.to(DEV))
     assert_close(outs, ref, what="star out")
     assert_close(hd.grad, hl.grad, what="star dh")
+
+
+@pytest.mark.parametrize("kind,F,aggs,scs", [
+    ("pattern", 48, ["mean", "dir1-dx", "dir2-dx", "dir3-dx", "dir4-dx"], S3),
+    ("cifar", 64, ["mean", "max", "std", "dir1-dx", "dir2-av"], ["identity"]),
+])
+def test_tile_kernels_equal_row_kernels(kind, F, aggs, scs):
+    """High-degree batches run one CTA per graph with the graph's source rows staged in shared memory
+    (agg_fwd_tile_kernel / agg_bwd_tile_kernel, opt-in with DGN_TILE=1 when E >= 6 N and graph boundaries are known -
+    measured slower than the row kernels on B200, see dgn_agg_row.cu): the arithmetic and
+    its order are those of the row kernels, so the results must be bit-identical - forward, all gradients."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, numpy as np, torch
+sys.path.insert(0, %r)
+from dgn_b200 import _lib
+from dgn_b200.data.synthetic import make_samples, avg_log_degree
+from dgn_b200.graph import collate
+from dgn_b200.nets.aggregators import AGGREGATORS
+from dgn_b200.nets.scalers import SCALERS
+from dgn_b200.ops import AggSpec, aggregate
+kind, F, aggs, scs = %r, %d, %r, %r
+samples = make_samples(kind, 6, seed=2, n_min=30, n_max=70)
+g, _ = collate(samples); g.to("cuda")
+assert g.number_of_edges() >= 6 * g.number_of_nodes()
+rng = np.random.default_rng(0)
+N = g.number_of_nodes()
+t = lambda: torch.tensor(rng.standard_normal((N, F)).astype(np.float32), device="cuda", requires_grad=True)
+h, P, Q = t(), t(), t()
+eig = g.ndata["eig"]
+if eig.shape[1] < 5:
+    eig = torch.cat([eig, torch.tensor(rng.standard_normal((N, 5 - eig.shape[1])).astype(np.float32), device="cuda")], 1)
+spec = AggSpec([AGGREGATORS[a] for a in aggs], [SCALERS[s] for s in scs], avg_log_degree(samples), F, eig.shape[1])
+out = aggregate(g, spec, _lib.MSG_AFFINE, h, eig, x=P, q=Q)
+gy = torch.tensor(rng.standard_normal(tuple(out.shape)).astype(np.float32), device="cuda")
+out.backward(gy)
+torch.save([out.detach().cpu(), h.grad.cpu(), P.grad.cpu(), Q.grad.cpu()], sys.argv[1])
+''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), kind, F, aggs, scs)
+    import tempfile
+    res = []
+    with tempfile.TemporaryDirectory() as tmp:
+        for tile in ("0", "1"):
+            path = os.path.join(tmp, "r%s.pt" % tile)
+            r = subprocess.run([sys.executable, "-c", code, path], env=dict(os.environ, DGN_TILE=tile), capture_output=True,
+                               text=True, timeout=300)
+            assert r.returncode == 0, r.stderr[-2000:]
+            res.append(torch.load(path))
+    for a, b, name in zip(res[0], res[1], ("out", "dh", "dP", "dQ")):
+        assert torch.equal(a, b), "tile kernels differ from row kernels in %s (max %.3e)" % (name, float((a - b).abs().max()))
