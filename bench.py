@@ -564,7 +564,7 @@ def run_gpu_arm(args):
     clocks = sampler.stop() if rank == 0 else None
 
     roof = cpu = None
-    if rank == 0:
+    if rank == 0 and w["hidden"] % 4 == 0:
         from dgn_b200.graph import collate
         step = main["step"]
         peak, peak_src = measured_peak()
@@ -643,12 +643,22 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-strong", action="store_true", help="N>1: skip the extra strong-scaling measurement")
     ap.add_argument("--eager", action="store_true", help="no CUDA-graph capture, unpadded batches (debug)")
+    ap.add_argument("--hidden", type=int, default=0, help="override the hidden width (e.g. 45: the shipped ZINC config)")
+    ap.add_argument("--aggregators", default="", help="override the aggregator list")
     ap.add_argument("--cpu-leg", action="store_true", help=argparse.SUPPRESS)       # internal: child of the GPU arm
     ap.add_argument("--cpu-budget", type=float, default=20.0, help=argparse.SUPPRESS)
     ap.add_argument("--cpu-threads", type=int, default=0, help=argparse.SUPPRESS)
     ap.add_argument("--cpu-no-opt", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.hidden or args.aggregators:
+        w = dict(WORKLOADS[args.workload])
+        if args.hidden:
+            w["hidden"] = args.hidden
+        if args.aggregators:
+            w["aggregators"] = args.aggregators
+        w["text"] += " [overrides: hidden=%d, aggregators=%r]" % (w["hidden"], w["aggregators"])
+        WORKLOADS[args.workload] = w
     if args.impl == "reference":
         # the unmodified reference moves tensors to 'cuda' whenever a GPU is visible (rb/nets/dgn_layer.py:82-84):
         # the CPU arm hides the GPUs before torch initialises CUDA

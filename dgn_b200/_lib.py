@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DGN_LIB_PATH") or os.path.join(_HERE, "libdgn_b200.so")
 
 MAX_AGG, MAX_SCALERS, MAX_SLOTS = 32, 4, 8
-ABI_VERSION = 12
+ABI_VERSION = 13
 NORM_WS_PER_COL = 640
 
 # DgnAggKind / DgnScalerKind / DgnMsgMode
@@ -113,6 +113,14 @@ class DgnBatchOut(C.Structure):
                 ("payload", DgnPayload * MAX_PAYLOADS)]
 
 
+class DgnPeerGroup(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("grad_ptrs", C.c_void_p), ("flag_ptrs", C.c_void_p),
+                ("epoch", C.c_void_p)]
+
+
+AR_BLOCKS, AR_MAX_WORLD = 32, 8
+
+
 class DgnHeadGrad(C.Structure):
     _fields_ = [("g_y", C.c_void_p), ("ld_gy", C.c_int32), ("d_x", C.c_void_p), ("ld_dx", C.c_int32),
                 ("d_w1", C.c_void_p), ("d_b1", C.c_void_p), ("d_w2", C.c_void_p), ("d_b2", C.c_void_p),
@@ -141,6 +149,8 @@ SIGNATURES = {
                                          C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dgn_adam_step": (C.c_int, [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
                                 C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dgn_allreduce_adam": (C.c_int, [C.POINTER(DgnPeerGroup), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
+                                     C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dgn_gemm_ws_floats": (C.c_int64, []),
     "dgn_gemm_tf32x3": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                   C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,

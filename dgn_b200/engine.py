@@ -24,7 +24,7 @@ import ctypes as C
 from . import _lib, ops
 import os
 
-from .parallel import allreduce_sum_, flatten_parameters
+from .parallel import allreduce_sum_, flat_numel, flatten_parameters, make_peer_gradients
 
 
 class FlatAdam:
@@ -79,8 +79,11 @@ class TrainStep:
         self.dev = next(net.parameters()).device
         self.graphed = graphed
         self.node_key, self.edge_key = node_key, edge_key
-        self.flat_p, self.flat_g = flatten_parameters(net)
         self.world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        # more than one rank: the gradients live in NVLink peer-mapped memory and ONE launch of our own kernel
+        # (dgn_allreduce_adam) all-reduces them and applies Adam, inside the captured graph; NCCL is the fallback
+        self.peer = make_peer_gradients(flat_numel(net), self.dev) if self.world > 1 else None
+        self.flat_p, self.flat_g = flatten_parameters(net, self.peer.grad if self.peer is not None else None)
         # gradient average over the ranks = SUM all-reduce + 1 / world folded into the Adam kernel
         self.opt = FlatAdam(self.flat_p, self.flat_g, lr=lr, weight_decay=weight_decay, grad_scale=1.0 / self.world)
         self.loss_weight = None
@@ -95,10 +98,11 @@ class TrainStep:
         self.targets = torch.zeros(targets_like.shape, dtype=targets_like.dtype, device=self.dev)
         self.targets.copy_(targets_like)
         self.loss = torch.zeros((), device=self.dev)
-        # With more than one rank the NCCL all-reduce of the flat gradient and the Adam launch stay OUTSIDE the captured
+        # NCCL fallback (no peer memory): with more than one rank the NCCL all-reduce of the flat gradient and the Adam launch stay OUTSIDE the captured
         # graph (2 eager launches per step).  Capturing the collective (DGN_GRAPH_ALLREDUCE=1) was tried on B200 / NCCL
         # 2.28.9 / torch 2.11: the capture of a graph that also forks a side stream hung, so it is opt-in only.
-        self.split_update = graphed and self.world > 1 and os.environ.get("DGN_GRAPH_ALLREDUCE", "0") != "1"
+        self.split_update = (graphed and self.world > 1 and self.peer is None and
+                             os.environ.get("DGN_GRAPH_ALLREDUCE", "0") != "1")
         self.launches_per_step = 0
         self.cuda_graph = None
         if graphed:
@@ -125,6 +129,9 @@ class TrainStep:
         self.loss_weight.fill_(float(w))
 
     def _reduce_and_update(self):
+        if self.peer is not None:             # one launch: NVLink reduce-scatter + all-gather + Adam (grad_scale)
+            self.peer.allreduce_adam(self.opt)
+            return
         allreduce_sum_(self.flat_g)           # one NCCL all-reduce of the flat gradient (no-op on a single rank)
         self.opt.step()                       # Adam on grad / world (grad_scale)
 

@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define DGN_ABI_VERSION 12
+#define DGN_ABI_VERSION 13
 #define DGN_MAX_AGG 32      /* aggregators per layer (the reference registry has 24)        */
 #define DGN_MAX_SCALERS 4   /* scalers per layer (the reference registry has 3)             */
 #define DGN_MAX_SLOTS 8     /* distinct eigen-weighted feature sums one launch can carry    */
@@ -286,6 +286,30 @@ int dgn_embedding_backward(int32_t n_rows, int32_t n_cols, int32_t vocab, const 
  * was captured into a CUDA graph follows a learning-rate scheduler (ReduceLROnPlateau, rb/main_molecules.py:89-130). */
 int dgn_adam_step(int64_t n, float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float lr, float beta1,
                   float beta2, float eps, float weight_decay, const float* hyper, int32_t* state, void* stream);
+
+/* Gradient all-reduce over NVLink peer memory fused with the Adam update (data-parallel training): one
+ * launch per step and rank instead of an NCCL all-reduce + dgn_adam_step, capturable in the step's CUDA graph.  Every
+ * rank's flat gradient buffer lives in symmetric (peer-mapped) device memory; the kernel reduce-scatters it in rank order
+ * (deterministic, every rank gets bit-identical sums), then all-gathers the slices and applies Adam to the local replica
+ * (grad_scale = 1 / world through `hyper`).  All ranks must launch it the same number of times.
+ *   grad_ptrs  DEVICE array [world] of uint64: the ranks' gradient buffers as mapped into THIS process
+ *   flag_ptrs  DEVICE array [world] of uint64: the ranks' signal pads, DGN_AR_FLAG_WORDS(world) uint32 each, zero before
+ *              the first launch
+ *   epoch      local DEVICE uint32[4], zero before the first launch; [2] becomes 1 if a peer did not reach a barrier
+ *              within ~10 s (the step's result is then invalid; the kernel does not hang)
+ * n must be a multiple of 4 floats (the engine pads its flat buffers); other arguments as dgn_adam_step. */
+#define DGN_AR_BLOCKS 32
+#define DGN_AR_MAX_WORLD 8
+#define DGN_AR_FLAG_WORDS(world) (3 * DGN_AR_BLOCKS * (world))
+typedef struct {
+  int32_t world, rank;
+  const uint64_t* grad_ptrs;
+  const uint64_t* flag_ptrs;
+  uint32_t* epoch;
+} DgnPeerGroup;
+int dgn_allreduce_adam(const DgnPeerGroup* pg, int64_t n, float* param, float* exp_avg, float* exp_avg_sq, float lr,
+                       float beta1, float beta2, float eps, float weight_decay, const float* hyper, int32_t* state,
+                       void* stream);
 
 /* C (+)= op(A) * op(B) in fp32 accuracy on the tcgen05 tensor cores (3xTF32 split, fp32 accumulation in tensor
  * memory).  Replaces the library GEMMs of the pre/post-transform MLPs (FCLayer, rb/nets/layers.py:76-100).

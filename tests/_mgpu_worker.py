@@ -46,8 +46,15 @@ def main():
     loss = float(step.run())
     torch.cuda.synchronize()
     if rank == 0:
-        torch.save({"flat_g": step.flat_g.cpu(), "flat_p": step.flat_p.detach().cpu(), "loss0": loss,
+        own = step.peer.slice_bounds() if step.peer is not None else (0, step.flat_g.numel())
+        torch.save({"own": own, "flat_g": step.flat_g.cpu(), "flat_p": step.flat_p.detach().cpu(), "loss0": loss,
                     "launches": step.launches_per_step}, os.path.join(out_dir, "rank0_%d.pt" % int(graphed)))
+    assert step.peer is None or not step.peer.timed_out()
+    # the replicas must stay bit-identical (deterministic rank-order sum on every rank)
+    mine_p = step.flat_p.detach().clone()
+    other = [torch.empty_like(mine_p) for _ in range(world)]
+    dist.all_gather(other, mine_p)
+    assert all(torch.equal(o, other[0]) for o in other), "replicas diverged"
     dist.barrier()
     dist.destroy_process_group()
 

@@ -5,6 +5,7 @@ Semantics (declared): BatchNorm statistics are per shard, so the
 shard on its own (its own batch statistics) and adds the gradients weighted by the shard's share of the batch; the shards
 are deliberately unequal."""
 import os
+import signal
 import socket
 import subprocess
 import sys
@@ -46,8 +47,10 @@ def shard_bounds(n, world):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("graphed", [1, 0])
-def test_two_rank_step_equals_weighted_per_shard_gradients(graphed):
+@pytest.mark.parametrize("graphed,peer", [(1, 1), (0, 1), (1, 0), (0, 0)])
+def test_two_rank_step_equals_weighted_per_shard_gradients(graphed, peer):
+    """peer=1: gradients in NVLink peer memory, dgn_allreduce_adam inside the captured graph; peer=0: NCCL all-reduce +
+    dgn_adam_step.  With the peer kernel a rank's buffer holds the reduced SUM only on the slice it owns."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     from dgn_b200.graph import collate
@@ -59,8 +62,15 @@ def test_two_rank_step_equals_weighted_per_shard_gradients(graphed):
         s.close()
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr",
                "127.0.0.1", "--master-port", str(port), os.path.join(REPO, "tests", "_mgpu_worker.py"), tmp, str(graphed)]
-        r = subprocess.run(cmd, cwd=REPO, capture_output=True, text=True, timeout=240)
-        assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+        proc = subprocess.Popen(cmd, cwd=REPO, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                                start_new_session=True, env=dict(os.environ, DGN_PEER_ALLREDUCE=str(peer)))
+        try:
+            out, _ = proc.communicate(timeout=150)
+        except subprocess.TimeoutExpired:
+            os.killpg(proc.pid, signal.SIGKILL)           # torchrun AND its workers
+            out, _ = proc.communicate()
+            raise AssertionError("two-rank worker timed out:\n" + out[-3000:])
+        assert proc.returncode == 0, out[-4000:]
         got = torch.load(os.path.join(tmp, "rank0_%d.pt" % graphed))
     dev = torch.device("cuda", 0)
     samples, make_net = build_case(dev)
@@ -73,7 +83,9 @@ def test_two_rank_step_equals_weighted_per_shard_gradients(graphed):
         loss = net.loss(scores, labels.float().unsqueeze(1).to(dev))
         (loss * ((hi - lo) / B)).backward()
     want_g = torch.cat([torch.nn.functional.pad(p.grad.reshape(-1), (0, (-p.numel()) % 4)) for p in net.parameters()])
-    assert_close(got["flat_g"] / world, want_g.cpu(), rel=2e-5, what="all-reduced gradient / world")
+    lo, hi = got["own"]
+    assert (hi - lo < want_g.numel()) == bool(peer), "peer-memory path %s" % ("not taken" if peer else "taken")
+    assert_close(got["flat_g"][lo:hi] / world, want_g.cpu()[lo:hi], rel=2e-5, what="all-reduced gradient / world")
     opt = torch.optim.Adam(net.parameters(), lr=1e-3)
     opt.step()
     want_p = torch.cat([torch.nn.functional.pad(p.detach().reshape(-1), (0, (-p.numel()) % 4)) for p in net.parameters()])
