@@ -115,10 +115,10 @@ class DgnBatchOut(C.Structure):
 
 class DgnPeerGroup(C.Structure):
     _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("grad_ptrs", C.c_void_p), ("flag_ptrs", C.c_void_p),
-                ("epoch", C.c_void_p)]
+                ("epoch", C.c_void_p), ("reduced", C.c_void_p), ("one_shot_max_world", C.c_int32)]
 
 
-AR_BLOCKS, AR_MAX_WORLD = 32, 8
+AR_BLOCKS, AR_MAX_WORLD = 148, 8
 
 
 class DgnHeadGrad(C.Structure):

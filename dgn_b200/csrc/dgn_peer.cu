@@ -4,6 +4,7 @@
 // The only exchange of a data-parallel DGN step is the all-reduce of the flat fp32 gradient (~0.5 M floats = 2.2 MB):
 // latency bound.  A library all-reduce costs a launch of its own plus the optimizer launch, both outside the captured
 // graph.  Here every rank's gradient buffer lives in symmetric (peer-mapped) memory and one kernel does
+// (two-shot form; with <= one_shot_max_world ranks every rank simply reads all buffers in full: one barrier fewer)
 //   barrier A   every rank's backward has finished (per-CTA flags in the peers' signal pads, st.release.sys / ld.acquire.sys)
 //   phase 1     reduce-scatter: rank r sums slice r of all ranks' gradients IN RANK ORDER (deterministic) over NVLink
 //               loads and writes the sum back into its own buffer
@@ -22,7 +23,7 @@ extern thread_local cudaError_t g_dgn_last_cuda;
 
 namespace dgn {
 
-constexpr int kArBlocks = DGN_AR_BLOCKS, kArThreads = 512;
+constexpr int kArBlocks = DGN_AR_BLOCKS, kArThreads = 1024;
 constexpr long long kSpinLimit = 20000000000ll;                          // ~10 s of SM clocks
 
 struct PeerArgs {
@@ -35,6 +36,7 @@ struct PeerArgs {
   float lr, b1, b2, eps, wd;
   const float* hyper;
   int* state;
+  float* reduced;                         // optional: receives the all-reduced SUM
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
@@ -51,9 +53,11 @@ __device__ __forceinline__ float4 ld_peer(const float4* p) {           // bypass
   return v;
 }
 
-// all ranks' CTA `blockIdx.x` meet: signal every peer, then wait for every peer's signal of this epoch
+// all ranks' CTA `blockIdx.x` meet: signal every peer, then wait for every peer's signal of this epoch.  FENCE: this
+// CTA wrote data the peers read after the barrier.
+template <bool FENCE>
 __device__ __forceinline__ void peer_barrier(const PeerArgs& k, int phase, unsigned epoch) {
-  __threadfence_system();
+  if (FENCE) __threadfence_system();
   __syncthreads();
   const int t = threadIdx.x;
   if (t < k.world && t != k.rank) {
@@ -69,57 +73,72 @@ __device__ __forceinline__ void peer_barrier(const PeerArgs& k, int phase, unsig
   __syncthreads();
 }
 
+struct AdamCoef { float b1, b2, eps, wd, gs, step_size, inv_sqrt_c2; };
+
+__device__ __forceinline__ void adam4(const PeerArgs& k, const AdamCoef& c, long long i, const float4 gg) {
+  float4 pp = *reinterpret_cast<float4*>(k.p + 4 * i), mm = *reinterpret_cast<float4*>(k.m + 4 * i),
+         vv = *reinterpret_cast<float4*>(k.v + 4 * i);
+  float* pa = &pp.x; float* ma = &mm.x; float* va = &vv.x; const float* ga = &gg.x;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float gr = fmaf(c.wd, pa[j], c.gs * ga[j]);
+    ma[j] = fmaf(c.b1, ma[j], (1.f - c.b1) * gr);
+    va[j] = fmaf(c.b2, va[j], (1.f - c.b2) * gr * gr);
+    pa[j] -= c.step_size * ma[j] / (sqrtf(va[j]) * c.inv_sqrt_c2 + c.eps);
+  }
+  *reinterpret_cast<float4*>(k.p + 4 * i) = pp;
+  *reinterpret_cast<float4*>(k.m + 4 * i) = mm;
+  *reinterpret_cast<float4*>(k.v + 4 * i) = vv;
+  if (k.reduced) *reinterpret_cast<float4*>(k.reduced + 4 * i) = gg;
+}
+
+// rank-order sum of element i over all ranks' buffers (all loads in flight before the first add)
+__device__ __forceinline__ float4 sum_ranks(const PeerArgs& k, long long i) {
+  float4 g[DGN_AR_MAX_WORLD];
+#pragma unroll
+  for (int q = 0; q < DGN_AR_MAX_WORLD; ++q)
+    if (q < k.world) g[q] = ld_peer(reinterpret_cast<const float4*>(k.grad_ptrs[q]) + i);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int q = 0; q < DGN_AR_MAX_WORLD; ++q)
+    if (q < k.world) { acc.x += g[q].x; acc.y += g[q].y; acc.z += g[q].z; acc.w += g[q].w; }
+  return acc;
+}
+
+// ONE_SHOT: every rank reads all the buffers in full (world - 1 buffers over NVLink, one barrier and one latency round
+// fewer); two-shot: reduce-scatter + all-gather (2 (world - 1) / world buffers).
+template <bool ONE_SHOT>
 __global__ void __launch_bounds__(kArThreads) allreduce_adam_kernel(const __grid_constant__ PeerArgs k) {
   pdl_prologue();
   const unsigned epoch = k.epoch[0] + 1u;
   const int W = k.world;
-  const long long n4 = (k.n + 3) / 4;                                  // buffers are padded to multiples of 4 floats
-  const long long per = (n4 + W - 1) / W;                              // float4 per rank slice
+  const long long n4 = k.n / 4;
   const long long tid = (long long)blockIdx.x * kArThreads + threadIdx.x, stride = (long long)kArBlocks * kArThreads;
-  float4* mine = reinterpret_cast<float4*>(k.grad_ptrs[k.rank]);
-
-  peer_barrier(k, 0, epoch);
-  // ---- phase 1: reduce-scatter of my slice, rank order ---------------------------------------------------------------
-  const long long s0 = per * k.rank, s1 = min(s0 + per, n4);
-  for (long long i = s0 + tid; i < s1; i += stride) {
-    float4 g[DGN_AR_MAX_WORLD];
-#pragma unroll
-    for (int q = 0; q < DGN_AR_MAX_WORLD; ++q)
-      if (q < W) g[q] = ld_peer(reinterpret_cast<const float4*>(k.grad_ptrs[q]) + i);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int q = 0; q < DGN_AR_MAX_WORLD; ++q)
-      if (q < W) { acc.x += g[q].x; acc.y += g[q].y; acc.z += g[q].z; acc.w += g[q].w; }
-    mine[i] = acc;
+  AdamCoef c;
+  {
+    float lr = k.lr;
+    c.b1 = k.b1; c.b2 = k.b2; c.eps = k.eps; c.wd = k.wd; c.gs = 1.f;
+    if (k.hyper) { lr = k.hyper[0]; c.wd = k.hyper[1]; c.gs = k.hyper[2]; }
+    const int t = k.state[0] + 1;
+    const float c1 = 1.f - powf(k.b1, (float)t), c2 = 1.f - powf(k.b2, (float)t);
+    c.step_size = lr / c1; c.inv_sqrt_c2 = rsqrtf(c2);
   }
-  peer_barrier(k, 1, epoch);
-  // ---- phase 2: all-gather + Adam on the local replica ---------------------------------------------------------------
-  float lr = k.lr, wd = k.wd, gs = 1.f;
-  if (k.hyper) { lr = k.hyper[0]; wd = k.hyper[1]; gs = k.hyper[2]; }
-  const int t = k.state[0] + 1;
-  const float c1 = 1.f - powf(k.b1, (float)t), c2 = 1.f - powf(k.b2, (float)t);
-  const float step_size = lr / c1, inv_sqrt_c2 = rsqrtf(c2);
-  for (long long i = tid; i < n4; i += stride) {
-    const int owner = (int)(i / per);
-    const float4 gg = ld_peer(reinterpret_cast<const float4*>(k.grad_ptrs[owner]) + i);
-    float4 pp = *reinterpret_cast<float4*>(k.p + 4 * i), mm = *reinterpret_cast<float4*>(k.m + 4 * i),
-           vv = *reinterpret_cast<float4*>(k.v + 4 * i);
-    float* pa = &pp.x; float* ma = &mm.x; float* va = &vv.x; const float* ga = &gg.x;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float gr = fmaf(wd, pa[j], gs * ga[j]);
-      ma[j] = fmaf(k.b1, ma[j], (1.f - k.b1) * gr);
-      va[j] = fmaf(k.b2, va[j], (1.f - k.b2) * gr * gr);
-      pa[j] -= step_size * ma[j] / (sqrtf(va[j]) * inv_sqrt_c2 + k.eps);
-    }
-    *reinterpret_cast<float4*>(k.p + 4 * i) = pp;
-    *reinterpret_cast<float4*>(k.m + 4 * i) = mm;
-    *reinterpret_cast<float4*>(k.v + 4 * i) = vv;
+  peer_barrier<false>(k, 0, epoch);                                    // every rank's backward has finished
+  if (ONE_SHOT) {
+    for (long long i = tid; i < n4; i += stride) adam4(k, c, i, sum_ranks(k, i));
+  } else {
+    const long long per = (n4 + W - 1) / W;                            // float4 per rank slice
+    float4* mine = reinterpret_cast<float4*>(k.grad_ptrs[k.rank]);
+    const long long s0 = per * k.rank, s1 = min(s0 + per, n4);
+    for (long long i = s0 + tid; i < s1; i += stride) mine[i] = sum_ranks(k, i);          // reduce-scatter
+    peer_barrier<true>(k, 1, epoch);
+    for (long long i = tid; i < n4; i += stride)                                          // all-gather + Adam
+      adam4(k, c, i, ld_peer(reinterpret_cast<const float4*>(k.grad_ptrs[(int)(i / per)]) + i));
   }
-  peer_barrier(k, 2, epoch);
+  peer_barrier<false>(k, 2, epoch);                                    // nobody still reads my buffer when I move on
   if (threadIdx.x == 0) {
     const unsigned done = atomicAdd(&k.epoch[1], 1u);
-    if (done == gridDim.x - 1) { k.epoch[1] = 0u; k.epoch[0] = epoch; k.state[0] = t; }
+    if (done == gridDim.x - 1) { k.epoch[1] = 0u; k.epoch[0] = epoch; k.state[0] = k.state[0] + 1; }
   }
 }
 
@@ -144,7 +163,11 @@ extern "C" int dgn_allreduce_adam(const DgnPeerGroup* pg, int64_t n, float* para
   k.epoch = reinterpret_cast<unsigned*>(pg->epoch);
   k.n = n; k.p = param; k.m = exp_avg; k.v = exp_avg_sq;
   k.lr = lr; k.b1 = beta1; k.b2 = beta2; k.eps = eps; k.wd = weight_decay; k.hyper = hyper; k.state = state;
-  launch_pdl(allreduce_adam_kernel, dim3(kArBlocks), dim3(kArThreads), 0, (cudaStream_t)stream, k);
+  k.reduced = pg->reduced;
+  if (pg->world <= pg->one_shot_max_world)
+    launch_pdl(allreduce_adam_kernel<true>, dim3(kArBlocks), dim3(kArThreads), 0, (cudaStream_t)stream, k);
+  else
+    launch_pdl(allreduce_adam_kernel<false>, dim3(kArBlocks), dim3(kArThreads), 0, (cudaStream_t)stream, k);
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { g_dgn_last_cuda = e; return DGN_ERR_CUDA; }
   return DGN_OK;

@@ -126,15 +126,13 @@ class PeerGradients:
         self.epoch = torch.zeros(4, dtype=torch.int32, device=device)
         torch.cuda.synchronize(device)
         dist.barrier(group)                                       # every pad is zero before anybody signals
+        import os
+        # DGN_PEER_KEEP_SUM=1: also store the all-reduced SUM in ``self.reduced`` (tests, gradient logging)
+        self.reduced = torch.zeros_like(self.grad) if os.environ.get("DGN_PEER_KEEP_SUM", "0") == "1" else None
+        self.one_shot = self.world <= int(os.environ.get("DGN_AR_ONESHOT_MAX_WORLD", "2"))
         self._pg = _lib.DgnPeerGroup(self.world, self.rank, self.grad_ptrs.data_ptr(), self.flag_ptrs.data_ptr(),
-                                     self.epoch.data_ptr())
-
-    def slice_bounds(self, rank=None):
-        """Element range of the flat gradient that ``rank`` owns (holds the all-reduced SUM after a step)."""
-        rank = self.rank if rank is None else rank
-        n4 = self.grad.numel() // 4
-        per = (n4 + self.world - 1) // self.world
-        return 4 * min(per * rank, n4), 4 * min(per * (rank + 1), n4)
+                                     self.epoch.data_ptr(), self.reduced.data_ptr() if self.reduced is not None else None,
+                                     self.world if self.one_shot else 0)
 
     def timed_out(self) -> bool:
         """True when a barrier of some step gave up waiting for a peer (synchronises)."""

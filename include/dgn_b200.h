@@ -298,7 +298,7 @@ int dgn_adam_step(int64_t n, float* param, const float* grad, float* exp_avg, fl
  *   epoch      local DEVICE uint32[4], zero before the first launch; [2] becomes 1 if a peer did not reach a barrier
  *              within ~10 s (the step's result is then invalid; the kernel does not hang)
  * n must be a multiple of 4 floats (the engine pads its flat buffers); other arguments as dgn_adam_step. */
-#define DGN_AR_BLOCKS 32
+#define DGN_AR_BLOCKS 148
 #define DGN_AR_MAX_WORLD 8
 #define DGN_AR_FLAG_WORDS(world) (3 * DGN_AR_BLOCKS * (world))
 typedef struct {
@@ -306,6 +306,9 @@ typedef struct {
   const uint64_t* grad_ptrs;
   const uint64_t* flag_ptrs;
   uint32_t* epoch;
+  float* reduced;             /* optional local DEVICE buffer of n floats: receives the all-reduced SUM (checks, logging) */
+  int32_t one_shot_max_world; /* world <= this: every rank reads all buffers in full (one barrier fewer); else
+                                 reduce-scatter + all-gather.  2 is a good default for ~2 MB of gradients */
 } DgnPeerGroup;
 int dgn_allreduce_adam(const DgnPeerGroup* pg, int64_t n, float* param, float* exp_avg, float* exp_avg_sq, float lr,
                        float beta1, float beta2, float eps, float weight_decay, const float* hyper, int32_t* state,

@@ -46,8 +46,9 @@ def main():
     loss = float(step.run())
     torch.cuda.synchronize()
     if rank == 0:
-        own = step.peer.slice_bounds() if step.peer is not None else (0, step.flat_g.numel())
-        torch.save({"own": own, "flat_g": step.flat_g.cpu(), "flat_p": step.flat_p.detach().cpu(), "loss0": loss,
+        summed = step.peer.reduced if step.peer is not None else step.flat_g
+        torch.save({"peer": None if step.peer is None else ("one-shot" if step.peer.one_shot else "two-shot"),
+                    "flat_g": summed.cpu(), "flat_p": step.flat_p.detach().cpu(), "loss0": loss,
                     "launches": step.launches_per_step}, os.path.join(out_dir, "rank0_%d.pt" % int(graphed)))
     assert step.peer is None or not step.peer.timed_out()
     # the replicas must stay bit-identical (deterministic rank-order sum on every rank)

@@ -47,10 +47,10 @@ def shard_bounds(n, world):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("graphed,peer", [(1, 1), (0, 1), (1, 0), (0, 0)])
+@pytest.mark.parametrize("graphed,peer", [(1, "one-shot"), (1, "two-shot"), (0, "one-shot"), (1, None), (0, None)])
 def test_two_rank_step_equals_weighted_per_shard_gradients(graphed, peer):
     """peer=1: gradients in NVLink peer memory, dgn_allreduce_adam inside the captured graph; peer=0: NCCL all-reduce +
-    dgn_adam_step.  With the peer kernel a rank's buffer holds the reduced SUM only on the slice it owns."""
+    dgn_adam_step."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     from dgn_b200.graph import collate
@@ -63,7 +63,8 @@ def test_two_rank_step_equals_weighted_per_shard_gradients(graphed, peer):
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr",
                "127.0.0.1", "--master-port", str(port), os.path.join(REPO, "tests", "_mgpu_worker.py"), tmp, str(graphed)]
         proc = subprocess.Popen(cmd, cwd=REPO, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
-                                start_new_session=True, env=dict(os.environ, DGN_PEER_ALLREDUCE=str(peer)))
+                                start_new_session=True, env=dict(os.environ, DGN_PEER_ALLREDUCE=str(int(peer is not None)), DGN_PEER_KEEP_SUM="1",
+                                         DGN_AR_ONESHOT_MAX_WORLD="2" if peer == "one-shot" else "0"))
         try:
             out, _ = proc.communicate(timeout=150)
         except subprocess.TimeoutExpired:
@@ -83,9 +84,8 @@ def test_two_rank_step_equals_weighted_per_shard_gradients(graphed, peer):
         loss = net.loss(scores, labels.float().unsqueeze(1).to(dev))
         (loss * ((hi - lo) / B)).backward()
     want_g = torch.cat([torch.nn.functional.pad(p.grad.reshape(-1), (0, (-p.numel()) % 4)) for p in net.parameters()])
-    lo, hi = got["own"]
-    assert (hi - lo < want_g.numel()) == bool(peer), "peer-memory path %s" % ("not taken" if peer else "taken")
-    assert_close(got["flat_g"][lo:hi] / world, want_g.cpu()[lo:hi], rel=2e-5, what="all-reduced gradient / world")
+    assert got["peer"] == peer, "gradient exchange went through %s, expected %s" % (got["peer"], peer)
+    assert_close(got["flat_g"] / world, want_g.cpu(), rel=2e-5, what="all-reduced gradient / world")
     opt = torch.optim.Adam(net.parameters(), lr=1e-3)
     opt.step()
     want_p = torch.cat([torch.nn.functional.pad(p.detach().reshape(-1), (0, (-p.numel()) % 4)) for p in net.parameters()])
