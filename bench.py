@@ -358,8 +358,8 @@ def kernel_roofline(w, graph, avg_log, device, folded, rot=8, replays=10):
     t_f, t_b = timed(fwd), timed(bwd)
     k_used = len({a.eig_idx for a in aggs if a.kind >= _lib.AGG_DIR_AV})
     bf, bb = agg_bytes(n_real, e_real, F, A, S, 3, k_used)
-    if folded:                                    # + the [E, F] spill the pretrans kernel reduces (written once)
-        bb += 4 * e_real * F
+    if folded:                                    # d_P is not produced; + the [E, F] spill the pretrans kernel reduces
+        bb += 4 * e_real * F - 4 * n_real * F
     return {"fwd_us": t_f * 1e6, "bwd_us": t_b * 1e6, "bytes_fwd": bf, "bytes_bwd": bb,
             "achieved": (bf + bb) / (t_f + t_b) / 1e9, "fwd_gbs": bf / t_f / 1e9, "bwd_gbs": bb / t_b / 1e9,
             "medges_per_s": e_real / (t_f + t_b) / 1e6}          # edges / kernel time of one layer

@@ -64,8 +64,13 @@ def time_graph(fn, sets, replays=5):
     return a.elapsed_time(b) * 1e-3 / (replays * len(sets))
 
 
-def run_case(name, scale, dev):
+def run_case(name, scale, dev, folded=False):
+    """``folded``: the layout the fused layer runs since round 2 - raw aggregates [N, F + A*F] (the scalers are folded
+    into the posttrans GEMM, dgn_post_forward) and a backward that leaves the per-edge gradients in the [E, F] workspace
+    (their source-side reduction is part of dgn_pair_gather_backward)."""
     kind, n_graphs, F, aggs, scs, k_used = CASES[name]
+    if folded:
+        scs = "identity"
     base = make_samples(kind, n_graphs, seed=0)
     samples = base * scale                                   # replicated batch: same statistics, `scale` x the size
     g, _ = collate(samples)
@@ -90,7 +95,8 @@ def run_case(name, scale, dev):
     eig = g.ndata["eig"]
     tf = time_graph(lambda t: agg_forward_raw(g, spec, _lib.MSG_AFFINE, t["P"], t["Q"], None, t["h"], eig, t["out"], True), sets)
     tb = time_graph(lambda t: agg_backward_raw(g, spec, _lib.MSG_AFFINE, t["P"], t["Q"], None, t["h"], eig, t["gy"], True,
-                                               d_x=t["dP"], d_q=t["dQ"], d_h=t["dh"], edge_ws=t["ws"]), sets)
+                                               d_x=None if folded else t["dP"], d_q=t["dQ"], d_h=t["dh"],
+                                               edge_ws=t["ws"]), sets)
     # the per-batch eigen-field build (one launch shared by all layers of a step), timed on its own
     t_field = 0.0
     if ops.FIELD_ENABLED:
@@ -104,8 +110,10 @@ def run_case(name, scale, dev):
         t_field = a.elapsed_time(b) * 1e-3 / 10
     bf = 4 * (E + N * (3 * F + k_used + 1) + N * S * A * F)
     bb = bf + 4 * N * 3 * F
+    if folded:                                               # d_P is not produced; the [E, F] spill is written once
+        bb += 4 * E * F - 4 * N * F
     pk = peak()
-    return {"case": name, "scale": scale, "graphs": len(samples), "N": N, "E": E, "F": F, "A": A, "S": S, "rot": rot,
+    return {"case": name, "scale": scale, "layout": "folded" if folded else "reference", "tile": os.environ.get("DGN_TILE", "0"), "graphs": len(samples), "N": N, "E": E, "F": F, "A": A, "S": S, "rot": rot,
             "fwd_us": tf * 1e6, "bwd_us": tb * 1e6, "field_build_us": t_field * 1e6, "bytes_fwd": bf, "bytes_bwd": bb,
             "fwd_gbs": bf / tf / 1e9, "bwd_gbs": bb / tb / 1e9, "fwd_frac": bf / tf / 1e9 / pk,
             "bwd_frac": bb / tb / 1e9 / pk, "frac": (bf + bb) / (tf + tb) / 1e9 / pk, "peak_gbs": pk,
@@ -116,13 +124,14 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cases", default="zinc,pattern,cifar,molhiv")
     ap.add_argument("--scales", default="1,4,16,64")
+    ap.add_argument("--folded", action="store_true", help="raw-aggregate layout of the fused layer (scalers in the GEMM)")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     for name in args.cases.split(","):
         for sc in [int(s) for s in args.scales.split(",")]:
             if name == "pattern" and sc > 4:
                 continue                                     # 1.5 M edges x scale: keep the sweep bounded
-            print(json.dumps(run_case(name, sc, dev)), flush=True)
+            print(json.dumps(run_case(name, sc, dev, args.folded)), flush=True)
             torch.cuda.empty_cache()
 
 
