@@ -4,8 +4,10 @@
 // with W = [W_src | W_dst] stored as one [F_out, 2 F_in (+edge)] parameter.  These K = F_in (<= 128) products are
 // launch-latency bound; doing both halves in ONE launch straight from the parameter's layout (no slicing, no
 // second GEMM) halves their cost.  Same for the backward d_h += d_P W_src + d_Q W_dst.
-// Tiles: 32 rows x 64 columns per 128-thread block, 4 x 4 outputs per thread, operands staged in shared
-// memory so that every inner-loop read is a conflict-free 128-bit load.
+// Tiles: 16 rows x 32 columns per 128-thread block (8 column groups x 16 rows: 1 x 4 outputs of each product per
+// thread).  Round 1 used 32 x 64 tiles with 4 x 4 outputs per thread: 94 CTAs of 4 warps for the bench batch, i.e. less
+// than one warp per scheduler on 2/3 of the SMs - ncu: 6 % warps active, 17 % issue slots used, 14 us for 49 MFLOP.
+// These products are latency bound, so the tile is sized for warps in flight (376 CTAs = 10 warps per SM), not reuse.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -14,70 +16,92 @@
 
 namespace dgn {
 
-constexpr int LR = 32, LC = 64, LT = 128;     // rows / columns per block, threads
+constexpr int LR = 16, LC = 32, LT = 128;     // rows / columns per block, threads
+constexpr int TPAD = 4;                       // row padding of the row-major operand tiles (keeps rows 16 B aligned)
 
-// Asynchronous 4-byte global -> shared copies (LDGSTS): the staging loops issue all their copies back to back instead
-// of 80 dependent load -> store round trips per thread - with 4 warps per CTA nothing else hides that latency.
+// Asynchronous global -> shared copies (LDGSTS): the staging loops issue all their copies back to back instead of
+// dependent load -> store round trips - with 4 warps per CTA nothing else hides that latency.
 __device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// W = [W_src | W_dst] is stored [F_out, 2 F_in]: the forward products need it k-major.  The block W[c0 : c0 + LC, :] is
+// staged TRANSPOSED: element (k, o) of each half at k * LC + (o ^ ((k & 7) << 2)).  A warp copies 8 consecutive k of 4
+// output rows per instruction: the global reads use whole 32-byte sectors (round 1 read one 4-byte word per row and
+// instruction - 32 L1 wavefronts each, most of the kernel's time), and the XOR swizzle spreads the 32 stores over the 32
+// banks.  The swizzle moves whole float4 groups, so the inner loop still reads its 4 output columns with one LDS.128.
+__device__ __forceinline__ void stage_w_transposed(float* wp, float* wq, const float* __restrict__ W, int ld_w, int Fi,
+                                                   int Fo, int c0, int t) {
+  const int kb = (Fi + 7) >> 3;
+  for (int e = t; e < kb * 8 * LC; e += LT) {
+    const int k_lo = e & 7, o_lo = (e >> 3) & 3, rest = e >> 5;
+    const int k = (rest % kb) * 8 + k_lo, o = (rest / kb) * 4 + o_lo;
+    if (k >= Fi) continue;
+    const int pos = k * LC + (o ^ (k_lo << 2));
+    if (c0 + o < Fo) {
+      cp_async4(wp + pos, W + (size_t)(c0 + o) * ld_w + k);
+      cp_async4(wq + pos, W + (size_t)(c0 + o) * ld_w + Fi + k);
+    } else {
+      wp[pos] = 0.f;
+      wq[pos] = 0.f;
+    }
+  }
+}
+
+// both products of one thread: row `hrow` (shared memory, Fi floats) against the staged W halves, columns tx*4 .. +3
+__device__ __forceinline__ void pair_products(const float* hrow, const float* wp, const float* wq, int Fi, int tx,
+                                              float (&ap)[4], float (&aq)[4]) {
+#pragma unroll 8
+  for (int i = 0; i < Fi; ++i) {
+    const float hv = hrow[i];
+    const int off = i * LC + ((tx * 4) ^ ((i & 7) << 2));
+    const float4 pv = *reinterpret_cast<const float4*>(wp + off);
+    const float4 qv = *reinterpret_cast<const float4*>(wq + off);
+    ap[0] = fmaf(hv, pv.x, ap[0]); ap[1] = fmaf(hv, pv.y, ap[1]); ap[2] = fmaf(hv, pv.z, ap[2]); ap[3] = fmaf(hv, pv.w, ap[3]);
+    aq[0] = fmaf(hv, qv.x, aq[0]); aq[1] = fmaf(hv, qv.y, aq[1]); aq[2] = fmaf(hv, qv.z, aq[2]); aq[3] = fmaf(hv, qv.w, aq[3]);
+  }
+}
 
 // P[n,o] = sum_i h[n,i] W[o,i] ;  Q[n,o] = sum_i h[n,i] W[o,Fi+i]
 __global__ void __launch_bounds__(LT) pair_linear_fwd_kernel(int N, int Fi, int Fo, const float* __restrict__ h, int ld_h,
-                                                             const float* __restrict__ W, int ld_w,
+                                                             int h_vec, const float* __restrict__ W, int ld_w,
                                                              float* __restrict__ P, int ld_p, float* __restrict__ Q,
                                                              int ld_q) {
   pdl_prologue();
   extern __shared__ __align__(16) float sm[];
-  float* ht = sm;                              // [Fi][LR]   h tile, transposed
-  float* wp = ht + Fi * LR;                    // [Fi][LC]   W_src block, transposed
-  float* wq = wp + Fi * LC;                    // [Fi][LC]   W_dst block, transposed
+  const int hld = Fi + TPAD;
+  float* hs = sm;                              // [LR][Fi + 4]  h tile, row-major
+  float* wp = hs + LR * hld;                   // [Fi][LC]      W_src block, transposed + swizzled
+  float* wq = wp + Fi * LC;                    // [Fi][LC]      W_dst block
   const int t = threadIdx.x, r0 = blockIdx.x * LR, c0 = blockIdx.y * LC;
-  // Staging transposes the tiles.  Consecutive threads take consecutive rows / output columns, so the shared-memory
-  // stores are conflict free (the other order - coalesced global reads, stride-LR stores - serialises every store
-  // instruction 32 ways and was most of this kernel's time); the strided global reads hit L1 / L2.
-  for (int idx = t; idx < LR * Fi; idx += LT) {
-    const int i = idx / LR, r = idx - i * LR;
-    if (r0 + r < N) cp_async4(ht + idx, h + (size_t)(r0 + r) * ld_h + i);
-    else ht[idx] = 0.f;
-  }
-  for (int idx = t; idx < LC * Fi; idx += LT) {
-    const int i = idx / LC, o = idx - i * LC;
-    if (c0 + o < Fo) {
-      cp_async4(wp + idx, W + (size_t)(c0 + o) * ld_w + i);
-      cp_async4(wq + idx, W + (size_t)(c0 + o) * ld_w + Fi + i);
+  const int q4 = Fi / 4;
+  for (int idx = t; idx < LR * q4; idx += LT) {
+    const int r = idx / q4, i = (idx - r * q4) * 4;
+    float* dst = hs + r * hld + i;
+    if (r0 + r < N) {
+      const float* src = h + (size_t)(r0 + r) * ld_h + i;
+      if (h_vec) cp_async16(dst, src);
+      else { cp_async4(dst, src); cp_async4(dst + 1, src + 1); cp_async4(dst + 2, src + 2); cp_async4(dst + 3, src + 3); }
     } else {
-      wp[idx] = 0.f;
-      wq[idx] = 0.f;
+      dst[0] = 0.f; dst[1] = 0.f; dst[2] = 0.f; dst[3] = 0.f;
     }
   }
+  stage_w_transposed(wp, wq, W, ld_w, Fi, Fo, c0, t);
   cp_async_wait_all();
   __syncthreads();
-  const int tx = t & 15, ty = t >> 4;          // 16 column groups x 8 row groups
-  float ap[4][4] = {}, aq[4][4] = {};
-#pragma unroll 4
-  for (int i = 0; i < Fi; ++i) {
-    const float4 hv = *reinterpret_cast<const float4*>(ht + i * LR + ty * 4);
-    const float4 pv = *reinterpret_cast<const float4*>(wp + i * LC + tx * 4);
-    const float4 qv = *reinterpret_cast<const float4*>(wq + i * LC + tx * 4);
-    const float hr[4] = {hv.x, hv.y, hv.z, hv.w}, pw[4] = {pv.x, pv.y, pv.z, pv.w}, qw[4] = {qv.x, qv.y, qv.z, qv.w};
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        ap[a][b] = fmaf(hr[a], pw[b], ap[a][b]);
-        aq[a][b] = fmaf(hr[a], qw[b], aq[a][b]);
-      }
-  }
-#pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    const int r = r0 + ty * 4 + a, c = c0 + tx * 4;
-    if (r < N && c < Fo) {                      // Fo % 4 == 0: the 4 columns are in or out together
-      *reinterpret_cast<float4*>(P + (size_t)r * ld_p + c) = make_float4(ap[a][0], ap[a][1], ap[a][2], ap[a][3]);
-      *reinterpret_cast<float4*>(Q + (size_t)r * ld_q + c) = make_float4(aq[a][0], aq[a][1], aq[a][2], aq[a][3]);
-    }
+  const int tx = t & 7, ty = t >> 3;           // 8 column groups x 16 rows
+  float ap[4] = {}, aq[4] = {};
+  pair_products(hs + ty * hld, wp, wq, Fi, tx, ap, aq);
+  const int r = r0 + ty, c = c0 + tx * 4;
+  if (r < N && c < Fo) {                        // Fo % 4 == 0: the 4 columns are in or out together
+    *reinterpret_cast<float4*>(P + (size_t)r * ld_p + c) = make_float4(ap[0], ap[1], ap[2], ap[3]);
+    *reinterpret_cast<float4*>(Q + (size_t)r * ld_q + c) = make_float4(aq[0], aq[1], aq[2], aq[3]);
   }
 }
 
@@ -87,35 +111,25 @@ __global__ void __launch_bounds__(LT) pair_linear_fwd_kernel(int N, int Fi, int 
 //   P = out W_src^T, Q = out W_dst^T                rb/nets/dgn_layer.py:75-80 of the next layer
 // The row tile is produced with coalesced 128-bit accesses (16 threads per row), written to `out` and kept in shared
 // memory for the two products.
-constexpr int HS_LD_PAD = 1;
 __global__ void __launch_bounds__(LT) norm_pair_fwd_kernel(const DgnNormArgs a, int Fo, const float* __restrict__ W, int ld_w,
                                                            float* __restrict__ P, int ld_p, float* __restrict__ Q,
                                                            int ld_q) {
   pdl_prologue();
   extern __shared__ __align__(16) float sm[];
-  const int Fi = a.n_cols, hld = Fi + HS_LD_PAD;
-  float* hs = sm;                              // [LR][Fi + 1]  epilogue output tile, row-major
-  float* wp = hs + LR * hld;                   // [Fi][LC]      W_src block, transposed
-  float* wq = wp + Fi * LC;                    // [Fi][LC]      W_dst block, transposed
+  const int Fi = a.n_cols, hld = Fi + TPAD;
+  float* hs = sm;                              // [LR][Fi + 4]  epilogue output tile, row-major
+  float* wp = hs + LR * hld;                   // [Fi][LC]      W_src block, transposed + swizzled
+  float* wq = wp + Fi * LC;                    // [Fi][LC]      W_dst block
   float* cst = wq + Fi * LC;                   // [5][Fi]       mean, rstd, gamma, beta, bias
+  float* part = cst + 5 * Fi;                  // [4][3][Fi]    statistics merge scratch
   const int t = threadIdx.x, r0 = blockIdx.x * LR, c0 = blockIdx.y * LC;
   const int n = a.n_rows_dev ? *a.n_rows_dev : a.n_rows;
-  for (int idx = t; idx < LC * Fi; idx += LT) {
-    const int i = idx / LC, o = idx - i * LC;
-    if (c0 + o < Fo) {
-      cp_async4(wp + idx, W + (size_t)(c0 + o) * ld_w + i);
-      cp_async4(wq + idx, W + (size_t)(c0 + o) * ld_w + Fi + i);
-    } else {
-      wp[idx] = 0.f;
-      wq[idx] = 0.f;
-    }
-  }
+  stage_w_transposed(wp, wq, W, ld_w, Fi, Fo, c0, t);
   // per-column constants; training-mode BatchNorm: merge the statistics slabs dgn_post_forward left in a.stats (slab
   // order -> every CTA gets the same bits), block (0, 0) also updates the running statistics and the [mean | rstd] header
   const bool bn = a.gamma != nullptr, merge = bn && a.training;
   if (merge) {
     const int nsub = (Fi <= LT) ? ((LT / Fi) < 4 ? (LT / Fi) : 4) : 1;   // threads per column (Fi = 64: 2)
-    float* part = hs;                                           // [nsub][3][Fi] scratch (the tile is not built yet)
     for (int c0 = 0; c0 < Fi; c0 += LT) {
       const int col = c0 + t % (Fi < LT ? Fi : LT), sub = (Fi < LT) ? t / Fi : 0;
       float cnt = 0.f, mu = 0.f, m2 = 0.f;
@@ -205,97 +219,100 @@ __global__ void __launch_bounds__(LT) norm_pair_fwd_kernel(const DgnNormArgs a, 
     }
     if (row < a.n_rows && blockIdx.y == 0)
       *reinterpret_cast<float4*>(a.out + (size_t)row * a.ld_o + i) = make_float4(o[0], o[1], o[2], o[3]);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) hs[r * hld + i + j] = o[j];
+    *reinterpret_cast<float4*>(hs + r * hld + i) = make_float4(o[0], o[1], o[2], o[3]);
   }
   cp_async_wait_all();
   __syncthreads();
-  const int tx = t & 15, ty = t >> 4;          // 16 column groups x 8 row groups
-  float ap[4][4] = {}, aq[4][4] = {};
-#pragma unroll 4
-  for (int i = 0; i < Fi; ++i) {
-    const float hr[4] = {hs[(ty * 4 + 0) * hld + i], hs[(ty * 4 + 1) * hld + i], hs[(ty * 4 + 2) * hld + i],
-                         hs[(ty * 4 + 3) * hld + i]};
-    const float4 pv = *reinterpret_cast<const float4*>(wp + i * LC + tx * 4);
-    const float4 qv = *reinterpret_cast<const float4*>(wq + i * LC + tx * 4);
-    const float pw[4] = {pv.x, pv.y, pv.z, pv.w}, qw[4] = {qv.x, qv.y, qv.z, qv.w};
-#pragma unroll
-    for (int a_ = 0; a_ < 4; ++a_)
-#pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        ap[a_][b] = fmaf(hr[a_], pw[b], ap[a_][b]);
-        aq[a_][b] = fmaf(hr[a_], qw[b], aq[a_][b]);
-      }
+  const int tx = t & 7, ty = t >> 3;           // 8 column groups x 16 rows
+  float ap[4] = {}, aq[4] = {};
+  pair_products(hs + ty * hld, wp, wq, Fi, tx, ap, aq);
+  const int r = r0 + ty, c = c0 + tx * 4;
+  if (r < a.n_rows && c < Fo) {
+    *reinterpret_cast<float4*>(P + (size_t)r * ld_p + c) = make_float4(ap[0], ap[1], ap[2], ap[3]);
+    *reinterpret_cast<float4*>(Q + (size_t)r * ld_q + c) = make_float4(aq[0], aq[1], aq[2], aq[3]);
   }
+}
+
+// The backward products read W in its stored orientation (k = output row): the column block W[:, c0 : c0 + LC] of each
+// half goes to shared memory with 16-byte copies.
+__device__ __forceinline__ void stage_w_rows(float* wsr, float* wds, const float* __restrict__ W, int ld_w, int w_vec, int Fi,
+                                             int Fo, int c0, int t) {
+  constexpr int C4 = LC / 4;
+  for (int idx = t; idx < Fo * C4; idx += LT) {
+    const int o = idx / C4, i = (idx - o * C4) * 4;
+    float* d1 = wsr + o * LC + i;
+    float* d2 = wds + o * LC + i;
+    if (c0 + i < Fi) {                          // Fi % 4 == 0: the 4 columns are in or out together
+      const float* s1 = W + (size_t)o * ld_w + c0 + i;
+      const float* s2 = s1 + Fi;
+      if (w_vec) {
+        cp_async16(d1, s1);
+        cp_async16(d2, s2);
+      } else {
 #pragma unroll
-  for (int a_ = 0; a_ < 4; ++a_) {
-    const int r = r0 + ty * 4 + a_, c = c0 + tx * 4;
-    if (r < a.n_rows && c < Fo) {
-      *reinterpret_cast<float4*>(P + (size_t)r * ld_p + c) = make_float4(ap[a_][0], ap[a_][1], ap[a_][2], ap[a_][3]);
-      *reinterpret_cast<float4*>(Q + (size_t)r * ld_q + c) = make_float4(aq[a_][0], aq[a_][1], aq[a_][2], aq[a_][3]);
+        for (int j = 0; j < 4; ++j) { cp_async4(d1 + j, s1 + j); cp_async4(d2 + j, s2 + j); }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { d1[j] = 0.f; d2[j] = 0.f; }
     }
   }
+}
+
+// d_h[r, c0 + tx*4 .. +3] += sum_o dP[r,o] W[o,c] + dQ[r,o] W[o,Fi+c]   (one row, four columns per thread)
+__device__ __forceinline__ void pair_products_bwd(const float* prow, const float* qrow, const float* wsr, const float* wds,
+                                                  int Fo, int tx, float (&acc)[4]) {
+#pragma unroll 8
+  for (int o = 0; o < Fo; ++o) {
+    const float pr = prow[o], qr = qrow[o];
+    const float4 sv = *reinterpret_cast<const float4*>(wsr + o * LC + tx * 4);
+    const float4 dv = *reinterpret_cast<const float4*>(wds + o * LC + tx * 4);
+    acc[0] = fmaf(pr, sv.x, fmaf(qr, dv.x, acc[0]));
+    acc[1] = fmaf(pr, sv.y, fmaf(qr, dv.y, acc[1]));
+    acc[2] = fmaf(pr, sv.z, fmaf(qr, dv.z, acc[2]));
+    acc[3] = fmaf(pr, sv.w, fmaf(qr, dv.w, acc[3]));
+  }
+}
+
+__device__ __forceinline__ void add_row4(float* d_h, int ld_dh, int r, int c, const float (&acc)[4]) {
+  float4* dst = reinterpret_cast<float4*>(d_h + (size_t)r * ld_dh + c);
+  float4 v = *dst;
+  v.x += acc[0]; v.y += acc[1]; v.z += acc[2]; v.w += acc[3];
+  *dst = v;
 }
 
 // d_h[n,i] += sum_o dP[n,o] W[o,i] + dQ[n,o] W[o,Fi+i]
 __global__ void __launch_bounds__(LT) pair_linear_bwd_kernel(int N, int Fi, int Fo, const float* __restrict__ dP, int ld_p,
                                                              const float* __restrict__ dQ, int ld_q,
-                                                             const float* __restrict__ W, int ld_w,
+                                                             const float* __restrict__ W, int ld_w, int w_vec,
                                                              float* __restrict__ d_h, int ld_dh) {
   pdl_prologue();
   extern __shared__ __align__(16) float sm[];
-  float* pt = sm;                              // [Fo][LR]  dP tile, transposed
-  float* qt = pt + Fo * LR;                    // [Fo][LR]  dQ tile, transposed
-  float* ws = qt + Fo * LR;                    // [Fo][LC]  W[:, c0:c0+LC]
-  float* wd = ws + Fo * LC;                    // [Fo][LC]  W[:, Fi+c0 : Fi+c0+LC]
+  const int pld = Fo + TPAD;
+  float* ps = sm;                              // [LR][Fo + 4]  dP tile, row-major
+  float* qs = ps + LR * pld;                   // [LR][Fo + 4]  dQ tile
+  float* wsr = qs + LR * pld;                  // [Fo][LC]      W[:, c0:c0+LC]
+  float* wds = wsr + Fo * LC;                  // [Fo][LC]      W[:, Fi+c0 : Fi+c0+LC]
   const int t = threadIdx.x, r0 = blockIdx.x * LR, c0 = blockIdx.y * LC;
-  for (int idx = t; idx < LR * Fo; idx += LT) {          // conflict-free transposing stores, see the forward
-    const int o = idx / LR, r = idx - o * LR;
+  stage_w_rows(wsr, wds, W, ld_w, w_vec, Fi, Fo, c0, t);
+  const int q4 = Fo / 4;
+  for (int idx = t; idx < LR * q4; idx += LT) {          // dP / dQ rows are 16 B aligned (lin_ok)
+    const int r = idx / q4, o = (idx - r * q4) * 4;
     if (r0 + r < N) {
-      cp_async4(pt + idx, dP + (size_t)(r0 + r) * ld_p + o);
-      cp_async4(qt + idx, dQ + (size_t)(r0 + r) * ld_q + o);
+      cp_async16(ps + r * pld + o, dP + (size_t)(r0 + r) * ld_p + o);
+      cp_async16(qs + r * pld + o, dQ + (size_t)(r0 + r) * ld_q + o);
     } else {
-      pt[idx] = 0.f;
-      qt[idx] = 0.f;
-    }
-  }
-  for (int idx = t; idx < Fo * LC; idx += LT) {
-    const int o = idx / LC, i = idx - o * LC;
-    if (c0 + i < Fi) {
-      cp_async4(ws + idx, W + (size_t)o * ld_w + c0 + i);
-      cp_async4(wd + idx, W + (size_t)o * ld_w + Fi + c0 + i);
-    } else {
-      ws[idx] = 0.f;
-      wd[idx] = 0.f;
+      *reinterpret_cast<float4*>(ps + r * pld + o) = make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(qs + r * pld + o) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
   cp_async_wait_all();
   __syncthreads();
-  const int tx = t & 15, ty = t >> 4;
-  float acc[4][4] = {};
-#pragma unroll 4
-  for (int o = 0; o < Fo; ++o) {
-    const float4 pv = *reinterpret_cast<const float4*>(pt + o * LR + ty * 4);
-    const float4 qv = *reinterpret_cast<const float4*>(qt + o * LR + ty * 4);
-    const float4 sv = *reinterpret_cast<const float4*>(ws + o * LC + tx * 4);
-    const float4 dv = *reinterpret_cast<const float4*>(wd + o * LC + tx * 4);
-    const float pr[4] = {pv.x, pv.y, pv.z, pv.w}, qr[4] = {qv.x, qv.y, qv.z, qv.w};
-    const float sw[4] = {sv.x, sv.y, sv.z, sv.w}, dw[4] = {dv.x, dv.y, dv.z, dv.w};
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-      for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(pr[a], sw[b], fmaf(qr[a], dw[b], acc[a][b]));
-  }
-#pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    const int r = r0 + ty * 4 + a, c = c0 + tx * 4;
-    if (r < N && c < Fi) {
-      float4* dst = reinterpret_cast<float4*>(d_h + (size_t)r * ld_dh + c);
-      float4 v = *dst;
-      v.x += acc[a][0]; v.y += acc[a][1]; v.z += acc[a][2]; v.w += acc[a][3];
-      *dst = v;
-    }
-  }
+  const int tx = t & 7, ty = t >> 3;
+  float acc[4] = {};
+  pair_products_bwd(ps + ty * pld, qs + ty * pld, wsr, wds, Fo, tx, acc);
+  const int r = r0 + ty, c = c0 + tx * 4;
+  if (r < N && c < Fi) add_row4(d_h, ld_dh, r, c, acc);
 }
 
 // pair_linear_bwd with the source-side reduction of the aggregation backward folded in (one launch instead of
@@ -307,32 +324,24 @@ __global__ void __launch_bounds__(LT) pair_gather_bwd_kernel(int N, int Fi, int 
                                                              const int32_t* __restrict__ out_slot,
                                                              const float* __restrict__ ws, int ld_ws,
                                                              const float* __restrict__ dQ, int ld_q,
-                                                             const float* __restrict__ W, int ld_w,
+                                                             const float* __restrict__ W, int ld_w, int w_vec,
                                                              float* __restrict__ d_h, int ld_dh,
                                                              float* __restrict__ dP, int ld_p) {
   pdl_prologue();
   extern __shared__ __align__(16) float sm[];
-  const int pld = Fo + 1;
-  float* ps = sm;                              // [LR][Fo + 1]  gathered dP tile, row-major
-  float* qs = ps + LR * pld;                   // [LR][Fo + 1]  dQ tile
+  const int pld = Fo + TPAD;
+  float* ps = sm;                              // [LR][Fo + 4]  gathered dP tile, row-major
+  float* qs = ps + LR * pld;                   // [LR][Fo + 4]  dQ tile
   float* wsr = qs + LR * pld;                  // [Fo][LC]      W[:, c0:c0+LC]
   float* wds = wsr + Fo * LC;                  // [Fo][LC]      W[:, Fi+c0 : Fi+c0+LC]
   const int t = threadIdx.x, r0 = blockIdx.x * LR, c0 = blockIdx.y * LC;
-  for (int idx = t; idx < Fo * LC; idx += LT) {
-    const int o = idx / LC, i = idx - o * LC;
-    if (c0 + i < Fi) {
-      cp_async4(wsr + idx, W + (size_t)o * ld_w + c0 + i);
-      cp_async4(wds + idx, W + (size_t)o * ld_w + Fi + c0 + i);
-    } else {
-      wsr[idx] = 0.f;
-      wds[idx] = 0.f;
-    }
-  }
+  stage_w_rows(wsr, wds, W, ld_w, w_vec, Fi, Fo, c0, t);
   const int q4 = Fo / 4;
   for (int idx = t; idx < LR * q4; idx += LT) {
     const int r = idx / q4, o = (idx - r * q4) * 4, u = r0 + r;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), qv = acc;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (u < N) {
+      cp_async16(qs + r * pld + o, dQ + (size_t)u * ld_q + o);
       const int j0 = __ldg(out_ptr + u), j1 = __ldg(out_ptr + u + 1);
       for (int j = j0; j < j1; j += 4) {                         // up to 4 edge rows in flight
         float4 v[4];
@@ -344,42 +353,19 @@ __global__ void __launch_bounds__(LT) pair_gather_bwd_kernel(int N, int Fi, int 
 #pragma unroll
         for (int e = 0; e < 4; ++e) { acc.x += v[e].x; acc.y += v[e].y; acc.z += v[e].z; acc.w += v[e].w; }
       }
-      qv = *reinterpret_cast<const float4*>(dQ + (size_t)u * ld_q + o);
       if (blockIdx.y == 0) *reinterpret_cast<float4*>(dP + (size_t)u * ld_p + o) = acc;
+    } else {
+      *reinterpret_cast<float4*>(qs + r * pld + o) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    float* pp = ps + r * pld + o;
-    float* qq = qs + r * pld + o;
-    pp[0] = acc.x; pp[1] = acc.y; pp[2] = acc.z; pp[3] = acc.w;
-    qq[0] = qv.x; qq[1] = qv.y; qq[2] = qv.z; qq[3] = qv.w;
+    *reinterpret_cast<float4*>(ps + r * pld + o) = acc;
   }
   cp_async_wait_all();
   __syncthreads();
-  const int tx = t & 15, ty = t >> 4;
-  float acc[4][4] = {};
-#pragma unroll 4
-  for (int o = 0; o < Fo; ++o) {
-    const float pr[4] = {ps[(ty * 4 + 0) * pld + o], ps[(ty * 4 + 1) * pld + o], ps[(ty * 4 + 2) * pld + o],
-                         ps[(ty * 4 + 3) * pld + o]};
-    const float qr[4] = {qs[(ty * 4 + 0) * pld + o], qs[(ty * 4 + 1) * pld + o], qs[(ty * 4 + 2) * pld + o],
-                         qs[(ty * 4 + 3) * pld + o]};
-    const float4 sv = *reinterpret_cast<const float4*>(wsr + o * LC + tx * 4);
-    const float4 dv = *reinterpret_cast<const float4*>(wds + o * LC + tx * 4);
-    const float sw[4] = {sv.x, sv.y, sv.z, sv.w}, dw[4] = {dv.x, dv.y, dv.z, dv.w};
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-      for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(pr[a], sw[b], fmaf(qr[a], dw[b], acc[a][b]));
-  }
-#pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    const int r = r0 + ty * 4 + a, c = c0 + tx * 4;
-    if (r < N && c < Fi) {
-      float4* dst = reinterpret_cast<float4*>(d_h + (size_t)r * ld_dh + c);
-      float4 v = *dst;
-      v.x += acc[a][0]; v.y += acc[a][1]; v.z += acc[a][2]; v.w += acc[a][3];
-      *dst = v;
-    }
-  }
+  const int tx = t & 7, ty = t >> 3;
+  float acc[4] = {};
+  pair_products_bwd(ps + ty * pld, qs + ty * pld, wsr, wds, Fo, tx, acc);
+  const int r = r0 + ty, c = c0 + tx * 4;
+  if (r < N && c < Fi) add_row4(d_h, ld_dh, r, c, acc);
 }
 
 }  // namespace dgn
@@ -405,9 +391,10 @@ extern "C" int dgn_pair_linear_forward(int32_t N, int32_t Fi, int32_t Fo, const 
   if (N < 0 || !h || !W || !P || !Q) return DGN_ERR_INVALID;
   if (!lin_ok(Fi, Fo, P, Q, ld_p, ld_q)) return DGN_ERR_UNSUPPORTED;
   if (N == 0) return DGN_OK;
-  const size_t smem = (size_t)(Fi * LR + 2 * Fi * LC) * sizeof(float);
+  const size_t smem = (size_t)(LR * (Fi + TPAD) + 2 * Fi * LC) * sizeof(float);
   if (int rc = lin_attr(pair_linear_fwd_kernel, smem)) return rc;
-  launch_pdl(pair_linear_fwd_kernel, dim3((N + LR - 1) / LR, (Fo + LC - 1) / LC), dim3(LT), smem, (cudaStream_t)stream, N, Fi, Fo, h, ld_h, W, ld_w, P, ld_p, Q, ld_q);
+  const int h_vec = (reinterpret_cast<uintptr_t>(h) & 15u) == 0 && ld_h % 4 == 0;
+  launch_pdl(pair_linear_fwd_kernel, dim3((N + LR - 1) / LR, (Fo + LC - 1) / LC), dim3(LT), smem, (cudaStream_t)stream, N, Fi, Fo, h, ld_h, h_vec, W, ld_w, P, ld_p, Q, ld_q);
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { g_dgn_last_cuda = e; return DGN_ERR_CUDA; }
   return DGN_OK;
@@ -425,7 +412,7 @@ extern "C" int dgn_norm_pair_forward(const DgnNormArgs* a, int32_t f_out, const 
     return DGN_ERR_UNSUPPORTED;
   if (a->n_rows == 0) return DGN_OK;
   const int Fi = a->n_cols;
-  const size_t smem = (size_t)(LR * (Fi + HS_LD_PAD) + 2 * Fi * LC + 5 * Fi) * sizeof(float);
+  const size_t smem = (size_t)(LR * (Fi + TPAD) + 2 * Fi * LC + (5 + 12) * Fi) * sizeof(float);
   if (int rc = lin_attr(norm_pair_fwd_kernel, smem)) return rc;
   launch_pdl(norm_pair_fwd_kernel, dim3((a->n_rows + LR - 1) / LR, (f_out + LC - 1) / LC), dim3(LT), smem,
              (cudaStream_t)stream, *a, f_out, w, ld_w, p, ld_p, q, ld_q);
@@ -440,9 +427,12 @@ extern "C" int dgn_pair_linear_backward(int32_t N, int32_t Fi, int32_t Fo, const
   if (N < 0 || !dP || !dQ || !W || !d_h) return DGN_ERR_INVALID;
   if (!lin_ok(Fi, Fo, d_h, d_h, ld_dh, ld_dh)) return DGN_ERR_UNSUPPORTED;
   if (N == 0) return DGN_OK;
-  const size_t smem = (size_t)(2 * Fo * LR + 2 * Fo * LC) * sizeof(float);
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  if (!al(dP) || !al(dQ) || ld_p % 4 || ld_q % 4) return DGN_ERR_UNSUPPORTED;
+  const size_t smem = (size_t)(2 * LR * (Fo + TPAD) + 2 * Fo * LC) * sizeof(float);
   if (int rc = lin_attr(pair_linear_bwd_kernel, smem)) return rc;
-  launch_pdl(pair_linear_bwd_kernel, dim3((N + LR - 1) / LR, (Fi + LC - 1) / LC), dim3(LT), smem, (cudaStream_t)stream, N, Fi, Fo, dP, ld_p, dQ, ld_q, W, ld_w, d_h, ld_dh);
+  const int w_vec = al(W) && ld_w % 4 == 0;
+  launch_pdl(pair_linear_bwd_kernel, dim3((N + LR - 1) / LR, (Fi + LC - 1) / LC), dim3(LT), smem, (cudaStream_t)stream, N, Fi, Fo, dP, ld_p, dQ, ld_q, W, ld_w, w_vec, d_h, ld_dh);
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { g_dgn_last_cuda = e; return DGN_ERR_CUDA; }
   return DGN_OK;
@@ -455,10 +445,11 @@ extern "C" int dgn_pair_gather_backward(int32_t N, int32_t Fi, int32_t Fo, const
   auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
   if (!lin_ok(Fi, Fo, d_h, dP, ld_dh, ld_p) || !al(edge_ws) || !al(dQ) || ld_ws % 4 || ld_q % 4) return DGN_ERR_UNSUPPORTED;
   if (N == 0) return DGN_OK;
-  const size_t smem = (size_t)(2 * LR * (Fo + 1) + 2 * Fo * LC) * sizeof(float);
+  const size_t smem = (size_t)(2 * LR * (Fo + TPAD) + 2 * Fo * LC) * sizeof(float);
   if (int rc = lin_attr(pair_gather_bwd_kernel, smem)) return rc;
+  const int w_vec = al(W) && ld_w % 4 == 0;
   launch_pdl(pair_gather_bwd_kernel, dim3((N + LR - 1) / LR, (Fi + LC - 1) / LC), dim3(LT), smem, (cudaStream_t)stream, N, Fi,
-             Fo, out_ptr, out_slot, edge_ws, ld_ws, dQ, ld_q, W, ld_w, d_h, ld_dh, dP, ld_p);
+             Fo, out_ptr, out_slot, edge_ws, ld_ws, dQ, ld_q, W, ld_w, w_vec, d_h, ld_dh, dP, ld_p);
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { g_dgn_last_cuda = e; return DGN_ERR_CUDA; }
   return DGN_OK;

@@ -574,6 +574,7 @@ class _SideQueue:
 _SIDE = {}
 SIDE_STREAM_ENABLED = False      # only inside step_scope(): plain autograd use stays single-stream
 DIRECT_GRADS = False             # only inside step_scope(): parameter gradients accumulate straight into .grad
+ACTIVE_SCOPE = None              # the step_scope in force (towers.py batches its packing copies per scope)
 
 
 class step_scope:
@@ -585,11 +586,12 @@ class step_scope:
 
     def __init__(self, device, direct_grads=True, side_stream=True):
         self.device, self.direct, self.side = device, direct_grads, side_stream
+        self.tower_state = {}            # towers.py: which packed layers were synchronised / ran in this scope
 
     def __enter__(self):
-        global SIDE_STREAM_ENABLED, DIRECT_GRADS, BN_COUNTERS
-        self._saved = (SIDE_STREAM_ENABLED, DIRECT_GRADS, BN_COUNTERS)
-        SIDE_STREAM_ENABLED, DIRECT_GRADS, BN_COUNTERS = self.side, self.direct, []
+        global SIDE_STREAM_ENABLED, DIRECT_GRADS, BN_COUNTERS, ACTIVE_SCOPE
+        self._saved = (SIDE_STREAM_ENABLED, DIRECT_GRADS, BN_COUNTERS, ACTIVE_SCOPE)
+        SIDE_STREAM_ENABLED, DIRECT_GRADS, BN_COUNTERS, ACTIVE_SCOPE = self.side, self.direct, [], self
         return self
 
     def flush_bn_counters(self):
@@ -599,9 +601,12 @@ class step_scope:
         BN_COUNTERS = []
 
     def __exit__(self, *exc):
-        global SIDE_STREAM_ENABLED, DIRECT_GRADS, BN_COUNTERS
+        global SIDE_STREAM_ENABLED, DIRECT_GRADS, BN_COUNTERS, ACTIVE_SCOPE
         side_join(self.device)
-        SIDE_STREAM_ENABLED, DIRECT_GRADS, BN_COUNTERS = self._saved
+        if self.tower_state and exc[0] is None:
+            from . import towers
+            towers.finish_scope(self)    # packed layers: running statistics and gradients back to the modules (2 launches)
+        SIDE_STREAM_ENABLED, DIRECT_GRADS, BN_COUNTERS, ACTIVE_SCOPE = self._saved
         return False
 
 

@@ -18,6 +18,7 @@ one launch each.  The zero blocks cost ~T x redundant flops in GEMMs that are la
 from __future__ import annotations
 
 import types
+import weakref
 
 import numpy as np
 import torch
@@ -41,16 +42,80 @@ def _launch(table, direction, device):
     ops._count(1)
 
 
+# ---- per-step batching of the packing copies -------------------------------------------------------------------------
+# Inside a step runner's scope (ops.step_scope, i.e. engine.TrainStep) the packing copies of ALL packed layers of the
+# device run as 4 launches per step instead of 5 per layer: [parameters + running statistics -> dense operands] and one
+# multi-tensor zero of the dense gradients when the first packed layer of the step runs, [running statistics back] and
+# [dense gradients += into .grad] when the scope closes.  The merged segment tables are cached per set of layers.
+_LIVE = weakref.WeakSet()
+_MERGED = {}
+_SERIAL = [0]
+
+
+def _merged(kind, fusions):
+    key = (kind,) + tuple((id(f), f._serial) for f in fusions)
+    t = _MERGED.get(key)
+    if t is None:
+        if len(_MERGED) > 64:
+            _MERGED.clear()
+        parts = []
+        for f in fusions:
+            for k in kind.split("+"):
+                tab = getattr(f, k)
+                if tab is not None and tab.numel():
+                    parts.append(tab)
+        t = torch.cat(parts) if parts else False
+        _MERGED[key] = t
+    return t
+
+
+def _sync_in(scope, dev):
+    """First packed layer of the step: refresh the dense operands of every prepared packed layer on `dev`."""
+    st = scope.tower_state
+    live = sorted((f for f in _LIVE if f._key is not None and f._key[0] == str(dev)), key=lambda f: f._order)
+    for f in live:
+        f.prepare(dev)                                            # re-validates the pointers the tables were built for
+    live = [f for f in live if f.t_grads_direct is not None]
+    tab = _merged("t_params+t_running", live)
+    if tab is not False:
+        _launch(tab, 0, dev)
+    if live:
+        torch._foreach_zero_([f.dense_grad for f in live])
+    st["synced"] = {id(f) for f in live}
+    st["fwd"], st["bwd"] = [], []
+
+
+def finish_scope(scope):
+    st, dev = scope.tower_state, scope.device
+    fwd = [f for f in st.get("fwd", []) if f.bn is not None]
+    if fwd:
+        tab = _merged("t_running", fwd)
+        if tab is not False:
+            _launch(tab, 1, dev)                                  # updated running statistics back to the towers
+    if st.get("bwd"):
+        tab = _merged("t_grads_direct", st["bwd"])
+        if tab is not False:
+            _launch(tab, 2, dev)                                  # dense gradients += into the towers' .grad
+    scope.tower_state = {}
+
+
 class _TowerFused(torch.autograd.Function):
     @staticmethod
     def forward(ctx, fusion, g, eig, snorm, training, h, *tower_params):
         f = fusion
         dev = h.device
         f.prepare(dev)
-        _launch(f.t_params, 0, dev)                               # tower parameters -> dense block operands (1 launch)
+        scope = ops.ACTIVE_SCOPE if (ops.ACTIVE_SCOPE is not None and ops.DIRECT_GRADS and training) else None
+        if scope is not None and "synced" not in scope.tower_state:
+            _sync_in(scope, dev)
+        batched = scope is not None and id(f) in scope.tower_state["synced"]
         has_bn = f.bn is not None
-        if has_bn:
-            _launch(f.t_running, 0, dev)                          # running statistics -> concatenated buffers
+        if batched:
+            scope.tower_state["fwd"].append(f)
+        else:
+            _launch(f.t_params, 0, dev)                           # tower parameters -> dense block operands (1 launch)
+            if has_bn:
+                _launch(f.t_running, 0, dev)                      # running statistics -> concatenated buffers
         direct = ops.DIRECT_GRADS and all(p.grad is not None for p in tower_params)
         cfg = LayerConfig(g, f.spec(eig.shape[1]), eig, snorm, f.bn, training, f.relu, f.residual, True, f.F, True,
                           (f.W_pre, f.b_pre, f.W_post, f.b_post, f.gamma if has_bn else None, f.beta if has_bn else None),
@@ -59,18 +124,25 @@ class _TowerFused(torch.autograd.Function):
         out = _FusedLayer.forward(inner, cfg, h, None, f.W_pre, f.b_pre, f.W_post, f.b_post,
                                   f.gamma if has_bn else None, f.beta if has_bn else None)
         if has_bn and training:
-            _launch(f.t_running, 1, dev)                          # updated running statistics back to the towers
+            if not batched:
+                _launch(f.t_running, 1, dev)                      # updated running statistics back to the towers
             for bn in f.tower_bns:
                 ops.count_bn_batch(bn)
         ctx.fusion, ctx.inner, ctx.direct, ctx.n_params = f, inner, direct, len(tower_params)
+        ctx.scope = scope if (batched and direct) else None
         return out
 
     @staticmethod
     def backward(ctx, g_out):
         f, dev = ctx.fusion, g_out.device
-        f.dense_grad.zero_()                                      # the fused layer accumulates into these (direct mode)
+        batched = ctx.scope is not None and ctx.scope is ops.ACTIVE_SCOPE and id(f) in ctx.scope.tower_state.get("synced", ())
+        if not batched:
+            f.dense_grad.zero_()                                  # the fused layer accumulates into these (direct mode)
         res = _FusedLayer.backward(ctx.inner, g_out)
         d_h = res[1]
+        if batched:                                               # scattered with the other layers when the scope closes
+            ctx.scope.tower_state["bwd"].append(f)
+            return (None,) * 5 + (d_h,) + (None,) * ctx.n_params
         side = ops.side_queue(dev)
         if ctx.direct:
             def _scatter():
@@ -98,6 +170,9 @@ class TowerFusion:
         self.relu, self.residual = bool(relu), bool(residual)
         self._key = None
         self._specs = {}
+        self._serial = 0                                           # bumped whenever prepare() rebuilds the tables
+        _SERIAL[0] += 1
+        self._order = _SERIAL[0]
 
     # ---- eligibility -------------------------------------------------------------------------------------------
     def supported(self, h) -> bool:
@@ -233,15 +308,28 @@ class TowerFusion:
         else:
             self.t_running = torch.zeros(0, dtype=torch.uint8, device=dev)
         self._key = key
+        self._serial += 1
+        _LIVE.add(self)
 
     # ---- the layer ------------------------------------------------------------------------------------------------
     def forward(self, g, h, snorm_n):
         t0 = self.convs[0]
         T, N = len(self.convs), h.shape[0]
         if self.Ftp != self.Ft:                                    # zero-pad every tower's column slice (45 -> 48)
-            h = torch.nn.functional.pad(h.reshape(N, T, self.Ft), (0, self.Ftp - self.Ft)).reshape(N, T * self.Ftp)
+            parent = getattr(h, "_dgn_padded", None)
+            if (T == 1 and parent is not None and parent.shape == (N, self.Ftp) and parent.data_ptr() == h.data_ptr()
+                    and parent._version == h._dgn_padded_version):
+                h = parent                                         # the previous padded layer's output: pad columns are 0
+            else:
+                h = torch.nn.functional.pad(h.reshape(N, T, self.Ft), (0, self.Ftp - self.Ft)).reshape(N, T * self.Ftp)
         out = self._forward_padded(g, h, snorm_n)
         if self.Fop != self.Fo_t:
+            if T == 1:
+                # a VIEW of the padded rows (leading dimension Fop): the next padded layer takes the parent as it is
+                # instead of slicing and re-padding (2 copies forward, 2 backward per layer boundary)
+                view = out[:, :self.Fo_t]
+                view._dgn_padded, view._dgn_padded_version = out, out._version
+                return view
             out = out.reshape(N, T, self.Fop)[:, :, :self.Fo_t].reshape(N, T * self.Fo_t)
         return out
 

@@ -89,7 +89,8 @@ def test_unaligned_shapes_fall_back_to_the_library():
     assert float((out.double() - ref).abs().max()) <= 1e-4 * float(ref.abs().max())
 
 
-@pytest.mark.parametrize("N,Fi,Fo,extra", [(3000, 64, 64, 0), (257, 16, 16, 8), (33, 20, 20, 0), (1000, 128, 128, 4), (5, 48, 48, 0)])
+@pytest.mark.parametrize("N,Fi,Fo,extra", [(3000, 64, 64, 0), (257, 16, 16, 8), (33, 20, 20, 0), (1000, 128, 128, 4), (5, 48, 48, 0),
+                                           (300, 32, 64, 3), (70, 36, 20, 1)])
 def test_pair_linear_matches_fp64(N, Fi, Fo, extra):
     """P = h W_src^T, Q = h W_dst^T and d_h += d_P W_src + d_Q W_dst straight from W = [W_src | W_dst | edge cols]."""
     from dgn_b200.ops import pair_linear_backward, pair_linear_forward

@@ -21,13 +21,19 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--workload", default="zinc")
+    ap.add_argument("--hidden", type=int, default=0)
+    ap.add_argument("--aggregators", default="")
     ap.add_argument("--out", default=os.path.join(REPO, "gpurun_out", "step_trace.json"))
     args = ap.parse_args()
     import bench
     from dgn_b200.data.synthetic import make_samples, avg_log_degree
     dev = torch.device("cuda", 0)
     torch.backends.cuda.matmul.allow_tf32 = False
-    w = bench.WORKLOADS[args.workload]
+    w = dict(bench.WORKLOADS[args.workload])
+    if args.hidden:
+        w["hidden"] = args.hidden
+    if args.aggregators:
+        w["aggregators"] = args.aggregators
     avg_log = avg_log_degree(make_samples(w["kind"], 1000 if w["kind"] != "pattern" else 64, seed=12345))
     pools = [make_samples(w["kind"], w["graphs_per_gpu"], seed=0)]
     net, step, host_batches, targets_host, _, _ = bench.build_step(w, pools, avg_log, dev, eager=False)
