@@ -14,8 +14,12 @@ For N>1 the default line also carries a `strong` object (the global-batch-128 fi
 Prints ONE JSON line (rank 0).
 
 * value      device-resident inputs, CUDA-event time of the K steps (L2 flushed between steps), max over ranks
-* e2e        same metric with HOST inputs: per step one H2D copy of the packed batch from pinned memory (the batch is
-             collated on the DEVICE from per-graph fragments inside the timed region) and a D2H read of the loss
+* e2e        same metric with HOST inputs through the public API (TrainStep.load_ids / run_logged): per step one H2D
+             copy of the sampler's index list from pinned memory, the batch is collated on the DEVICE from the
+             HBM-resident dataset fragments inside the timed region, and the loss is copied to pinned host memory; the
+             host reads the loss of step i after queueing step i+1.  Timed like `value` (L2 flush between steps, one
+             event pair per step).  `with_blocking_loss_read_every_step_no_l2_flush` = loss.item() after every step
+             (round-1 method: one event pair around the loop), `with_host_collated_batches` = round-1 input path
 * roofline   the fused aggregation kernels of one layer of the workload as the step runs them (raw aggregates, the
              scalers are folded into the posttrans GEMM), timed alone with CUDA events (CUDA graph of 8 launches over
              rotating operand sets > L2); algorithmic bytes of SURVEY.md 8(d) / DESIGN.md over the measured HBM copy
@@ -30,6 +34,7 @@ from __future__ import annotations
 import argparse
 import importlib.util
 import json
+import math
 import os
 import subprocess
 import sys
@@ -476,7 +481,7 @@ def time_steps(step, host_batches, targets_host, edges, dev, args, barrier, eage
     barrier()
     host_ms = e0.elapsed_time(e1)
     if dataset is None:
-        return step_ms, host_ms, n_edges, launches, h2d, d2h, host_ms
+        return step_ms, host_ms, n_edges, launches, h2d, d2h, host_ms, None
     # end-to-end (b), the headline: the sampler's index list in (pinned host memory -> H2D), the batch is COLLATED ON THE
     # DEVICE from the dataset-resident fragments inside the timed region, loss out
     B = host_batches[0].graph_capacity
@@ -495,7 +500,31 @@ def time_steps(step, host_batches, targets_host, edges, dev, args, barrier, eage
         d2h += 4
     e1.record()
     barrier()
-    return step_ms, e0.elapsed_time(e1), n_edges, launches, h2d, d2h, host_ms
+    sync_ms = e0.elapsed_time(e1)
+    # the same loop with the loss of step i read by the host after step i + 1 has been queued (TrainStep.run_logged: async
+    # 4-byte D2H into a pinned ring): every step still copies its inputs in and its loss out inside the timed region
+    # Timed like `value`: the L2 is flushed between steps and every step has its own event pair around
+    # [index H2D -> collation -> step -> loss D2H]; a host that falls behind shows up as GPU idle time inside the pair.
+    pending, seen, evs = None, 0.0, []
+    for i in range(args.steps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        step.load_ids(dataset, ids[i % POOL])
+        cur = step.run_logged()
+        b.record()
+        evs.append((a, b))
+        if pending is not None:
+            pending[1].synchronize()
+            seen += float(pending[0])
+        pending = cur
+    pending[1].synchronize()
+    seen += float(pending[0])
+    barrier()
+    piped_ms = sum(a.elapsed_time(b) for a, b in evs)
+    if not math.isfinite(seen):
+        raise SystemExit("bench.py: non-finite loss in the e2e leg")
+    return step_ms, sync_ms, n_edges, launches, h2d, d2h, host_ms, piped_ms
 
 
 def run_gpu_arm(args):
@@ -531,17 +560,19 @@ def run_gpu_arm(args):
         pools = make_pools(syn, w, per, rank, world, scaling)
         net, step, host_batches, targets_host, capacity, dataset = build_step(w, pools, avg_log, dev, eager)
         edges = [g.n_real_edges for g in host_batches]
-        step_ms, e2e_ms, n_edges, launches, h2d, d2h, host_ms = time_steps(step, host_batches, targets_host, edges, dev,
-                                                                            args, barrier, eager, dataset)
-        stats = torch.tensor([step_ms, e2e_ms, float(n_edges), host_ms], device=dev, dtype=torch.float64)
+        step_ms, sync_ms, n_edges, launches, h2d, d2h, host_ms, piped_ms = time_steps(
+            step, host_batches, targets_host, edges, dev, args, barrier, eager, dataset)
+        stats = torch.tensor([step_ms, sync_ms, float(n_edges), host_ms, piped_ms or sync_ms], device=dev,
+                             dtype=torch.float64)
         if world > 1:
             mx, sm = stats.clone(), stats.clone()
             dist.all_reduce(mx, op=dist.ReduceOp.MAX)
             dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-            step_ms, e2e_ms, total_edges, host_ms = float(mx[0]), float(mx[1]), float(sm[2]), float(mx[3])
+            step_ms, sync_ms, total_edges, host_ms, e2e_ms = float(mx[0]), float(mx[1]), float(sm[2]), float(mx[3]), float(mx[4])
         else:
-            total_edges = float(n_edges)
+            total_edges, e2e_ms = float(n_edges), float(stats[4])
         return {"value": total_edges / (step_ms * 1e-3) / 1e6, "e2e": total_edges / (e2e_ms * 1e-3) / 1e6,
+                "e2e_sync": total_edges / (sync_ms * 1e-3) / 1e6, "pipelined": piped_ms is not None,
                 "ms_per_step": step_ms / args.steps, "e2e_ms_per_step": e2e_ms / args.steps, "launches": launches,
                 "e2e_host": total_edges / (host_ms * 1e-3) / 1e6, "device_collate": dataset is not None,
                 "h2d": h2d // args.steps, "d2h": d2h // args.steps, "edges_per_step_per_gpu": float(np.mean(edges)),
@@ -619,6 +650,11 @@ def run_gpu_arm(args):
                         "input": ("sampler index list (pinned host) -> H2D -> batch collated on the device from the "
                                   "HBM-resident dataset, inside the timed region" if main["device_collate"] else
                                   "host-collated packed batch (pinned) -> one H2D copy"),
+                        "output": ("every step's loss -> 4-byte D2H into pinned memory; the host reads the loss of step i "
+                                   "after it has queued step i+1 (TrainStep.run_logged); L2 flushed between steps, one "
+                                   "event pair per step around H2D + collation + step + D2H" if main["pipelined"] else
+                                   "loss.item() after every step"),
+                        "with_blocking_loss_read_every_step_no_l2_flush": main["e2e_sync"],
                         "with_host_collated_batches": main["e2e_host"]},
                 "gpu_launches": main["launches"], "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
                 "params": main["params"], "edges_per_step_per_gpu": main["edges_per_step_per_gpu"],

@@ -125,6 +125,22 @@ __global__ void __launch_bounds__(LT) norm_pair_fwd_kernel(const DgnNormArgs a, 
   const int t = threadIdx.x, r0 = blockIdx.x * LR, c0 = blockIdx.y * LC;
   const int n = a.n_rows_dev ? *a.n_rows_dev : a.n_rows;
   stage_w_transposed(wp, wq, W, ld_w, Fi, Fo, c0, t);
+  // this thread's row operands are requested BEFORE the statistics merge (a chain of dependent loads and two barriers)
+  constexpr int kItems = (LR * 32 + LT - 1) / LT;               // Fi <= 128: at most LR * 32 float4 items per tile
+  const int q4 = Fi / 4;
+  float4 yv[kItems], rv[kItems];
+  float sn[kItems];
+#pragma unroll
+  for (int it = 0; it < kItems; ++it) {
+    const int idx = t + it * LT, r = idx / q4, i = (idx - r * q4) * 4, row = r0 + r;
+    yv[it] = rv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+    sn[it] = 1.f;
+    if (idx < LR * q4 && row < n) {
+      yv[it] = *reinterpret_cast<const float4*>(a.y + (size_t)row * a.ld_y + i);
+      if (a.snorm) sn[it] = a.snorm[row];
+      if (a.residual) rv[it] = *reinterpret_cast<const float4*>(a.residual + (size_t)row * a.ld_res + i);
+    }
+  }
   // per-column constants; training-mode BatchNorm: merge the statistics slabs dgn_post_forward left in a.stats (slab
   // order -> every CTA gets the same bits), block (0, 0) also updates the running statistics and the [mean | rstd] header
   const bool bn = a.gamma != nullptr, merge = bn && a.training;
@@ -196,22 +212,18 @@ __global__ void __launch_bounds__(LT) norm_pair_fwd_kernel(const DgnNormArgs a, 
     cst[4 * Fi + i] = a.y_bias ? a.y_bias[i] : 0.f;
   }
   __syncthreads();
-  const int q4 = Fi / 4;
-  for (int idx = t; idx < LR * q4; idx += LT) {
+#pragma unroll
+  for (int it = 0; it < kItems; ++it) {
+    const int idx = t + it * LT;
+    if (idx >= LR * q4) break;
     const int r = idx / q4, i = (idx - r * q4) * 4, row = r0 + r;
     float o[4] = {0.f, 0.f, 0.f, 0.f};
     if (row < n) {
-      const float4 yv = *reinterpret_cast<const float4*>(a.y + (size_t)row * a.ld_y + i);
-      const float sn = a.snorm ? a.snorm[row] : 1.f;
-      const float yy[4] = {yv.x, yv.y, yv.z, yv.w};
-      float rs[4] = {0.f, 0.f, 0.f, 0.f};
-      if (a.residual) {
-        const float4 rv = *reinterpret_cast<const float4*>(a.residual + (size_t)row * a.ld_res + i);
-        rs[0] = rv.x; rs[1] = rv.y; rs[2] = rv.z; rs[3] = rv.w;
-      }
+      const float yy[4] = {yv[it].x, yv[it].y, yv[it].z, yv[it].w};
+      const float rs[4] = {rv[it].x, rv[it].y, rv[it].z, rv[it].w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        float z = (yy[j] + cst[4 * Fi + i + j]) * sn;
+        float z = (yy[j] + cst[4 * Fi + i + j]) * sn[it];
         float v = (z - cst[i + j]) * cst[Fi + i + j] * cst[2 * Fi + i + j] + cst[3 * Fi + i + j];
         if (a.relu) v = fmaxf(v, 0.f);
         o[j] = v + rs[j];
@@ -335,6 +347,10 @@ __global__ void __launch_bounds__(LT) pair_gather_bwd_kernel(int N, int Fi, int 
   float* wsr = qs + LR * pld;                  // [Fo][LC]      W[:, c0:c0+LC]
   float* wds = wsr + Fo * LC;                  // [Fo][LC]      W[:, Fi+c0 : Fi+c0+LC]
   const int t = threadIdx.x, r0 = blockIdx.x * LR, c0 = blockIdx.y * LC;
+  const int tx = t & 7, ty = t >> 3;
+  const int orow = r0 + ty, ocol = c0 + tx * 4;
+  float4 old = make_float4(0.f, 0.f, 0.f, 0.f);                 // d_h is accumulated into: request it first
+  if (orow < N && ocol < Fi) old = *reinterpret_cast<const float4*>(d_h + (size_t)orow * ld_dh + ocol);
   stage_w_rows(wsr, wds, W, ld_w, w_vec, Fi, Fo, c0, t);
   const int q4 = Fo / 4;
   for (int idx = t; idx < LR * q4; idx += LT) {
@@ -361,11 +377,11 @@ __global__ void __launch_bounds__(LT) pair_gather_bwd_kernel(int N, int Fi, int 
   }
   cp_async_wait_all();
   __syncthreads();
-  const int tx = t & 7, ty = t >> 3;
   float acc[4] = {};
   pair_products_bwd(ps + ty * pld, qs + ty * pld, wsr, wds, Fo, tx, acc);
-  const int r = r0 + ty, c = c0 + tx * 4;
-  if (r < N && c < Fi) add_row4(d_h, ld_dh, r, c, acc);
+  if (orow < N && ocol < Fi)
+    *reinterpret_cast<float4*>(d_h + (size_t)orow * ld_dh + ocol) =
+        make_float4(old.x + acc[0], old.y + acc[1], old.z + acc[2], old.w + acc[3]);
 }
 
 }  // namespace dgn

@@ -183,6 +183,21 @@ class TrainStep:
         self.blob.copy_(device_blob, non_blocking=True)
         self.targets.copy_(device_targets, non_blocking=True)
 
+    def run_logged(self):
+        """``run()`` + an asynchronous 4-byte D2H copy of the loss into a pinned ring.  Returns ``(value, event)``:
+        ``value`` is a pinned host scalar that holds the loss once ``event.synchronize()`` returns.  A training loop
+        that reads the loss of step i after it has queued step i + 1 never leaves the GPU waiting for the host
+        (the ring has 4 slots: read a value before 4 more steps are queued)."""
+        import torch as _t
+        if getattr(self, "_ring", None) is None:
+            self._ring = _t.empty(4, dtype=_t.float32).pin_memory()
+            self._ring_ev = [_t.cuda.Event() for _ in range(4)]
+            self._ring_i = 0
+        i = self._ring_i = (self._ring_i + 1) % 4
+        self._ring[i:i + 1].copy_(self.run().reshape(1), non_blocking=True)
+        self._ring_ev[i].record()
+        return self._ring[i], self._ring_ev[i]
+
     def run(self):
         """One training step on the staged batch; returns the loss as a device scalar."""
         if self.cuda_graph is not None:
