@@ -195,6 +195,15 @@ class BatchedGraph:
         """Device pointer to the real node count (None when the batch is not padded)."""
         return self._t["meta"] if (self.padded and self.device.type == "cuda") else None
 
+    def check_overflow(self) -> None:
+        """After a device-side collation (``dgn_collate_device``): raises if the selected graphs did not fit the fixed
+        capacities (the batch was truncated on the device and flagged in ``meta[3]``).  Synchronises - call it lazily,
+        e.g. once per epoch or when a loss looks wrong."""
+        if self.padded and self.device.type == "cuda" and int(self._t["meta"][3].item()) != 0:
+            from ._lib import DgnError
+            raise DgnError("a device-collated batch exceeded the capacity (%d nodes, %d edges, %d graphs)"
+                           % (self._n, self.number_of_edges(), self.graph_capacity))
+
     # ---- DGL-like surface ----------------------------------------------------------------------
     def number_of_nodes(self):
         return self._n

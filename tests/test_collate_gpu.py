@@ -45,6 +45,10 @@ def test_device_collate_equals_host_collate(kind, kw):
     small.bind_device_blob(torch.zeros(small._host_blob.numel(), dtype=torch.uint8, device=DEV))
     ds.collate_into(small, torch.arange(B, dtype=torch.int32, device=DEV), None)
     assert int(small.meta[3]) == 1
+    from dgn_b200._lib import DgnError
+    with pytest.raises(DgnError):
+        small.check_overflow()
+    dev_g.check_overflow()                                       # the batches that fitted are not flagged
 
 
 def test_train_step_from_index_list_equals_host_batches():
