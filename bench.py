@@ -562,6 +562,8 @@ def run_gpu_arm(args):
         edges = [g.n_real_edges for g in host_batches]
         step_ms, sync_ms, n_edges, launches, h2d, d2h, host_ms, piped_ms = time_steps(
             step, host_batches, targets_host, edges, dev, args, barrier, eager, dataset)
+        if getattr(step, "peer", None) is not None and step.peer.timed_out():
+            raise SystemExit("bench.py: a rank did not reach a barrier of dgn_allreduce_adam - results invalid")
         stats = torch.tensor([step_ms, sync_ms, float(n_edges), host_ms, piped_ms or sync_ms], device=dev,
                              dtype=torch.float64)
         if world > 1:

@@ -24,7 +24,7 @@ extern thread_local cudaError_t g_dgn_last_cuda;
 namespace dgn {
 
 constexpr int kArBlocks = DGN_AR_BLOCKS, kArThreads = 1024;
-constexpr long long kSpinLimit = 20000000000ll;                          // ~10 s of SM clocks
+constexpr long long kSpinLimit = 60000000000ll;                          // ~30 s of SM clocks
 
 struct PeerArgs {
   int world, rank;

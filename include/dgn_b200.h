@@ -296,7 +296,7 @@ int dgn_adam_step(int64_t n, float* param, const float* grad, float* exp_avg, fl
  *   flag_ptrs  DEVICE array [world] of uint64: the ranks' signal pads, DGN_AR_FLAG_WORDS(world) uint32 each, zero before
  *              the first launch
  *   epoch      local DEVICE uint32[4], zero before the first launch; [2] becomes 1 if a peer did not reach a barrier
- *              within ~10 s (the step's result is then invalid; the kernel does not hang)
+ *              within ~30 s (the step's result is then invalid; the kernel does not hang)
  * n must be a multiple of 4 floats (the engine pads its flat buffers); other arguments as dgn_adam_step. */
 #define DGN_AR_BLOCKS 148
 #define DGN_AR_MAX_WORLD 8
