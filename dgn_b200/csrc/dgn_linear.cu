@@ -31,54 +31,69 @@ __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// W = [W_src | W_dst] is stored [F_out, 2 F_in]: the forward products need it k-major.  The block W[c0 : c0 + LC, :] is
-// staged TRANSPOSED: element (k, o) of each half at k * LC + (o ^ ((k & 7) << 2)).  A warp copies 8 consecutive k of 4
-// output rows per instruction: the global reads use whole 32-byte sectors (round 1 read one 4-byte word per row and
-// instruction - 32 L1 wavefronts each, most of the kernel's time), and the XOR swizzle spreads the 32 stores over the 32
-// banks.  The swizzle moves whole float4 groups, so the inner loop still reads its 4 output columns with one LDS.128.
-__device__ __forceinline__ void stage_w_transposed(float* wp, float* wq, const float* __restrict__ W, int ld_w, int Fi,
-                                                   int Fo, int c0, int t) {
-  const int kb = (Fi + 7) >> 3;
-  for (int e = t; e < kb * 8 * LC; e += LT) {
-    const int k_lo = e & 7, o_lo = (e >> 3) & 3, rest = e >> 5;
-    const int k = (rest % kb) * 8 + k_lo, o = (rest / kb) * 4 + o_lo;
-    if (k >= Fi) continue;
-    const int pos = k * LC + (o ^ (k_lo << 2));
+// W = [W_src | W_dst] is stored [F_out, 2 F_in (+ edge columns)].  The forward products keep the block
+// W[c0 : c0 + LC, 0 : 2 F_in] in its stored orientation: row o at o * wld, wld = 2 F_in + 4, copied with 16-byte
+// cp.async (8 per thread; round 1 transposed it with 4-byte copies - 64 per thread plus their index arithmetic were
+// most of the kernel's instructions).  A thread owns the output columns tx, tx + 8, tx + 16, tx + 24 and walks k four
+// at a time: one LDS.128 of its h row and one per column and half; wld / 4 is odd, so the 8 column groups of a warp hit
+// 8 different 4-bank groups (conflict free), the 4 rows of a warp broadcast.
+__device__ __forceinline__ void stage_w_block(float* wb, int wld, const float* __restrict__ W, int ld_w, int w_vec, int Fi,
+                                              int Fo, int c0, int t) {
+  const int q4 = (2 * Fi) / 4;
+  for (int idx = t; idx < LC * q4; idx += LT) {
+    const int o = idx / q4, i = (idx - o * q4) * 4;
+    float* dst = wb + o * wld + i;
     if (c0 + o < Fo) {
-      cp_async4(wp + pos, W + (size_t)(c0 + o) * ld_w + k);
-      cp_async4(wq + pos, W + (size_t)(c0 + o) * ld_w + Fi + k);
+      const float* src = W + (size_t)(c0 + o) * ld_w + i;
+      if (w_vec) cp_async16(dst, src);
+      else { cp_async4(dst, src); cp_async4(dst + 1, src + 1); cp_async4(dst + 2, src + 2); cp_async4(dst + 3, src + 3); }
     } else {
-      wp[pos] = 0.f;
-      wq[pos] = 0.f;
+      dst[0] = 0.f; dst[1] = 0.f; dst[2] = 0.f; dst[3] = 0.f;
     }
   }
 }
 
-// both products of one thread: row `hrow` (shared memory, Fi floats) against the staged W halves, columns tx*4 .. +3
-__device__ __forceinline__ void pair_products(const float* hrow, const float* wp, const float* wq, int Fi, int tx,
+// both products of one thread: row `hrow` (shared memory, Fi floats) against the staged W block, columns tx + 8 b.
+// Every accumulator is one fma chain in ascending k, like the reference's GEMM row.
+__device__ __forceinline__ void pair_products(const float* hrow, const float* wb, int wld, int Fi, int tx,
                                               float (&ap)[4], float (&aq)[4]) {
-#pragma unroll 8
-  for (int i = 0; i < Fi; ++i) {
-    const float hv = hrow[i];
-    const int off = i * LC + ((tx * 4) ^ ((i & 7) << 2));
-    const float4 pv = *reinterpret_cast<const float4*>(wp + off);
-    const float4 qv = *reinterpret_cast<const float4*>(wq + off);
-    ap[0] = fmaf(hv, pv.x, ap[0]); ap[1] = fmaf(hv, pv.y, ap[1]); ap[2] = fmaf(hv, pv.z, ap[2]); ap[3] = fmaf(hv, pv.w, ap[3]);
-    aq[0] = fmaf(hv, qv.x, aq[0]); aq[1] = fmaf(hv, qv.y, aq[1]); aq[2] = fmaf(hv, qv.z, aq[2]); aq[3] = fmaf(hv, qv.w, aq[3]);
+#pragma unroll 2
+  for (int i = 0; i < Fi; i += 4) {
+    const float4 hv = *reinterpret_cast<const float4*>(hrow + i);
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const float* wr = wb + (tx + 8 * b) * wld + i;
+      const float4 pv = *reinterpret_cast<const float4*>(wr);
+      const float4 qv = *reinterpret_cast<const float4*>(wr + Fi);
+      ap[b] = fmaf(hv.w, pv.w, fmaf(hv.z, pv.z, fmaf(hv.y, pv.y, fmaf(hv.x, pv.x, ap[b]))));
+      aq[b] = fmaf(hv.w, qv.w, fmaf(hv.z, qv.z, fmaf(hv.y, qv.y, fmaf(hv.x, qv.x, aq[b]))));
+    }
+  }
+}
+
+// rows of P / Q: this thread's four columns are 8 apart
+__device__ __forceinline__ void store_pq(float* __restrict__ P, int ld_p, float* __restrict__ Q, int ld_q, int r, int c0,
+                                         int tx, int Fo, const float (&ap)[4], const float (&aq)[4]) {
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    const int c = c0 + tx + 8 * b;
+    if (c < Fo) {
+      P[(size_t)r * ld_p + c] = ap[b];
+      Q[(size_t)r * ld_q + c] = aq[b];
+    }
   }
 }
 
 // P[n,o] = sum_i h[n,i] W[o,i] ;  Q[n,o] = sum_i h[n,i] W[o,Fi+i]
 __global__ void __launch_bounds__(LT) pair_linear_fwd_kernel(int N, int Fi, int Fo, const float* __restrict__ h, int ld_h,
                                                              int h_vec, const float* __restrict__ W, int ld_w,
-                                                             float* __restrict__ P, int ld_p, float* __restrict__ Q,
-                                                             int ld_q) {
+                                                             int w_vec, float* __restrict__ P, int ld_p,
+                                                             float* __restrict__ Q, int ld_q) {
   pdl_prologue();
   extern __shared__ __align__(16) float sm[];
-  const int hld = Fi + TPAD;
-  float* hs = sm;                              // [LR][Fi + 4]  h tile, row-major
-  float* wp = hs + LR * hld;                   // [Fi][LC]      W_src block, transposed + swizzled
-  float* wq = wp + Fi * LC;                    // [Fi][LC]      W_dst block
+  const int hld = Fi + TPAD, wld = 2 * Fi + TPAD;
+  float* hs = sm;                              // [LR][Fi + 4]    h tile, row-major
+  float* wb = hs + LR * hld;                   // [LC][2 Fi + 4]  W block, rows = output columns
   const int t = threadIdx.x, r0 = blockIdx.x * LR, c0 = blockIdx.y * LC;
   const int q4 = Fi / 4;
   for (int idx = t; idx < LR * q4; idx += LT) {
@@ -92,17 +107,13 @@ __global__ void __launch_bounds__(LT) pair_linear_fwd_kernel(int N, int Fi, int 
       dst[0] = 0.f; dst[1] = 0.f; dst[2] = 0.f; dst[3] = 0.f;
     }
   }
-  stage_w_transposed(wp, wq, W, ld_w, Fi, Fo, c0, t);
+  stage_w_block(wb, wld, W, ld_w, w_vec, Fi, Fo, c0, t);
   cp_async_wait_all();
   __syncthreads();
   const int tx = t & 7, ty = t >> 3;           // 8 column groups x 16 rows
   float ap[4] = {}, aq[4] = {};
-  pair_products(hs + ty * hld, wp, wq, Fi, tx, ap, aq);
-  const int r = r0 + ty, c = c0 + tx * 4;
-  if (r < N && c < Fo) {                        // Fo % 4 == 0: the 4 columns are in or out together
-    *reinterpret_cast<float4*>(P + (size_t)r * ld_p + c) = make_float4(ap[0], ap[1], ap[2], ap[3]);
-    *reinterpret_cast<float4*>(Q + (size_t)r * ld_q + c) = make_float4(aq[0], aq[1], aq[2], aq[3]);
-  }
+  pair_products(hs + ty * hld, wb, wld, Fi, tx, ap, aq);
+  if (r0 + ty < N) store_pq(P, ld_p, Q, ld_q, r0 + ty, c0, tx, Fo, ap, aq);
 }
 
 // Layer epilogue of layer l fused with the node-level pretrans halves of layer l+1 (one launch instead of
@@ -112,19 +123,18 @@ __global__ void __launch_bounds__(LT) pair_linear_fwd_kernel(int N, int Fi, int 
 // The row tile is produced with coalesced 128-bit accesses (16 threads per row), written to `out` and kept in shared
 // memory for the two products.
 __global__ void __launch_bounds__(LT) norm_pair_fwd_kernel(const DgnNormArgs a, int Fo, const float* __restrict__ W, int ld_w,
-                                                           float* __restrict__ P, int ld_p, float* __restrict__ Q,
-                                                           int ld_q) {
+                                                           int w_vec, float* __restrict__ P, int ld_p,
+                                                           float* __restrict__ Q, int ld_q) {
   pdl_prologue();
   extern __shared__ __align__(16) float sm[];
-  const int Fi = a.n_cols, hld = Fi + TPAD;
-  float* hs = sm;                              // [LR][Fi + 4]  epilogue output tile, row-major
-  float* wp = hs + LR * hld;                   // [Fi][LC]      W_src block, transposed + swizzled
-  float* wq = wp + Fi * LC;                    // [Fi][LC]      W_dst block
-  float* cst = wq + Fi * LC;                   // [5][Fi]       mean, rstd, gamma, beta, bias
-  float* part = cst + 5 * Fi;                  // [4][3][Fi]    statistics merge scratch
+  const int Fi = a.n_cols, hld = Fi + TPAD, wld = 2 * Fi + TPAD;
+  float* hs = sm;                              // [LR][Fi + 4]    epilogue output tile, row-major
+  float* wb = hs + LR * hld;                   // [LC][2 Fi + 4]  W block, rows = output columns
+  float* cst = wb + LC * wld;                  // [5][Fi]         mean, rstd, gamma, beta, bias
+  float* part = cst + 5 * Fi;                  // [4][3][Fi]      statistics merge scratch
   const int t = threadIdx.x, r0 = blockIdx.x * LR, c0 = blockIdx.y * LC;
   const int n = a.n_rows_dev ? *a.n_rows_dev : a.n_rows;
-  stage_w_transposed(wp, wq, W, ld_w, Fi, Fo, c0, t);
+  stage_w_block(wb, wld, W, ld_w, w_vec, Fi, Fo, c0, t);
   // this thread's row operands are requested BEFORE the statistics merge (a chain of dependent loads and two barriers)
   constexpr int kItems = (LR * 32 + LT - 1) / LT;               // Fi <= 128: at most LR * 32 float4 items per tile
   const int q4 = Fi / 4;
@@ -237,12 +247,8 @@ __global__ void __launch_bounds__(LT) norm_pair_fwd_kernel(const DgnNormArgs a, 
   __syncthreads();
   const int tx = t & 7, ty = t >> 3;           // 8 column groups x 16 rows
   float ap[4] = {}, aq[4] = {};
-  pair_products(hs + ty * hld, wp, wq, Fi, tx, ap, aq);
-  const int r = r0 + ty, c = c0 + tx * 4;
-  if (r < a.n_rows && c < Fo) {
-    *reinterpret_cast<float4*>(P + (size_t)r * ld_p + c) = make_float4(ap[0], ap[1], ap[2], ap[3]);
-    *reinterpret_cast<float4*>(Q + (size_t)r * ld_q + c) = make_float4(aq[0], aq[1], aq[2], aq[3]);
-  }
+  pair_products(hs + ty * hld, wb, wld, Fi, tx, ap, aq);
+  if (r0 + ty < a.n_rows) store_pq(P, ld_p, Q, ld_q, r0 + ty, c0, tx, Fo, ap, aq);
 }
 
 // The backward products read W in its stored orientation (k = output row): the column block W[:, c0 : c0 + LC] of each
@@ -407,10 +413,11 @@ extern "C" int dgn_pair_linear_forward(int32_t N, int32_t Fi, int32_t Fo, const 
   if (N < 0 || !h || !W || !P || !Q) return DGN_ERR_INVALID;
   if (!lin_ok(Fi, Fo, P, Q, ld_p, ld_q)) return DGN_ERR_UNSUPPORTED;
   if (N == 0) return DGN_OK;
-  const size_t smem = (size_t)(LR * (Fi + TPAD) + 2 * Fi * LC) * sizeof(float);
+  const size_t smem = (size_t)(LR * (Fi + TPAD) + LC * (2 * Fi + TPAD)) * sizeof(float);
   if (int rc = lin_attr(pair_linear_fwd_kernel, smem)) return rc;
   const int h_vec = (reinterpret_cast<uintptr_t>(h) & 15u) == 0 && ld_h % 4 == 0;
-  launch_pdl(pair_linear_fwd_kernel, dim3((N + LR - 1) / LR, (Fo + LC - 1) / LC), dim3(LT), smem, (cudaStream_t)stream, N, Fi, Fo, h, ld_h, h_vec, W, ld_w, P, ld_p, Q, ld_q);
+  const int w_vec = (reinterpret_cast<uintptr_t>(W) & 15u) == 0 && ld_w % 4 == 0;
+  launch_pdl(pair_linear_fwd_kernel, dim3((N + LR - 1) / LR, (Fo + LC - 1) / LC), dim3(LT), smem, (cudaStream_t)stream, N, Fi, Fo, h, ld_h, h_vec, W, ld_w, w_vec, P, ld_p, Q, ld_q);
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { g_dgn_last_cuda = e; return DGN_ERR_CUDA; }
   return DGN_OK;
@@ -428,10 +435,11 @@ extern "C" int dgn_norm_pair_forward(const DgnNormArgs* a, int32_t f_out, const 
     return DGN_ERR_UNSUPPORTED;
   if (a->n_rows == 0) return DGN_OK;
   const int Fi = a->n_cols;
-  const size_t smem = (size_t)(LR * (Fi + TPAD) + 2 * Fi * LC + (5 + 12) * Fi) * sizeof(float);
+  const size_t smem = (size_t)(LR * (Fi + TPAD) + LC * (2 * Fi + TPAD) + (5 + 12) * Fi) * sizeof(float);
   if (int rc = lin_attr(norm_pair_fwd_kernel, smem)) return rc;
+  const int w_vec = al(w) && ld_w % 4 == 0;
   launch_pdl(norm_pair_fwd_kernel, dim3((a->n_rows + LR - 1) / LR, (f_out + LC - 1) / LC), dim3(LT), smem,
-             (cudaStream_t)stream, *a, f_out, w, ld_w, p, ld_p, q, ld_q);
+             (cudaStream_t)stream, *a, f_out, w, ld_w, w_vec, p, ld_p, q, ld_q);
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { g_dgn_last_cuda = e; return DGN_ERR_CUDA; }
   return DGN_OK;
