@@ -15,6 +15,7 @@
 // Every rank sees bit-identical sums, so the replicas never drift.  Traffic per rank: 2 (world-1)/world of the buffer.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/dgn_b200.h"
 #include "dgn_launch.cuh"
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(kArThreads) allreduce_adam_kernel(const __grid
   const unsigned epoch = k.epoch[0] + 1u;
   const int W = k.world;
   const long long n4 = k.n / 4;
-  const long long tid = (long long)blockIdx.x * kArThreads + threadIdx.x, stride = (long long)kArBlocks * kArThreads;
+  const long long tid = (long long)blockIdx.x * kArThreads + threadIdx.x, stride = (long long)gridDim.x * kArThreads;
   AdamCoef c;
   {
     float lr = k.lr;
@@ -164,10 +165,16 @@ extern "C" int dgn_allreduce_adam(const DgnPeerGroup* pg, int64_t n, float* para
   k.n = n; k.p = param; k.m = exp_avg; k.v = exp_avg_sq;
   k.lr = lr; k.b1 = beta1; k.b2 = beta2; k.eps = eps; k.wd = weight_decay; k.hyper = hyper; k.state = state;
   k.reduced = pg->reduced;
+  // Every CTA takes part in every barrier (world - 1 remote flag stores each): the grid is sized by the data, ~4 float4
+  // per thread, not by the SM count.  All ranks derive the same grid from n (DGN_AR_GRID overrides, for tuning).
+  static const int force_grid = [] { const char* e = getenv("DGN_AR_GRID"); return e ? atoi(e) : 0; }();
+  long long want = (n / 4 + 4LL * kArThreads - 1) / (4LL * kArThreads);
+  if (force_grid > 0) want = force_grid;
+  const unsigned grid = (unsigned)(want < 8 ? 8 : (want > kArBlocks ? kArBlocks : want));
   if (pg->world <= pg->one_shot_max_world)
-    launch_pdl(allreduce_adam_kernel<true>, dim3(kArBlocks), dim3(kArThreads), 0, (cudaStream_t)stream, k);
+    launch_pdl(allreduce_adam_kernel<true>, dim3(grid), dim3(kArThreads), 0, (cudaStream_t)stream, k);
   else
-    launch_pdl(allreduce_adam_kernel<false>, dim3(kArBlocks), dim3(kArThreads), 0, (cudaStream_t)stream, k);
+    launch_pdl(allreduce_adam_kernel<false>, dim3(grid), dim3(kArThreads), 0, (cudaStream_t)stream, k);
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { g_dgn_last_cuda = e; return DGN_ERR_CUDA; }
   return DGN_OK;

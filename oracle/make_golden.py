@@ -189,6 +189,46 @@ def mol_net_case(kind, samples, avg_log, seed, **over):
     return out
 
 
+def class_net_case(kind, samples, avg_log, seed, **over):
+    """SBM (node classification, class-balanced CE) / superpixel (graph classification) DGNNet of the unmodified
+    reference - scores, loss, all parameter gradients."""
+    from oracle.graphs import collate_standin
+    if kind == "sbm":
+        from nets.SBMs_node_classification.dgn_net import DGNNet
+    else:
+        from nets.superpixels_graph_classification.dgn_net import DGNNet
+    g, labels, snorm_n, snorm_e = collate_standin(samples)
+    x, e = g.ndata["feat"], g.edata["feat"]
+    params = dict(hidden_dim=16, out_dim=16, in_feat_dropout=0.0, dropout=0.0, L=3, type_net="complex", pos_enc_dim=0,
+                  readout="mean", graph_norm=True, batch_norm=True, aggregators="mean dir1-dx dir2-dx",
+                  scalers=SCALERS3, avg_d={"log": torch.tensor(avg_log, dtype=torch.float32)}, residual=True,
+                  edge_feat=False, edge_dim=0, pretrans_layers=1, posttrans_layers=1, device="cpu")
+    if kind == "sbm":
+        params.update(in_dim=3, n_classes=2)
+    else:
+        params.update(in_dim=int(x.shape[1]), in_dim_edge=1, n_classes=10)
+    params.update(over)
+    torch.manual_seed(seed)
+    net = DGNNet(params)
+    net.train()
+    scores = net.forward(g, x, e, snorm_n, snorm_e)
+    targets = labels.long()
+    loss = net.loss(scores, targets)
+    loss.backward()
+    out = {"node_feat": _np(x), "edge_feat": _np(e), "targets": _np(targets), "scores": _np(scores), "loss": _np(loss),
+           "snorm_n": _np(snorm_n), "eig": _np(g.ndata["eig"]), "avg_log": np.float32(avg_log),
+           "src": _np(g.edges()[0]).astype(np.int32), "dst": _np(g.edges()[1]).astype(np.int32),
+           "batch_num_nodes": np.array(g.batch_num_nodes, dtype=np.int64), "seed": np.int64(seed),
+           "kind": np.array(kind)}
+    for k, v in params.items():
+        if isinstance(v, (int, float, bool, str)):
+            out["p/" + k] = np.array(v)
+    out.update(_flat_state(net))
+    for k, p in net.named_parameters():
+        out["grad/" + k] = _np(p.grad) if p.grad is not None else np.zeros(tuple(p.shape), np.float32)
+    return out
+
+
 def main(only_new=False):
     sys.path.insert(0, REPO)
     from dgn_b200.data.synthetic import make_samples, avg_log_degree
@@ -236,6 +276,16 @@ def main(only_new=False):
         "net_zinc_directional": net_case(DGNNet, zinc, avg_z, 45, "simple", "mean dir1-dx dir1-av", readout="directional"),
         "net_zinc_directional_abs": net_case(DGNNet, zinc, avg_z, 46, "complex", "mean max dir2-dx",
                                              readout="directional_abs"),
+    })
+    # the node-classification (SBM PATTERN, BASELINE configs[4]) and superpixel (CIFAR10, configs[2]) nets
+    pat = make_samples("pattern", 3, seed=31, n_min=20, n_max=30)
+    cif = make_samples("cifar", 4, seed=32, n_min=20, n_max=30)
+    cases.update({
+        "net_sbm_pattern": class_net_case("sbm", pat, avg_log_degree(pat), 47, aggregators="mean dir1-dx dir2-dx dir3-dx"),
+        "net_superpixel_cifar": class_net_case("superpixel", cif, avg_log_degree(cif), 48, hidden_dim=20, out_dim=20,
+                                               scalers="identity", readout="mean"),
+        "net_superpixel_simple_max": class_net_case("superpixel", cif, avg_log_degree(cif), 49, type_net="simple",
+                                                    aggregators="mean max dir1-av", readout="max"),
     })
     for name, payload in cases.items():
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **payload)

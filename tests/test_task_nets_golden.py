@@ -9,6 +9,7 @@ from tests.helpers import assert_close, load_golden, samples_from_golden
 
 MOL_CASES = ["net_hiv_towers", "net_hiv_edge", "net_pcba_vn", "net_pcba_logsum"]
 DIR_CASES = ["net_zinc_directional", "net_zinc_directional_abs"]
+CLASS_CASES = ["net_sbm_pattern", "net_superpixel_cifar", "net_superpixel_simple_max"]   # BASELINE configs[4] / configs[2] nets
 
 
 def _mol_params(gold, device):
@@ -77,7 +78,44 @@ def test_oracle_directional_readout_matches_reference(case):
     _check(net, scores, loss, gold)
 
 
+@pytest.mark.parametrize("case", CLASS_CASES)
+def test_oracle_classification_net_matches_reference(case):
+    """SBM node classification (class-balanced cross-entropy, rb/nets/SBMs_node_classification/dgn_net.py:66-81) and
+    superpixel graph classification (rb/nets/superpixels_graph_classification/dgn_net.py)."""
+    from oracle.graphs import collate_standin
+    from oracle.task_nets import PatternNet, SuperpixelNet
+    gold = load_golden(case)
+    samples = samples_from_golden(gold)
+    g, _, snorm_n, snorm_e = collate_standin(samples)
+    torch.manual_seed(int(gold["seed"]))
+    net = (PatternNet if str(gold["kind"]) == "sbm" else SuperpixelNet)(_mol_params(gold, "cpu")).train()
+    _load_params(net, gold)
+    scores = net(g, g.ndata["feat"], g.edata["feat"], snorm_n, snorm_e)
+    loss = net.loss(scores, torch.tensor(gold["targets"]))
+    loss.backward()
+    _check(net, scores, loss, gold)
+
+
 # ---------------------------------------------------------------------------------------------- GPU: product path
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", CLASS_CASES)
+def test_cuda_classification_net_matches_reference(case):
+    from dgn_b200.graph import collate
+    from dgn_b200.task_nets.SBMs_node_classification import DGNNet as SbmNet
+    from dgn_b200.task_nets.superpixels_graph_classification import DGNNet as SpNet
+    gold = load_golden(case)
+    g, _ = collate(samples_from_golden(gold))
+    g.to("cuda")
+    net = (SbmNet if str(gold["kind"]) == "sbm" else SpNet)(_mol_params(gold, "cuda"))
+    _load_params(net, gold)
+    net.to("cuda").train()
+    scores = net(g, g.ndata["feat"], g.edata["feat"], g.snorm_n, None)
+    loss = net.loss(scores, torch.tensor(gold["targets"], device="cuda"))
+    loss.backward()
+    _check(net, scores, loss, gold)
+
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("case", MOL_CASES)
 def test_cuda_mol_net_matches_reference(case):

@@ -37,6 +37,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--numel", type=int, default=546304)
     ap.add_argument("--iters", type=int, default=300)
+    ap.add_argument("--tag", default="")
     args = ap.parse_args()
     local = int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -45,7 +46,8 @@ def main():
     from dgn_b200.engine import FlatAdam
     from dgn_b200.parallel import PeerGradients, allreduce_sum_
     world = dist.get_world_size()
-    out = {"numel": args.numel, "world": world, "unit": "us per exchange+update"}
+    out = {"numel": args.numel, "world": world, "unit": "us per exchange+update", "grid": os.environ.get("DGN_AR_GRID", "auto"),
+           "tag": args.tag}
     for name, env in (("peer_one_shot", str(world)), ("peer_two_shot", "0")):
         os.environ["DGN_AR_ONESHOT_MAX_WORLD"] = env
         peer = PeerGradients(args.numel, dev)
