@@ -165,12 +165,12 @@ extern "C" int dgn_allreduce_adam(const DgnPeerGroup* pg, int64_t n, float* para
   k.n = n; k.p = param; k.m = exp_avg; k.v = exp_avg_sq;
   k.lr = lr; k.b1 = beta1; k.b2 = beta2; k.eps = eps; k.wd = weight_decay; k.hyper = hyper; k.state = state;
   k.reduced = pg->reduced;
-  // Every CTA takes part in every barrier (world - 1 remote flag stores each): the grid is sized by the data, ~4 float4
-  // per thread, not by the SM count.  All ranks derive the same grid from n (DGN_AR_GRID overrides, for tuning).
+  // One CTA per SM.  Measured at N = 2 (tools/peer_bench.py, DGN_AR_GRID sweep): 148 CTAs 19.7 us, 64: 24.3, 34: 28.7,
+  // 16: 42.9 - the kernel is bound by each thread's serial remote-load latency, not by the per-CTA barrier traffic, so
+  // fewer CTAs (fewer flag stores, more iterations per thread) lose.  All ranks must use the same grid.
   static const int force_grid = [] { const char* e = getenv("DGN_AR_GRID"); return e ? atoi(e) : 0; }();
-  long long want = (n / 4 + 4LL * kArThreads - 1) / (4LL * kArThreads);
-  if (force_grid > 0) want = force_grid;
-  const unsigned grid = (unsigned)(want < 8 ? 8 : (want > kArBlocks ? kArBlocks : want));
+  const int want = force_grid > 0 ? force_grid : kArBlocks;
+  const unsigned grid = (unsigned)(want < 1 ? 1 : (want > kArBlocks ? kArBlocks : want));
   if (pg->world <= pg->one_shot_max_world)
     launch_pdl(allreduce_adam_kernel<true>, dim3(grid), dim3(kArThreads), 0, (cudaStream_t)stream, k);
   else
