@@ -22,10 +22,12 @@
 
 #include "../../include/dgn_b200.h"
 #include "dgn_launch.cuh"
+#include "dgn_umma.cuh"                            // mbarrier / tcgen05 / descriptor wrappers, 3xTF32 split (shared with dgn_post.cu)
 
 namespace dgn {
+using namespace umma;
 
-constexpr int BM = 128, BN = 64, BK = 32;          // tile (BK floats = one 128 B swizzle row)
+constexpr int BM = 128, BN = 64;                   // output tile; BK = 32 floats of K (one 128 B swizzle row) from dgn_umma.cuh
 constexpr int kStages = 2;                         // 96 KB per CTA -> two CTAs per SM hide each other's load latency
 constexpr int kLoaderThreads = 128;
 constexpr int kGemmThreads = 160;                   // 4 loader/epilogue warps + 1 MMA warp
@@ -33,48 +35,9 @@ constexpr int A_TILE = BM * BK * 4, B_TILE = BN * BK * 4;                 // byt
 constexpr int STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;                      // hi + lo of both operands
 constexpr int GEMM_SMEM = kStages * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
-__device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mb_init(uint64_t* b, int n) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(b)), "r"(n)); }
-__device__ __forceinline__ void mb_arrive(uint64_t* b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(b)) : "memory"); }
-__device__ __forceinline__ void mb_wait(uint64_t* b, uint32_t parity) {
-  uint32_t ok = 0;
-  while (!ok) {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(s32(b)), "r"(parity) : "memory");
-  }
-}
-
-// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address, leading / stride byte offsets
-// (all >> 4), version 1 (Blackwell) at bit 46, layout type at bits 61..63:
-//   2 = SWIZZLE_128B          K-major tf32 operands   (8 rows x 128 B atoms, 16 B chunks XOR row)
-//   1 = SWIZZLE_128B_BASE32B  MN-major tf32 operands  (4 rows x 128 B atoms, 32 B chunks XOR row) - the only
-//                             MN-major layout the tensor core accepts for 32-bit inputs
-constexpr uint32_t kLayoutSW128 = 2, kLayoutSW128Base32 = 1;
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
-  uint64_t d = 0;
-  d |= (uint64_t)((addr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)layout << 61;
-  return d;
-}
-
-// instruction descriptor (cute::UMMA::InstrDescriptor) for kind::tf32, fp32 accumulate, M x N = 128 x 64
+// instruction descriptor for kind::tf32, fp32 accumulate, M x N = 128 x 64
 __host__ __device__ constexpr uint32_t instr_desc(bool a_mn_major, bool b_mn_major) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
-         ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-}
-
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(bar)) : "memory");
+  return instr_desc_tf32(BM, BN, a_mn_major, b_mn_major);
 }
 
 struct GemmArgs {
@@ -85,25 +48,6 @@ struct GemmArgs {
   int accumulate, c_transposed, splits, kb_per_split;
   float* ws; unsigned* counters;
 };
-
-// byte offset of element chunk (row r, 16-byte chunk ch of the 128-byte row) inside a swizzled atom stack
-__device__ __forceinline__ uint32_t sw128(uint32_t row_in_atom, uint32_t ch) { return row_in_atom * 128u + ((ch ^ row_in_atom) << 4); }
-
-// round-to-nearest TF32 (the tensor core itself just ignores the low 13 mantissa bits, so pre-rounded values are
-// consumed exactly): |a - hi| <= 2^-12 |a|, and the residual is rounded once more, leaving ~2^-23 |a| unaccounted
-// (integer add + mask = round-half-away in magnitude; the cvt.rna.tf32.f32 instruction does the same but runs on a
-//  low-throughput conversion pipe and made the loader warps the bottleneck of the whole kernel)
-__device__ __forceinline__ float rn_tf32(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
-
-__device__ __forceinline__ void split_store(unsigned char* hi_tile, unsigned char* lo_tile, uint32_t off, float4 v) {
-  float4 h, l;
-  h.x = rn_tf32(v.x); l.x = rn_tf32(v.x - h.x);
-  h.y = rn_tf32(v.y); l.y = rn_tf32(v.y - h.y);
-  h.z = rn_tf32(v.z); l.z = rn_tf32(v.z - h.z);
-  h.w = rn_tf32(v.w); l.w = rn_tf32(v.w - h.w);
-  *reinterpret_cast<float4*>(hi_tile + off) = h;
-  *reinterpret_cast<float4*>(lo_tile + off) = l;
-}
 
 // One operand tile: ROWS (M or N extent) x BK, K-major source [ROWS][K] or MN-major source [K][ROWS].
 // fetch_tile issues the global loads into registers (the next k-block is fetched before the current one is
