@@ -230,12 +230,21 @@ def run_reference_arm(args):
         print(json.dumps(r), flush=True)
         return
     r = cpu_reference_time(w, args.steps, args.warmup, budget_s=150.0)
+    # hygiene: this arm must not have touched the product - neither the package nor its library
+    assert not any(m == "dgn_b200" or m.startswith("dgn_b200.") for m in sys.modules), "reference arm imported dgn_b200"
+    try:
+        assert "libdgn_b200" not in open("/proc/self/maps").read(), "reference arm mapped libdgn_b200.so"
+    except OSError:
+        pass
     line = {"impl": "reference", "metric": w["metric"], "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": r["steps_done"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(w, args.workload, 1, "weak"),
+            # the SAME config dict as the GPU arm prints for these flags; a CPU step is a bounded sample of it: one
+            # rank's shard (the metric, edges / s, does not depend on how many shards are timed)
+            "config": workload_config(w, args.workload, max(args.gpus, 1), args.scaling),
             "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
-                             "sample": cpu_sample_text(w, r)},
+                             "sample": cpu_sample_text(w, r) + ("" if args.gpus <= 1 else
+                                                                "; one rank's shard of the %d-GPU workload per step" % args.gpus)},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
