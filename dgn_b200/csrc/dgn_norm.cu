@@ -128,12 +128,7 @@ __global__ void __launch_bounds__(kTX * kTY) norm_apply_kernel(const DgnNormArgs
   const int col = blockIdx.y * kTX + threadIdx.x;
   __shared__ float s_mean[kTX], s_rstd[kTX];
   __shared__ float s_cnt[kTY][kTX], s_mu[kTY][kTX], s_m2[kTY][kTX];
-  if (a.gamma && a.training && a.stat_parts < 0) {                              // header finalised by the producer
-    if (threadIdx.y == 0 && col < a.n_cols) {
-      s_mean[threadIdx.x] = a.stats[col];
-      s_rstd[threadIdx.x] = a.stats[a.n_cols + col];
-    }
-  } else if (a.gamma) {
+  if (a.gamma) {
     float mean = 0.f, var = 1.f;
     if (a.training) merged_stats(a, n, col, s_cnt, s_mu, s_m2, mean, var);     // all threads (has a barrier)
     if (threadIdx.y == 0 && col < a.n_cols) {
@@ -473,7 +468,7 @@ static dim3 norm_grid_apply(const DgnNormArgs* a) {
 }
 
 extern "C" int dgn_norm_forward(const DgnNormArgs* a, void* stream) {
-  if (!a || !a->y || !a->out || a->n_rows < 0 || a->n_cols <= 0) return DGN_ERR_INVALID;
+  if (!a || !a->y || !a->out || a->n_rows < 0 || a->n_cols <= 0 || a->stat_parts < 0) return DGN_ERR_INVALID;
   if (a->gamma && (!a->beta || !a->stats)) return DGN_ERR_INVALID;
   if (a->gamma && !a->training && (!a->running_mean || !a->running_var)) return DGN_ERR_INVALID;
   if (a->n_rows == 0) return DGN_OK;
